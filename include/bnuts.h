@@ -1,0 +1,161 @@
+/* bnuts.h — C ABI of the B200 batched-chain NUTS engine (libbnuts.so).
+ *
+ * Drop-in boundary for the hot path of chriselrod/InplaceDHMC.jl.  The reference
+ * has no FFI: its seam is Julia dispatch.  Each entry point below names the
+ * reference call it replaces (paths relative to the reference checkout).  A Julia
+ * host binds these with `ccall` (see INTEGRATION.md and julia/BNuts.jl).
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative bnuts_status; the message
+ *    is available from bnuts_last_error(); nothing throws or aborts across the ABI
+ *  - host buffers are caller-owned, plain pointers + strides, always Float64 /
+ *    Int32 (the reference is Float64-only: src/warmup.jl:108,115,119; src/mcmc.jl:117-122)
+ *  - an engine is driven by one host thread at a time; engines are independent
+ *  - one engine = the chains resident on one GPU; a multi-GPU job creates one
+ *    engine per process/GPU with disjoint [chain_offset, chain_offset+n_chains)
+ *  - all calls are synchronous on return
+ */
+#ifndef BNUTS_H
+#define BNUTS_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bnuts_engine bnuts_engine;
+
+typedef enum {
+  BNUTS_OK = 0,
+  BNUTS_ERR_INVALID_ARGUMENT = -1,
+  BNUTS_ERR_NO_MODEL = -2,
+  BNUTS_ERR_CUDA = -3,
+  BNUTS_ERR_NONFINITE_START = -4,  /* ≙ DomainError, src/stepsize.jl:128,136,152-153 */
+  BNUTS_ERR_STEPSIZE_SEARCH = -5,  /* ≙ error(), src/stepsize.jl:71,101 */
+  BNUTS_ERR_STEPSIZE_COLLAPSE = -6,/* ≙ AssertionError eps < 1e-10, src/warmup.jl:291-296 */
+  BNUTS_ERR_UNSUPPORTED = -7,
+  BNUTS_ERR_INTERNAL = -8
+} bnuts_status;
+
+enum { BNUTS_F64 = 0, BNUTS_F32 = 1 };                 /* engine arithmetic type */
+enum { BNUTS_X_F64 = 0, BNUTS_X_F32 = 1, BNUTS_X_BF16 = 2 }; /* design-matrix storage */
+enum { BNUTS_GRAD_AUTO = 0, BNUTS_GRAD_DETERMINISTIC = 1, BNUTS_GRAD_TENSOR = 2 };
+enum { BNUTS_METRIC_NONE = 0, BNUTS_METRIC_DIAG = 1 }; /* ≙ TuningNUTS{Nothing|Diagonal}, src/warmup.jl:217-234 */
+
+/* ≙ NUTS(max_depth, min_Δ) src/NUTS.jl:204-220 + run geometry */
+typedef struct {
+  int32_t struct_size;   /* sizeof(bnuts_config), for ABI evolution */
+  int32_t dtype;         /* BNUTS_F64 | BNUTS_F32 */
+  int32_t n_chains;      /* chains resident in this engine */
+  int32_t dim;           /* D */
+  int32_t max_depth;     /* default 10 (src/NUTS.jl:214) */
+  int32_t device;        /* CUDA device ordinal */
+  double  min_delta;     /* default -1000.0 (src/NUTS.jl:214) */
+  uint64_t seed;         /* Philox key */
+  int32_t chain_offset;  /* global id of chain 0 (RNG is keyed by global id) */
+  int32_t gradient_path; /* BNUTS_GRAD_* */
+} bnuts_config;
+
+/* ≙ TreeStatisticsNUTS, src/NUTS.jl:229-242 — same 32-byte layout, so Julia can
+ * unsafe_wrap the buffer as Vector{TreeStatisticsNUTS}. */
+typedef struct {
+  double  pi;              /* log density of the selected draw (with its own momentum) */
+  double  acceptance_rate; /* min(1, exp(log_sum_alpha)/steps), src/NUTS.jl:84 */
+  int32_t term_left;       /* InvalidTree.left  (src/tree.jl:278-300) */
+  int32_t term_right;      /* InvalidTree.right; (1,0) = REACHED_MAX_DEPTH */
+  int32_t depth;
+  int32_t steps;
+} bnuts_tree_stats;
+
+/* ≙ DualAveraging(δ,γ,κ,t₀), src/stepsize.jl:173-193 */
+typedef struct { double delta, gamma, kappa; int32_t t0; int32_t _pad; } bnuts_dual_averaging;
+
+/* ≙ InitialStepsizeSearch, src/stepsize.jl:16-38 */
+typedef struct {
+  double a_min, a_max, eps0, C;
+  int32_t maxiter_crossing, maxiter_bisect;
+} bnuts_stepsize_search;
+
+typedef struct {
+  int64_t leapfrogs;        /* gradient evaluations of finished transitions */
+  int64_t transitions;      /* finished transitions */
+  int64_t lockstep_steps;   /* kernel-level leapfrog rounds launched */
+  int64_t kernel_launches;  /* launches of this library's kernels */
+  int64_t divergences;
+} bnuts_counter_block;
+
+int32_t bnuts_create(const bnuts_config* cfg, bnuts_engine** out);
+int32_t bnuts_destroy(bnuts_engine* e);
+/* e == NULL returns the message of the last failed bnuts_create on this thread */
+const char* bnuts_last_error(const bnuts_engine* e);
+
+/* Models.  The reference takes a user AbstractProbabilityModel and calls
+ * logdensity_and_gradient!(∇ℓq, ℓ, q, sptr) (src/kinetic_energy.jl:73); a device
+ * engine cannot call a Julia closure, so the benchmark targets are built in. */
+int32_t bnuts_model_iid_normal(bnuts_engine* e);
+int32_t bnuts_model_funnel(bnuts_engine* e);
+int32_t bnuts_model_gaussian(bnuts_engine* e, const double* precision /* [D][D] */);
+/* X is [N][D] row-major in x_dtype; y is [N] of 0/1.  row_blocks fixes the
+ * summation order of the deterministic path (ignored by the tensor path). */
+int32_t bnuts_model_logistic(bnuts_engine* e, const void* X, int32_t x_dtype, const double* y,
+                             int64_t N, double prior_precision, int32_t row_blocks);
+
+/* ≙ initialize_warmup_state(q = …), src/warmup.jl:100-129: sets q and evaluates
+ * ℓ, ∇ℓ.  q == NULL draws U[-2,2]^D (src/warmup.jl:73) from Philox. */
+int32_t bnuts_set_positions(bnuts_engine* e, const double* q /* [C][D] */);
+int32_t bnuts_get_state(bnuts_engine* e, double* q, double* grad, double* logdensity);
+
+/* ≙ GaussianKineticEnergy(M⁻¹) src/hamiltonian.jl:50-74; W = 1/sqrt(M⁻¹).
+ * minv == NULL resets to the identity (src/warmup.jl:102). Per-chain metric. */
+int32_t bnuts_set_metric_diag(bnuts_engine* e, const double* minv /* [C][D] */);
+int32_t bnuts_get_metric_diag(bnuts_engine* e, double* minv /* [C][D] */);
+
+int32_t bnuts_set_stepsize(bnuts_engine* e, const double* eps /* [C] */);
+int32_t bnuts_get_stepsize(bnuts_engine* e, double* eps /* [C] */);
+
+/* Philox key and the transition counter the next transition will use. */
+int32_t bnuts_seed(bnuts_engine* e, uint64_t seed, uint32_t next_transition);
+
+/* ≙ sample_tree(...; p = …, directions = …) src/NUTS.jl:251-258: the next T
+ * transitions of every chain use these directions and momenta instead of Philox.
+ * dirs [T][C]; p [T][C][D] (either may be NULL to keep that stream random). */
+int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const double* p);
+
+/* ≙ stack leapfrog, src/kinetic_energy.jl:164-195: nsteps leapfrogs of signed
+ * step eps[c] from the engine's current (q, ∇ℓ) with momentum p_in; engine state
+ * is not modified.  Outputs [C][D] / [C], any may be NULL. */
+int32_t bnuts_leapfrog(bnuts_engine* e, const double* p_in, const double* eps, int32_t nsteps,
+                       double* q_out, double* p_out, double* grad_out, double* logdensity_out);
+
+/* ≙ warmup!(InitialStepsizeSearch) src/warmup.jl:188-200 + src/stepsize.jl:51-126,150-164 */
+int32_t bnuts_find_initial_stepsize(bnuts_engine* e, const bnuts_stepsize_search* params);
+
+/* ≙ warmup!(TuningNUTS{M}) src/warmup.jl:269-314: N transitions with dual
+ * averaging restarted from the current eps (src/stepsize.jl:208-212), then (metric_kind
+ * == DIAG) the regularised variance update (src/hamiltonian.jl:117-189) and
+ * eps <- final_ϵ (src/stepsize.jl:241).  lambda < 0 means the default 5/N.
+ * Optional outputs: chain_out/stats_out as bnuts_sample; eps_out [C][N]. */
+int32_t bnuts_warmup_stage(bnuts_engine* e, int32_t N, int32_t metric_kind,
+                           const bnuts_dual_averaging* da, double lambda,
+                           double* chain_out, int64_t stride_draw, int64_t stride_chain,
+                           bnuts_tree_stats* stats_out, int64_t stats_stride_chain,
+                           double* eps_out);
+
+/* ≙ mcmc! src/warmup.jl:316-332 with the output layout of threaded_mcmc
+ * (src/mcmc.jl:140-152): draw n of chain c is written at
+ * chain_out[c*stride_chain + n*stride_draw + d] (strides in elements), its
+ * statistics at stats_out[c*stats_stride_chain + n].  selected_index (may be
+ * NULL) receives the trajectory position of the selected draw, [C][N]. */
+int32_t bnuts_sample(bnuts_engine* e, int32_t N,
+                     double* chain_out, int64_t stride_draw, int64_t stride_chain,
+                     bnuts_tree_stats* stats_out, int64_t stats_stride_chain,
+                     int32_t* selected_index);
+
+int32_t bnuts_counters(bnuts_engine* e, bnuts_counter_block* out);
+/* per-chain numerical status: 0 ok, else a bnuts_status */
+int32_t bnuts_chain_status(bnuts_engine* e, int32_t* status /* [C] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNUTS_H */

@@ -1,0 +1,8 @@
+"""bnuts — B200-native batched-chain NUTS engine behind InplaceDHMC.jl's API names.
+
+The directory name contains a dot, so import it through the root-level shim
+``import inplacedhmc_jl_b200`` (see inplacedhmc_jl_b200.py).
+"""
+from ._capi import (Engine, BnutsError, load_library, DEFAULT_LIB, TREE_STATS_DTYPE, EXPORTS,  # noqa: F401
+                    F64, F32, X_F64, X_F32, X_BF16, GRAD_AUTO, GRAD_DETERMINISTIC, GRAD_TENSOR,
+                    METRIC_NONE, METRIC_DIAG)
