@@ -1,0 +1,368 @@
+// engine_core.h — host-side engine behind the C ABI of include/bnuts.h.
+//
+// Written once over an execution policy X:
+//   CudaExec  (engine_cuda.cu)        — the product: device memory, kernels, streams
+//   HostExec  (tests/hostemu/*.cpp)   — a serial emulation used only by the CPU test
+//                                       suite to exercise this file and the state
+//                                       machine without a GPU
+// X provides raw memory (alloc/free/h2d/d2h/zero), the per-chain launches
+// (prepare / advance / metric / finish_da / totals) and the batched gradient
+// evaluators of the GEMM-shaped targets.
+//
+// Call structure mirrors the reference drivers: bnuts_warmup_stage ≙
+// warmup!(TuningNUTS) (src/warmup.jl:269-314), bnuts_sample ≙ mcmc!
+// (src/warmup.jl:316-332), bnuts_find_initial_stepsize ≙ src/warmup.jl:188-200.
+#pragma once
+#include <string>
+#include <vector>
+#include <cstring>
+#include "../../include/bnuts.h"
+#include "backend.h"
+
+namespace bn {
+
+static_assert(sizeof(TreeStats) == sizeof(bnuts_tree_stats), "stats layout");
+
+template <class T> struct ModelCtx {
+  int32_t kind = MODEL_NONE;
+  // gaussian
+  T* P = nullptr;            // [D][D] device
+  // logistic
+  T* X = nullptr;            // [N][D] device (deterministic path)
+  T* y = nullptr;            // [N]
+  uint16_t* Xb = nullptr;    // [Npad][Dt] bf16 device (tensor path)
+  float* yf = nullptr;       // [Npad]
+  int64_t N = 0, Npad = 0;
+  int32_t row_blocks = 1;
+  bool tensor = false;
+  bool batched() const { return kind == MODEL_GAUSSIAN || kind == MODEL_LOGISTIC; }
+};
+
+template <class T, class X> struct EngineCore {
+  bnuts_config cfg{};
+  X x;
+  EngineMem<T> M{};
+  RunParams<T> rp{};
+  ModelCtx<T> model;
+  uint32_t next_t = 0;
+  std::string err;
+  bnuts_counter_block counters{};
+  // per-call device output buffers (grown on demand)
+  size_t cap_draws = 0, cap_stats = 0;
+  TreeStats* d_stats = nullptr; int32_t* d_sel = nullptr; double* d_eps_hist = nullptr;
+  uint32_t* d_inj_dirs = nullptr; double* d_inj_p = nullptr;
+  double* d_tmp_cd = nullptr;   // [C][D] scratch (positions / momenta in)
+  double* d_tmp_c = nullptr;    // [C]
+  std::vector<double> h_draws;  // staging when caller strides are not compact
+
+  int32_t fail(int32_t code, const std::string& m) { err = m; return code; }
+
+  int32_t init(const bnuts_config& c) {
+    cfg = c;
+    if (c.max_depth > MAX_LEVELS) return fail(BNUTS_ERR_UNSUPPORTED, "max_depth > 20 not supported by the device engine");
+    int32_t rc = x.init(c.device, err);
+    if (rc) return rc;
+    M.C = c.n_chains; M.D = c.dim; M.Dp = (c.dim + 31) / 32 * 32;
+    M.S = c.max_depth + 4; M.L = c.max_depth;
+    M.model_kind = MODEL_NONE;
+    const size_t CD = size_t(M.C) * M.Dp;
+    M.zs = x.template alloc<T>(CD * M.S * 3);
+    M.zlq = x.template alloc<T>(size_t(M.C) * M.S);
+    M.st_rho = x.template alloc<T>(CD * M.L);
+    M.st_psf = x.template alloc<T>(CD * M.L);
+    M.m_rho = x.template alloc<T>(CD); M.m_psm = x.template alloc<T>(CD); M.m_psp = x.template alloc<T>(CD);
+    M.ps_cur = x.template alloc<T>(CD); M.Minv = x.template alloc<T>(CD); M.W = x.template alloc<T>(CD);
+    M.cs = x.template alloc<ChainState<T>>(M.C);
+    d_tmp_cd = x.template alloc<double>(size_t(M.C) * M.D * 4 + M.C);
+    d_tmp_c = x.template alloc<double>(M.C);
+    if (!M.zs || !M.st_rho || !M.st_psf || !M.cs || !d_tmp_cd) return fail(BNUTS_ERR_CUDA, "device allocation failed");
+    x.zero(M.zs, CD * M.S * 3 * sizeof(T));
+    x.zero(M.zlq, size_t(M.C) * M.S * sizeof(T));
+    x.zero(M.cs, size_t(M.C) * sizeof(ChainState<T>));
+    rp.max_depth = c.max_depth; rp.min_delta = T(c.min_delta); rp.seed = c.seed;
+    rp.chain_offset = c.chain_offset; rp.n_chains = c.n_chains; rp.n_slots = M.S;
+    std::vector<double> ones(size_t(M.C) * M.D, 1.0);
+    set_metric(nullptr);
+    std::vector<double> e1(M.C, 1.0);
+    set_stepsize(e1.data());
+    return x.check(err);
+  }
+  void destroy() {
+    x.sync();
+    void* ptrs[] = {M.zs, M.zlq, M.st_rho, M.st_psf, M.m_rho, M.m_psm, M.m_psp, M.ps_cur, M.Minv, M.W, M.cs,
+                    M.stage_q, M.stage_g, M.stage_l, M.stage_bh, M.stage_bl, M.draws, d_stats, d_sel, d_eps_hist,
+                    d_inj_dirs, d_inj_p, d_tmp_cd, d_tmp_c, model.P, model.X, model.y, model.Xb, model.yf};
+    for (void* p : ptrs) if (p) x.free(p);
+    x.shutdown();
+  }
+
+  // ---------------------------------------------------------------- models
+  void free_model() {
+    void** ps[] = {(void**)&model.P, (void**)&model.X, (void**)&model.y, (void**)&model.Xb, (void**)&model.yf,
+                   (void**)&M.stage_q, (void**)&M.stage_g, (void**)&M.stage_l, (void**)&M.stage_bh, (void**)&M.stage_bl};
+    for (void** p : ps) if (*p) { x.free(*p); *p = nullptr; }
+    model = ModelCtx<T>();
+    M.stage_nb = 0;
+  }
+  int32_t model_simple(int kind) {
+    free_model();
+    model.kind = kind; M.model_kind = kind;
+    return 0;
+  }
+  void alloc_stage(int nb) {
+    const size_t CD = size_t(M.C) * M.Dp;
+    M.stage_nb = nb;
+    M.stage_q = x.template alloc<T>(CD);
+    M.stage_g = x.template alloc<T>(CD * nb);
+    M.stage_l = x.template alloc<T>(size_t(M.C) * nb);
+    x.zero(M.stage_q, CD * sizeof(T));
+    x.zero(M.stage_g, CD * nb * sizeof(T));
+    x.zero(M.stage_l, size_t(M.C) * nb * sizeof(T));
+  }
+  int32_t model_gaussian(const double* P) {
+    if (!P) return fail(BNUTS_ERR_INVALID_ARGUMENT, "precision is NULL");
+    free_model();
+    const size_t n = size_t(M.D) * M.D;
+    std::vector<T> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = T(P[i]);
+    model.P = x.template alloc<T>(n);
+    x.h2d(model.P, h.data(), n * sizeof(T));
+    alloc_stage(1);
+    model.kind = MODEL_GAUSSIAN; M.model_kind = MODEL_GAUSSIAN;
+    return x.check(err);
+  }
+  int32_t model_logistic(const void* Xh, int32_t xd, const double* y, int64_t N, double tau, int32_t rb) {
+    if (!Xh || !y || N <= 0 || rb <= 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad logistic arguments");
+    if (xd != BNUTS_X_F64 && xd != BNUTS_X_F32 && xd != BNUTS_X_BF16) return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad x_dtype");
+    free_model();
+    const bool want_tensor = cfg.gradient_path == BNUTS_GRAD_TENSOR ||
+                             (cfg.gradient_path == BNUTS_GRAD_AUTO && sizeof(T) == 4 && X::has_tensor_path);
+    if (want_tensor) {
+      if (sizeof(T) != 4 || !X::has_tensor_path)
+        return fail(BNUTS_ERR_UNSUPPORTED, "tensor gradient path needs dtype F32 on the CUDA engine");
+      int32_t rc = x.logistic_tensor_setup(*this, Xh, xd, y, N, err);
+      if (rc) return rc;
+      model.tensor = true;
+    } else {
+      const size_t n = size_t(N) * M.D;
+      std::vector<T> h(n);
+      std::vector<T> hy(static_cast<size_t>(N));
+      for (size_t i = 0; i < n; ++i) {
+        double v;
+        if (xd == BNUTS_X_F64) v = static_cast<const double*>(Xh)[i];
+        else if (xd == BNUTS_X_F32) v = double(static_cast<const float*>(Xh)[i]);
+        else v = double(bf16_val(static_cast<const uint16_t*>(Xh)[i]));
+        h[i] = T(v);
+      }
+      for (int64_t i = 0; i < N; ++i) hy[size_t(i)] = T(y[i]);
+      model.X = x.template alloc<T>(n); model.y = x.template alloc<T>(size_t(N));
+      if (!model.X || !model.y) return fail(BNUTS_ERR_CUDA, "device allocation failed");
+      x.h2d(model.X, h.data(), n * sizeof(T));
+      x.h2d(model.y, hy.data(), size_t(N) * sizeof(T));
+      model.row_blocks = rb;
+      alloc_stage(rb);
+    }
+    model.N = N;
+    M.tau = T(tau);
+    model.kind = MODEL_LOGISTIC; M.model_kind = MODEL_LOGISTIC;
+    return x.check(err);
+  }
+
+  // ---------------------------------------------------------------- state setters
+  int32_t set_metric(const double* minv) {
+    std::vector<T> hm(size_t(M.C) * M.Dp, T(1)), hw(size_t(M.C) * M.Dp, T(1));
+    for (int c = 0; c < M.C; ++c)
+      for (int d = 0; d < M.D; ++d) {
+        const double m = minv ? minv[size_t(c) * M.D + d] : 1.0;
+        hm[size_t(c) * M.Dp + d] = T(m);
+        hw[size_t(c) * M.Dp + d] = T(1.0 / sqrt_(m));  // ≙ src/hamiltonian.jl:53-55
+      }
+    x.h2d(M.Minv, hm.data(), hm.size() * sizeof(T));
+    x.h2d(M.W, hw.data(), hw.size() * sizeof(T));
+    return x.check(err);
+  }
+  int32_t get_metric(double* out) {
+    std::vector<T> hm(size_t(M.C) * M.Dp);
+    x.d2h(hm.data(), M.Minv, hm.size() * sizeof(T));
+    for (int c = 0; c < M.C; ++c)
+      for (int d = 0; d < M.D; ++d) out[size_t(c) * M.D + d] = double(hm[size_t(c) * M.Dp + d]);
+    return x.check(err);
+  }
+  int32_t set_stepsize(const double* eps) {
+    x.h2d(d_tmp_c, eps, size_t(M.C) * sizeof(double));
+    x.set_eps(M, d_tmp_c);
+    return x.check(err);
+  }
+  int32_t get_stepsize(double* eps) {
+    x.get_eps(M, d_tmp_c);
+    x.d2h(eps, d_tmp_c, size_t(M.C) * sizeof(double));
+    return x.check(err);
+  }
+
+  // ---------------------------------------------------------------- run loop
+  // Lockstep: [batched gradient] -> advance (consume leaf, merges, next leapfrog) -> ...
+  // until every chain is idle.  Elementwise targets run inside advance().
+  int32_t run(bool pending) {
+    const bool batched = model.batched();
+    const int iters = batched ? 1 : (1 << 30);
+    for (;;) {
+      if (pending && batched) { x.gradient(*this); counters.kernel_launches += 1; }
+      const int64_t np = x.advance(M, rp, iters);
+      counters.kernel_launches += 1;
+      counters.lockstep_steps += 1;
+      pending = np > 0;
+      if (!pending) break;
+    }
+    return x.check(err);
+  }
+  void ensure_out(int N, bool want_draws) {
+    const size_t nd = size_t(M.C) * N * M.D, ns = size_t(M.C) * N;
+    if (want_draws && nd > cap_draws) {
+      if (M.draws) x.free(M.draws);
+      M.draws = x.template alloc<double>(nd);
+      cap_draws = nd;
+    }
+    if (ns > cap_stats) {
+      if (d_stats) { x.free(d_stats); x.free(d_sel); x.free(d_eps_hist); }
+      d_stats = x.template alloc<TreeStats>(ns);
+      d_sel = x.template alloc<int32_t>(ns);
+      d_eps_hist = x.template alloc<double>(ns);
+      cap_stats = ns;
+    }
+  }
+  void copy_out(int N, double* chain_out, int64_t sd, int64_t sc, bnuts_tree_stats* stats_out, int64_t ssc,
+                int32_t* sel, double* eps_out) {
+    const int C = M.C, D = M.D;
+    if (chain_out) {
+      if (sd == D && sc == int64_t(N) * D) x.d2h(chain_out, M.draws, size_t(C) * N * D * sizeof(double));
+      else {
+        h_draws.resize(size_t(C) * N * D);
+        x.d2h(h_draws.data(), M.draws, h_draws.size() * sizeof(double));
+        for (int c = 0; c < C; ++c)
+          for (int n = 0; n < N; ++n)
+            std::memcpy(chain_out + c * sc + n * sd, &h_draws[(size_t(c) * N + n) * D], size_t(D) * sizeof(double));
+      }
+    }
+    if (stats_out) {
+      if (ssc == N) x.d2h(stats_out, d_stats, size_t(C) * N * sizeof(TreeStats));
+      else for (int c = 0; c < C; ++c) x.d2h(stats_out + c * ssc, d_stats + size_t(c) * N, size_t(N) * sizeof(TreeStats));
+    }
+    if (sel) x.d2h(sel, d_sel, size_t(C) * N * sizeof(int32_t));
+    if (eps_out) x.d2h(eps_out, d_eps_hist, size_t(C) * N * sizeof(double));
+  }
+
+  int32_t transitions(int N, const bnuts_dual_averaging* da, int metric_kind, double lambda, double* chain_out,
+                      int64_t sd, int64_t sc, bnuts_tree_stats* stats_out, int64_t ssc, int32_t* sel, double* eps_out) {
+    if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
+    if (N <= 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "N must be positive");
+    if (metric_kind != BNUTS_METRIC_NONE && metric_kind != BNUTS_METRIC_DIAG)
+      return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad metric_kind");
+    const bool want_draws = chain_out != nullptr || metric_kind == BNUTS_METRIC_DIAG;
+    ensure_out(N, want_draws);
+    double* keep_draws = M.draws;
+    if (!want_draws) M.draws = nullptr;
+    rp.da_on = da ? 1 : 0;
+    if (da) { rp.da.delta = da->delta; rp.da.gamma = da->gamma; rp.da.kappa = da->kappa; rp.da.t0 = da->t0; }
+    rp.stats = d_stats; rp.sel = d_sel; rp.eps_hist = d_eps_hist; rp.n_total = N;
+    PrepareArgs a{}; a.mode = MODE_SAMPLE; a.N = N; a.t0 = next_t;
+    x.prepare(M, rp, a);
+    int32_t rc = run(false);
+    if (rc) { M.draws = keep_draws; return rc; }
+    if (metric_kind == BNUTS_METRIC_DIAG) x.metric_update(M, N, lambda < 0 ? 5.0 / N : lambda);  // ≙ src/warmup.jl:308-309
+    if (da) x.finish_da(M);                                                                     // ≙ final_ϵ, :313
+    next_t += uint32_t(N);
+    copy_out(N, chain_out, sd, sc, stats_out, ssc, sel, eps_out);
+    M.draws = keep_draws;
+    rc = x.check(err);
+    if (rc) return rc;
+    if (x.any_status(M, ST_STEPSIZE_COLLAPSE))
+      return fail(BNUTS_ERR_STEPSIZE_COLLAPSE, "step size fell below 1e-10 during adaptation");
+    return 0;
+  }
+
+  int32_t set_positions(const double* q) {
+    if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
+    if (q) { x.h2d(d_tmp_cd, q, size_t(M.C) * M.D * sizeof(double)); M.pos_in = d_tmp_cd; } else M.pos_in = nullptr;
+    PrepareArgs a{}; a.mode = MODE_EVAL;
+    x.prepare(M, rp, a);
+    int32_t rc = run(true);
+    if (rc) return rc;
+    if (x.any_status(M, ST_NONFINITE_START)) return fail(BNUTS_ERR_NONFINITE_START, "starting point has non-finite density");
+    return 0;
+  }
+  int32_t get_state(double* q, double* g, double* l) {
+    double* o = d_tmp_cd;
+    x.gather_state(M, o);
+    const size_t n = size_t(M.C) * M.D;
+    if (q) x.d2h(q, o, n * sizeof(double));
+    if (g) x.d2h(g, o + n, n * sizeof(double));
+    if (l) x.d2h(l, o + 2 * n, size_t(M.C) * sizeof(double));
+    return x.check(err);
+  }
+  int32_t inject(int32_t Tn, const uint32_t* dirs, const double* p) {
+    if (Tn < 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "T < 0");
+    if (d_inj_dirs) { x.free(d_inj_dirs); d_inj_dirs = nullptr; }
+    if (d_inj_p) { x.free(d_inj_p); d_inj_p = nullptr; }
+    if (dirs && Tn > 0) {
+      d_inj_dirs = x.template alloc<uint32_t>(size_t(Tn) * M.C);
+      x.h2d(d_inj_dirs, dirs, size_t(Tn) * M.C * sizeof(uint32_t));
+    }
+    if (p && Tn > 0) {
+      d_inj_p = x.template alloc<double>(size_t(Tn) * M.C * M.D);
+      x.h2d(d_inj_p, p, size_t(Tn) * M.C * M.D * sizeof(double));
+    }
+    rp.inj_T = Tn; rp.inj_start = next_t; rp.inj_dirs = d_inj_dirs; rp.inj_p = d_inj_p;
+    return x.check(err);
+  }
+  int32_t leapfrog(const double* p_in, const double* eps, int nsteps, double* q_out, double* p_out, double* g_out,
+                   double* l_out) {
+    if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
+    if (!p_in || !eps || nsteps < 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "p_in, eps required");
+    const size_t n = size_t(M.C) * M.D;
+    double* d_p = x.template alloc<double>(n);
+    double* d_out = x.template alloc<double>(3 * n + M.C);
+    x.h2d(d_p, p_in, n * sizeof(double));
+    x.h2d(d_tmp_c, eps, size_t(M.C) * sizeof(double));
+    M.bare_p_in = d_p; M.bare_out = d_out;
+    PrepareArgs a{}; a.mode = MODE_BARE; a.N = nsteps; a.bare_eps = d_tmp_c;
+    x.prepare(M, rp, a);
+    int32_t rc = run(false);
+    if (!rc) {
+      if (q_out) x.d2h(q_out, d_out, n * sizeof(double));
+      if (p_out) x.d2h(p_out, d_out + n, n * sizeof(double));
+      if (g_out) x.d2h(g_out, d_out + 2 * n, n * sizeof(double));
+      if (l_out) x.d2h(l_out, d_out + 3 * n, size_t(M.C) * sizeof(double));
+      rc = x.check(err);
+    }
+    M.bare_p_in = nullptr; M.bare_out = nullptr;
+    x.free(d_p); x.free(d_out);
+    return rc;
+  }
+  int32_t find_initial_stepsize(const bnuts_stepsize_search& P) {
+    if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
+    rp.search.a_min = P.a_min; rp.search.a_max = P.a_max; rp.search.eps0 = P.eps0; rp.search.C = P.C;
+    rp.search.maxiter_crossing = P.maxiter_crossing; rp.search.maxiter_bisect = P.maxiter_bisect;
+    rp.da_on = 0;
+    PrepareArgs a{}; a.mode = MODE_SEARCH; a.t0 = next_t;
+    x.prepare(M, rp, a);
+    int32_t rc = run(false);
+    next_t += 1;
+    if (rc) return rc;
+    if (x.any_status(M, ST_NONFINITE_START) || x.any_status(M, ST_STEPSIZE_SEARCH))
+      return fail(BNUTS_ERR_STEPSIZE_SEARCH, "initial step size search failed for some chains");
+    return 0;
+  }
+  int32_t get_counters(bnuts_counter_block* out) {
+    int64_t tot[3];
+    x.totals(M, tot);
+    counters.leapfrogs = tot[0]; counters.transitions = tot[1]; counters.divergences = tot[2];
+    *out = counters;
+    return x.check(err);
+  }
+  int32_t chain_status(int32_t* st) {
+    x.get_status(M, st);
+    return x.check(err);
+  }
+};
+
+}  // namespace bn
