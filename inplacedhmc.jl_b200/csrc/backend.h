@@ -73,14 +73,20 @@ struct SerialLanes {
 struct WarpLanes {
   static constexpr int NACC = 1;
   int lane;
-  __device__ __forceinline__ int first() const { return lane; }
-  __device__ __forceinline__ int stride() const { return 32; }
-  __device__ __forceinline__ int acc(int) const { return 0; }
-  __device__ __forceinline__ bool lane0() const { return lane == 0; }
-  __device__ __forceinline__ void sync() const { __syncwarp(); }
-  template <class T> __device__ __forceinline__ T reduce(T* part) const {
+  BN_HD int first() const { return lane; }
+  BN_HD int stride() const { return 32; }
+  BN_HD int acc(int) const { return 0; }
+  BN_HD bool lane0() const { return lane == 0; }
+  BN_HD void sync() const {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+  }
+  template <class T> BN_HD T reduce(T* part) const {
     T v = part[0];
+#if defined(__CUDA_ARCH__)
     for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+#endif
     return v;
   }
 };

@@ -1,0 +1,289 @@
+// engine_cuda.cu — CUDA execution policy of the engine (sm_100a) and libbnuts.so's
+// C ABI.  One warp owns one chain; see backend.h for the HBM layout and
+// nuts_machine.h for the per-chain state machine these kernels run.
+//
+// Kernels:
+//   k_prepare        per-call chain set-up                     (≙ loop prologues, src/warmup.jl:283-287)
+//   k_advance        consume leaf + merges + next leapfrog     (≙ src/tree.jl:321-444, src/kinetic_energy.jl:126-163)
+//   k_grad_gaussian  deterministic G = -P·Q                    (≙ logdensity_and_gradient!, src/kinetic_energy.jl:73)
+//   k_grad_logistic  deterministic logistic-regression gradient, fixed row-block order
+//   logistic_tc.cu   tcgen05/TMA fused two-GEMM logistic gradient (fp32 variant)
+//   k_metric, k_finish_da, small gathers
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <string>
+
+#include "engine_core.h"
+#include "logistic_tc.h"
+
+namespace bn {
+
+constexpr int ADV_THREADS = 128;  // 4 chains per CTA
+
+template <class T> __global__ void __launch_bounds__(ADV_THREADS) k_prepare(EngineMem<T> M, RunParams<T> rp, PrepareArgs a) {
+  const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (c >= M.C) return;
+  prepare_chain(M, rp, a, c, WarpLanes{(int)(threadIdx.x & 31)});
+}
+
+template <class T>
+__global__ void __launch_bounds__(ADV_THREADS) k_advance(EngineMem<T> M, RunParams<T> rp, int iters, unsigned long long* pending) {
+  const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (c >= M.C) return;
+  const int lane = (int)(threadIdx.x & 31);
+  const bool p = advance_chain(M, rp, c, WarpLanes{lane}, iters);
+  if (p && lane == 0) atomicAdd(pending, 1ull);
+}
+
+template <class T> __global__ void __launch_bounds__(ADV_THREADS) k_metric(EngineMem<T> M, int N, double lambda) {
+  const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (c >= M.C) return;
+  metric_update_chain(M, c, N, lambda, WarpLanes{(int)(threadIdx.x & 31)});
+}
+
+template <class T> __global__ void k_finish_da(EngineMem<T> M) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < M.C && M.cs[c].status == 0) M.cs[c].eps = exp_(M.cs[c].da_logepsbar);  // ≙ final_ϵ, src/stepsize.jl:241
+}
+template <class T> __global__ void k_set_eps(EngineMem<T> M, const double* e) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < M.C) M.cs[c].eps = e[c];
+}
+template <class T> __global__ void k_get_eps(EngineMem<T> M, double* e) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < M.C) e[c] = M.cs[c].eps;
+}
+template <class T> __global__ void k_get_status(EngineMem<T> M, int32_t* st) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < M.C) st[c] = M.cs[c].status;
+}
+template <class T> __global__ void k_totals(EngineMem<T> M, unsigned long long* tot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= M.C) return;
+  atomicAdd(&tot[0], (unsigned long long)M.cs[c].tot_leapfrogs);
+  atomicAdd(&tot[1], (unsigned long long)M.cs[c].tot_transitions);
+  atomicAdd(&tot[2], (unsigned long long)M.cs[c].tot_divergences);
+}
+template <class T> __global__ void k_gather_state(EngineMem<T> M, double* o) {
+  const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (c >= M.C) return;
+  const int lane = (int)(threadIdx.x & 31);
+  const int64_t n = (int64_t)M.C * M.D;
+  const int s = M.cs[c].slot_cur;
+  const T* q = M.zs + ((int64_t)c * M.S + s) * 3 * M.Dp;
+  for (int d = lane; d < M.D; d += 32) {
+    o[(int64_t)c * M.D + d] = (double)q[d];
+    o[n + (int64_t)c * M.D + d] = (double)q[2 * M.Dp + d];
+  }
+  if (lane == 0) o[2 * n + c] = (double)M.zlq[(int64_t)c * M.S + s];
+}
+
+// ------------------------------------------------------------------ deterministic gradients
+// G[c][d] = -sum_k P[d][k] Q[c][k], k strictly sequential per output so the result
+// is bit-identical to the oracle's scalar loop.  64x64 output tile, 4x4 per thread.
+template <class T>
+__global__ void __launch_bounds__(256) k_grad_gaussian(const T* __restrict__ P, const T* Q, T* G, int C, int D, int Dp) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ T Ps[TK][TM + 1];
+  __shared__ T Qs[TK][TN + 1];
+  const int d0 = blockIdx.x * TM, c0 = blockIdx.y * TN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  for (int k0 = 0; k0 < D; k0 += TK) {
+    for (int idx = threadIdx.x; idx < TM * TK; idx += 256) {
+      const int r = idx / TK, k = idx % TK;
+      const int d = d0 + r, kk = k0 + k;
+      Ps[k][r] = (d < D && kk < D) ? P[(int64_t)d * D + kk] : T(0);
+      const int c = c0 + r;
+      Qs[k][r] = (c < C && kk < D) ? Q[(int64_t)c * Dp + kk] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = Ps[k][ty * 4 + i]; b[i] = Qs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma_(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + ty * 4 + i, c = c0 + tx * 4 + j;
+      if (d < D && c < C) G[(int64_t)c * Dp + d] = -acc[i][j];
+    }
+}
+
+// One warp = 32 chains, one CTA per (chain group, row block).  Rows of the block are
+// walked sequentially; eta and the gradient partials accumulate in index order.
+template <class T>
+__global__ void __launch_bounds__(32) k_grad_logistic(const T* __restrict__ X, const T* __restrict__ y, const T* Q, T* G,
+                                                       T* Lp, int64_t N, int D, int Dp, int C, int64_t R) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int XR = 8;
+  T* qs = reinterpret_cast<T*>(smem_raw);  // [D][32]
+  T* ps = qs + (size_t)D * 32;             // [D][32]
+  T* xs = ps + (size_t)D * 32;             // [XR][D]
+  T* ys = xs + (size_t)XR * D;             // [XR]
+  const int lane = threadIdx.x;
+  const int c = blockIdx.x * 32 + lane;
+  const int b = blockIdx.y;
+  const bool valid = c < C;
+  for (int d = 0; d < D; ++d) {
+    qs[d * 32 + lane] = valid ? Q[(int64_t)c * Dp + d] : T(0);
+    ps[d * 32 + lane] = T(0);
+  }
+  T pl = T(0);
+  const int64_t i0 = (int64_t)b * R;
+  const int64_t i1 = (i0 + R < N) ? i0 + R : N;
+  for (int64_t it = i0; it < i1; it += XR) {
+    const int nr = (int)((i1 - it < XR) ? (i1 - it) : XR);
+    __syncwarp();
+    for (int idx = lane; idx < nr * D; idx += 32) xs[idx] = X[it * D + idx];
+    if (lane < nr) ys[lane] = y[it + lane];
+    __syncwarp();
+    for (int r = 0; r < nr; ++r) {
+      const T* xr = xs + r * D;
+      T eta = T(0);
+      for (int d = 0; d < D; ++d) eta = fma_(xr[d], qs[d * 32 + lane], eta);
+      T rr, lt;
+      logistic_elem(eta, ys[r], &rr, &lt);
+      pl = pl + lt;
+      for (int d = 0; d < D; ++d) ps[d * 32 + lane] = fma_(xr[d], rr, ps[d * 32 + lane]);
+    }
+  }
+  if (valid) {
+    T* g = G + ((int64_t)b * C + c) * Dp;
+    for (int d = 0; d < D; ++d) g[d] = ps[d * 32 + lane];
+    Lp[(int64_t)b * C + c] = pl;
+  }
+}
+
+// ------------------------------------------------------------------ execution policy
+struct CudaExec {
+  static constexpr bool has_tensor_path = true;
+  cudaStream_t stream = nullptr;
+  cudaError_t first_err = cudaSuccess;
+  const char* first_where = "";
+  unsigned long long* d_scal = nullptr;  // [4]
+  unsigned long long* h_scal = nullptr;  // pinned [4]
+  int32_t* d_status = nullptr;
+  int device = 0;
+  LogisticTC tc;
+
+  void note(cudaError_t e, const char* where) {
+    if (e != cudaSuccess && first_err == cudaSuccess) { first_err = e; first_where = where; }
+  }
+  int32_t init(int dev, std::string& err) {
+    device = dev;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { err = std::string("no CUDA device: ") + cudaGetErrorString(e); return BNUTS_ERR_CUDA; }
+    if (dev < 0 || dev >= n) { err = "bad device ordinal"; return BNUTS_ERR_INVALID_ARGUMENT; }
+    note(cudaSetDevice(dev), "cudaSetDevice");
+    note(cudaMalloc(&d_scal, 4 * sizeof(unsigned long long)), "cudaMalloc");
+    note(cudaMallocHost(&h_scal, 4 * sizeof(unsigned long long)), "cudaMallocHost");
+    return check(err);
+  }
+  void shutdown() {
+    tc.destroy();
+    if (d_scal) cudaFree(d_scal);
+    if (h_scal) cudaFreeHost(h_scal);
+    if (d_status) cudaFree(d_status);
+  }
+  template <class U> U* alloc(size_t n) {
+    void* p = nullptr;
+    note(cudaSetDevice(device), "cudaSetDevice");
+    note(cudaMalloc(&p, (n ? n : 1) * sizeof(U)), "cudaMalloc");
+    return static_cast<U*>(p);
+  }
+  void free(void* p) { cudaFree(p); }
+  void h2d(void* d, const void* s, size_t n) { note(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream), "h2d"); note(cudaStreamSynchronize(stream), "h2d sync"); }
+  void d2h(void* d, const void* s, size_t n) { note(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream), "d2h"); note(cudaStreamSynchronize(stream), "d2h sync"); }
+  void zero(void* d, size_t n) { note(cudaMemsetAsync(d, 0, n, stream), "memset"); }
+  void sync() { note(cudaStreamSynchronize(stream), "sync"); }
+  int32_t check(std::string& err) {
+    note(cudaGetLastError(), "kernel launch");
+    if (first_err == cudaSuccess) return 0;
+    err = std::string("CUDA failure in ") + first_where + ": " + cudaGetErrorString(first_err);
+    return BNUTS_ERR_CUDA;
+  }
+  static int warp_grid(int C) { return (C * 32 + ADV_THREADS - 1) / ADV_THREADS; }
+
+  template <class T> void prepare(const EngineMem<T>& M, const RunParams<T>& rp, const PrepareArgs& a) {
+    note(cudaSetDevice(device), "cudaSetDevice");
+    k_prepare<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, a);
+  }
+  template <class T> int64_t advance(const EngineMem<T>& M, const RunParams<T>& rp, int iters) {
+    note(cudaMemsetAsync(d_scal, 0, sizeof(unsigned long long), stream), "memset");
+    k_advance<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, iters, d_scal);
+    note(cudaGetLastError(), "k_advance");
+    note(cudaMemcpyAsync(h_scal, d_scal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "pending d2h");
+    note(cudaStreamSynchronize(stream), "k_advance sync");
+    if (first_err != cudaSuccess) return 0;
+    return (int64_t)h_scal[0];
+  }
+  template <class E> void gradient(E& eng) {
+    auto& M = eng.M;
+    using T = typename std::remove_reference<decltype(*M.zs)>::type;
+    if (eng.model.kind == MODEL_GAUSSIAN) {
+      dim3 grid((M.D + 63) / 64, (M.C + 63) / 64);
+      k_grad_gaussian<T><<<grid, 256, 0, stream>>>(eng.model.P, M.stage_q, M.stage_g, M.C, M.D, M.Dp);
+    } else if (eng.model.kind == MODEL_LOGISTIC) {
+      if (eng.model.tensor) { tc.run(stream); }
+      else {
+        const int nb = eng.model.row_blocks;
+        const int64_t R = (eng.model.N + nb - 1) / nb;
+        const size_t smem = ((size_t)M.D * 64 + (size_t)8 * M.D + 8) * sizeof(T);
+        note(cudaFuncSetAttribute(k_grad_logistic<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        dim3 grid((M.C + 31) / 32, nb);
+        k_grad_logistic<T><<<grid, 32, smem, stream>>>(eng.model.X, eng.model.y, M.stage_q, M.stage_g, M.stage_l,
+                                                      eng.model.N, M.D, M.Dp, M.C, R);
+      }
+    }
+    note(cudaGetLastError(), "gradient kernel");
+  }
+  template <class E> int32_t logistic_tensor_setup(E& eng, const void* Xh, int32_t xd, const double* y, int64_t N, std::string& err) {
+    return logistic_tc_setup(tc, eng, Xh, xd, y, N, err);
+  }
+  template <class T> void metric_update(const EngineMem<T>& M, int N, double lambda) {
+    k_metric<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, N, lambda);
+  }
+  template <class T> void finish_da(const EngineMem<T>& M) { k_finish_da<T><<<(M.C + 127) / 128, 128, 0, stream>>>(M); }
+  template <class T> void set_eps(const EngineMem<T>& M, const double* e) { k_set_eps<T><<<(M.C + 127) / 128, 128, 0, stream>>>(M, e); }
+  template <class T> void get_eps(const EngineMem<T>& M, double* e) { k_get_eps<T><<<(M.C + 127) / 128, 128, 0, stream>>>(M, e); }
+  template <class T> void get_status(const EngineMem<T>& M, int32_t* st) {
+    if (!d_status) note(cudaMalloc(&d_status, (size_t)M.C * sizeof(int32_t)), "cudaMalloc");
+    k_get_status<T><<<(M.C + 127) / 128, 128, 0, stream>>>(M, d_status);
+    d2h(st, d_status, (size_t)M.C * sizeof(int32_t));
+  }
+  template <class T> bool any_status(const EngineMem<T>& M, int32_t code) {
+    std::vector<int32_t> st(M.C);
+    get_status(M, st.data());
+    for (int32_t v : st) if (v == code) return true;
+    return false;
+  }
+  template <class T> void gather_state(const EngineMem<T>& M, double* o) {
+    k_gather_state<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, o);
+  }
+  template <class T> void totals(const EngineMem<T>& M, int64_t* tot) {
+    note(cudaMemsetAsync(d_scal, 0, 3 * sizeof(unsigned long long), stream), "memset");
+    k_totals<T><<<(M.C + 127) / 128, 128, 0, stream>>>(M, d_scal);
+    d2h(h_scal, d_scal, 3 * sizeof(unsigned long long));
+    for (int i = 0; i < 3; ++i) tot[i] = (int64_t)h_scal[i];
+  }
+};
+
+}  // namespace bn
+
+#define BNUTS_EXEC bn::CudaExec
+#include "capi_impl.h"

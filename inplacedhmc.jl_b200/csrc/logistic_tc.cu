@@ -1,0 +1,490 @@
+// logistic_tc.cu — fused two-GEMM logistic-regression gradient on tcgen05 + TMA (sm_100a).
+//
+// Replaces the model call of the reference's leapfrog (logdensity_and_gradient!,
+// call site src/kinetic_energy.jl:73) for the Bayesian logistic-regression target
+// when thousands of chains advance in lockstep:
+//     H = X·B            (N x C, never materialised)
+//     R = y − σ(H),  ℓ_c = Σ_i [y_i H_ic − softplus(H_ic)]
+//     G = Xᵀ·R           (D x C)
+// One CTA owns a tile of 128 chains and a contiguous range of 128-row blocks of X.
+// Chains are the MMA M dimension, so TMEM lane = chain: each elementwise thread
+// owns one chain, the sum over data rows is a serial per-thread accumulation and
+// the residual tile goes back to TMEM as the A operand of the second GEMM
+// (FlashAttention-shaped: S in TMEM -> elementwise -> P in TMEM -> second MMA).
+//
+//   GEMM1  S[128 chains x 128 rows]  = Bt[128 x Dt] · Xblk[128 rows x Dt]ᵀ   (A, B from smem, K-major)
+//   GEMM2  Gt[128 chains x Dt]      += R[128 x 128 rows] · Xblk[128 rows x Dt] (A from TMEM, B = same smem
+//                                                                               tile read MN-major)
+// fp32 accuracy on bf16 tensor cores: X is exact in bf16 (checked at set-up), the
+// per-chain operands are split in two bf16 terms (β = βh + βl, r = rh + rl) and
+// accumulated in fp32; the TMEM accumulator of GEMM2 is flushed every
+// `flush_every` row blocks and summed outside the tensor core.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// warps 2-5 elementwise/epilogue (TMEM lane group = warp % 4).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+
+#include "logistic_tc.h"
+
+namespace bn {
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int ROWS = 128;            // data rows per block (GEMM1 N, GEMM2 K)
+constexpr int CHAINS = 128;          // chains per CTA (MMA M)
+constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 64 bf16 (one SW128 box)
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(const void* tmap, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] · B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] · B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, 128-byte swizzle (layout_type 2), descriptor version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major operand tile [128 rows][64 k] (+k-chunks 16 KB apart): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kk) {
+  return make_desc(tile + (uint32_t)(kk >> 2) * CHUNK_BYTES + (uint32_t)(kk & 3) * 32u, 16u, 1024u);
+}
+// MN-major operand: the same tile read as [K = rows][MN = columns]; 64-column chunks
+// are 16 KB apart (LBO), 8-row groups 1024 B apart (SBO); one MMA consumes 16 rows
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) {
+  return make_desc(tile + (uint32_t)kk * 2048u, (uint32_t)CHUNK_BYTES, 1024u);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// two floats -> packed bf16x2 (lo = a, hi = b), round to nearest even
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+template <int DT> struct SmemPlan {
+  static constexpr int KC = DT / 64;
+  static constexpr int B_BYTES = KC * CHUNK_BYTES;   // one β term
+  static constexpr int X_BYTES = KC * CHUNK_BYTES;   // one X stage
+  static constexpr int NS = (DT == 128) ? 4 : 6;
+  static constexpr int OFF_BH = 0;
+  static constexpr int OFF_BL = B_BYTES;
+  static constexpr int OFF_X = 2 * B_BYTES;
+  static constexpr int OFF_Y = OFF_X + NS * X_BYTES;
+  static constexpr int OFF_BAR = OFF_Y + NS * ROWS * 4;
+  static constexpr int NBAR = 1 + 2 * NS + 6 + 2;
+  static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
+};
+
+template <int DT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
+              const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ y, float* G, float* L, int C, int Dp,
+              long long N, int nblk_total, int nsplit, int flush_every) {
+  using P = SmemPlan<DT>;
+  constexpr int NS = P::NS;
+  constexpr int KC = P::KC;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SW128 needs 1024 B alignment
+  unsigned char* sBh = smem + P::OFF_BH;
+  unsigned char* sBl = smem + P::OFF_BL;
+  unsigned char* sX = smem + P::OFF_X;
+  float* sY = reinterpret_cast<float*>(smem + P::OFF_Y);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
+  uint64_t* bar_b = bars;               // β tiles landed
+  uint64_t* x_full = bars + 1;          // [NS]
+  uint64_t* x_empty = x_full + NS;      // [NS]
+  uint64_t* s_full = x_empty + NS;      // [2] GEMM1 done
+  uint64_t* r_full = s_full + 2;        // [2] residual written to TMEM
+  uint64_t* sr_empty = r_full + 2;      // [2] GEMM2 done with the buffer
+  uint64_t* g_full = sr_empty + 2;      // accumulator complete for this flush period
+  uint64_t* g_empty = g_full + 1;       // accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int b0 = (int)(((long long)nblk_total * split) / nsplit);
+  const int b1 = (int)(((long long)nblk_total * (split + 1)) / nsplit);
+  const int nb = b1 - b0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_b, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 128); mbar_init(&sr_empty[i], 1); }
+    mbar_init(g_full, 1);
+    mbar_init(g_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S = tmem;              // 2 x 128 columns (S, overwritten in place by R)
+  const uint32_t tmem_G = tmem + 256;        // DT columns
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0 && nb > 0) {
+      mbar_expect_tx(bar_b, 2 * P::B_BYTES);
+      for (int kc = 0; kc < KC; ++kc) {
+        tma_load_2d(&tmBh, sBh + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+        tma_load_2d(&tmBl, sBl + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+      }
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS;
+        const uint32_t ph = (uint32_t)(i / NS) & 1u;
+        mbar_wait(&x_empty[st], ph ^ 1u);
+        mbar_expect_tx(&x_full[st], P::X_BYTES + ROWS * 4);
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK_BYTES, &x_full[st], kc * 64, (b0 + i) * ROWS);
+        bulk_load_1d(sY + st * ROWS, y + (size_t)(b0 + i) * ROWS, ROWS * 4, &x_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0 && nb > 0) {
+      constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DT >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t aBh = smem_u32(sBh), aBl = smem_u32(sBl), aX = smem_u32(sX);
+      mbar_wait(bar_b, 0);
+      auto gemm1 = [&](int i) {
+        const int st = i % NS, buf = i & 1, u = i >> 1;
+        mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
+        if (u >= 1) mbar_wait(&sr_empty[buf], (uint32_t)(u - 1) & 1u);
+        tc_fence_after();
+        const uint32_t xt = aX + (uint32_t)st * P::X_BYTES;
+        const uint32_t d = tmem_S + (uint32_t)buf * 128u;
+#pragma unroll
+        for (int kk = 0; kk < DT / 16; ++kk) mma_ss(d, desc_kmajor(aBh, kk), desc_kmajor(xt, kk), IDESC1, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < DT / 16; ++kk) mma_ss(d, desc_kmajor(aBl, kk), desc_kmajor(xt, kk), IDESC1, 1u);
+        tc_commit(&s_full[buf]);
+      };
+      gemm1(0);
+      int period = 0, in_period = 0;
+      for (int i = 0; i < nb; ++i) {
+        if (i + 1 < nb) gemm1(i + 1);
+        const int st = i % NS, buf = i & 1, u = i >> 1;
+        mbar_wait(&r_full[buf], (uint32_t)u & 1u);
+        if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
+        tc_fence_after();
+        const uint32_t xt = aX + (uint32_t)st * P::X_BYTES;
+        const uint32_t a = tmem_S + (uint32_t)buf * 128u;
+#pragma unroll
+        for (int kk = 0; kk < ROWS / 16; ++kk)
+          mma_ts(tmem_G, a + (uint32_t)(kk >> 1) * 32u + (uint32_t)(kk & 1) * 8u, desc_mnmajor(xt, kk), IDESC2,
+                 (in_period > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < ROWS / 16; ++kk)
+          mma_ts(tmem_G, a + (uint32_t)(kk >> 1) * 32u + (uint32_t)(kk & 1) * 8u + 16u, desc_mnmajor(xt, kk), IDESC2, 1u);
+        tc_commit(&x_empty[st]);
+        tc_commit(&sr_empty[buf]);
+        ++in_period;
+        const bool last = (i + 1 == nb);
+        if (last || (flush_every > 0 && in_period == flush_every)) {
+          tc_commit(g_full);
+          ++period;
+          in_period = 0;
+        }
+      }
+    }
+  } else {
+    // ===================================================== elementwise + epilogue (128 threads)
+    const int q = warp & 3;                       // TMEM lane group of this warp
+    const int chain = tile * CHAINS + q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    double lsum = 0.0;
+    int period = 0, in_period = 0;
+    const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    for (int i = 0; i < nb; ++i) {
+      const int st = i % NS, buf = i & 1, u = i >> 1;
+      mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);   // y of this block is visible
+      mbar_wait(&s_full[buf], (uint32_t)u & 1u);
+      tc_fence_after();
+      const float* ys = sY + st * ROWS;
+      const long long row0 = (long long)(b0 + i) * ROWS;
+      const int nvalid = (N - row0 >= ROWS) ? ROWS : (int)(N - row0);
+      const uint32_t tS = tmem_S + (uint32_t)buf * 128u + lane_sel;
+      float bsum = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tS + (uint32_t)ch * 32u, v);
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float rr[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float eta = __uint_as_float(v[j + e]);
+            const float yy = ys[ch * 32 + j + e];
+            const float t = ex2_approx(-fabsf(eta) * LOG2E);
+            const float d = 1.0f + t;
+            const float s = rcp_approx(d);
+            const float sig = eta >= 0.f ? s : t * s;
+            const float sp = fmaxf(eta, 0.f) + LN2 * lg2_approx(d);
+            rr[e] = yy - sig;
+            const float lt = fmaf(yy, eta, -sp);
+            bsum += (ch * 32 + j + e < nvalid) ? lt : 0.f;
+          }
+          const uint32_t h = pack_bf16(rr[0], rr[1]);
+          const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xffff0000u);
+          hi[j >> 1] = h;
+          lo[j >> 1] = pack_bf16(rr[0] - h0, rr[1] - h1);
+        }
+        tmem_st16(tS + (uint32_t)ch * 32u, hi);
+        tmem_st16(tS + (uint32_t)ch * 32u + 16u, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&r_full[buf]);
+      lsum += (double)bsum;
+      ++in_period;
+      const bool last = (i + 1 == nb);
+      if (last || (flush_every > 0 && in_period == flush_every)) {
+        // drain the GEMM2 accumulator of this period and add it outside the tensor core
+        mbar_wait(g_full, (uint32_t)period & 1u);
+        tc_fence_after();
+        float* g = G + ((size_t)split * C + (size_t)chain) * Dp;
+#pragma unroll 1
+        for (int ch = 0; ch < DT / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, v);
+          tmem_ld_wait();
+          if (chain < C) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int d = ch * 32 + j;
+              if (d < Dp) {
+                const float add = __uint_as_float(v[j]);
+                g[d] = (period == 0) ? add : g[d] + add;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(g_empty);
+        ++period;
+        in_period = 0;
+      }
+    }
+    if (chain < C) {
+      if (nb == 0) {
+        float* g = G + ((size_t)split * C + (size_t)chain) * Dp;
+        for (int d = 0; d < Dp; ++d) g[d] = 0.f;
+      }
+      L[(size_t)split * C + chain] = (float)lsum;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 matrix [rows][cols] row-major, box = 128 rows x 64 columns, 128-byte swizzle
+bool encode_map(void* out, const void* base, uint64_t rows, uint64_t cols) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int DT> void launch(LogisticTC& tc, cudaStream_t s) {
+  using P = SmemPlan<DT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    tc.last = cudaFuncSetAttribute(k_logistic_tc<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL + 1024);
+    attr_done = true;
+  }
+  const int tiles = (tc.C + CHAINS - 1) / CHAINS;
+  dim3 grid(tiles, tc.nsplit);
+  CUtensorMap mX, mH, mL;
+  std::memcpy(&mX, tc.tmaps[0], sizeof(CUtensorMap));
+  std::memcpy(&mH, tc.tmaps[1], sizeof(CUtensorMap));
+  std::memcpy(&mL, tc.tmaps[2], sizeof(CUtensorMap));
+  k_logistic_tc<DT><<<grid, TC_THREADS, P::TOTAL + 1024, s>>>(mX, mH, mL, tc.yf, tc.G, tc.L, tc.C, tc.Dp, (long long)tc.N,
+                                                              (int)(tc.Npad / ROWS), tc.nsplit, tc.flush_every);
+}
+
+}  // namespace
+
+void LogisticTC::run(cudaStream_t s) {
+  if (!ready) return;
+  if (Dt == 64) launch<64>(*this, s); else launch<128>(*this, s);
+}
+void LogisticTC::destroy() {
+  if (Xb) cudaFree(Xb);
+  if (yf) cudaFree(yf);
+  Xb = nullptr; yf = nullptr; ready = false;
+}
+
+int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, int64_t N, int32_t C, int32_t D, int32_t Dp,
+                          std::string& err) {
+  tc.destroy();
+  tc.C = C; tc.D = D; tc.Dp = Dp; tc.N = N;
+  tc.Dt = (D <= 64) ? 64 : 128;
+  tc.Npad = (N + ROWS - 1) / ROWS * ROWS;
+  const char* fe = std::getenv("BNUTS_TC_FLUSH");
+  if (fe) tc.flush_every = std::atoi(fe);
+  std::vector<uint16_t> xp(size_t(tc.Npad) * tc.Dt, 0);
+  for (int64_t i = 0; i < N; ++i) std::memcpy(&xp[size_t(i) * tc.Dt], &Xh[size_t(i) * D], size_t(D) * 2);
+  std::vector<float> yp(size_t(tc.Npad), 0.f);
+  for (int64_t i = 0; i < N; ++i) yp[size_t(i)] = float(y[i]);
+  if (cudaMalloc(&tc.Xb, xp.size() * 2) != cudaSuccess || cudaMalloc(&tc.yf, yp.size() * 4) != cudaSuccess) {
+    err = "device allocation failed (tensor path X)";
+    return BNUTS_ERR_CUDA;
+  }
+  cudaMemcpy(tc.Xb, xp.data(), xp.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(tc.yf, yp.data(), yp.size() * 4, cudaMemcpyHostToDevice);
+  // split plan: one wave of CTAs over the SMs
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = (C + CHAINS - 1) / CHAINS;
+  int ns = sms / tiles;
+  if (ns < 1) ns = 1;
+  const int64_t nblk = tc.Npad / ROWS;
+  if (ns > nblk) ns = (int)nblk;
+  const char* se = std::getenv("BNUTS_TC_NSPLIT");
+  if (se) ns = std::atoi(se);
+  if (ns < 1) ns = 1;
+  tc.nsplit = ns;
+  return 0;
+}
+
+int32_t logistic_tc_maps(LogisticTC& tc, std::string& err) {
+  const uint64_t crow = (uint64_t)tc.C;
+  if (!encode_map(tc.tmaps[0], tc.Xb, (uint64_t)tc.Npad, (uint64_t)tc.Dt) ||
+      !encode_map(tc.tmaps[1], tc.bh, crow, (uint64_t)tc.Dt) || !encode_map(tc.tmaps[2], tc.bl, crow, (uint64_t)tc.Dt)) {
+    err = "cuTensorMapEncodeTiled failed";
+    return BNUTS_ERR_CUDA;
+  }
+  tc.ready = true;
+  return 0;
+}
+
+}  // namespace bn

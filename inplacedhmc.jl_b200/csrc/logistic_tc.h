@@ -1,0 +1,82 @@
+// logistic_tc.h — host interface of the tcgen05/TMA logistic-regression gradient
+// kernel (logistic_tc.cu).  fp32 engine only; X must lie on the bf16 grid.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/bnuts.h"
+#include "backend.h"
+
+namespace bn {
+
+struct LogisticTC {
+  // problem
+  int32_t C = 0, D = 0, Dp = 0, Dt = 0;
+  int64_t N = 0, Npad = 0;
+  int32_t nsplit = 1;
+  int32_t flush_every = 8;   // row blocks per TMEM-accumulator flush (0 = only at the end)
+  // device buffers owned here
+  uint16_t* Xb = nullptr;    // [Npad][Dt] bf16
+  float* yf = nullptr;       // [Npad]
+  // borrowed from the engine
+  const uint16_t* bh = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
+  float* G = nullptr;        // [nsplit][C][Dp]
+  float* L = nullptr;        // [nsplit][C]
+  // opaque tensor maps (3 x CUtensorMap, 128 B each, 64 B aligned)
+  alignas(64) unsigned char tmaps[3][128];
+  bool ready = false;
+  cudaError_t last = cudaSuccess;
+
+  void run(cudaStream_t s);
+  void destroy();
+};
+
+// build device copies of X (bf16, padded) and y, the tensor maps and the split plan
+int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xbf16_host /*[N][D]*/, const double* y, int64_t N,
+                          int32_t C, int32_t D, int32_t Dp, std::string& err);
+
+int32_t logistic_tc_maps(LogisticTC& tc, std::string& err);
+
+template <class E>
+int32_t logistic_tc_setup(LogisticTC& tc, E& eng, const void* Xh, int32_t xd, const double* y, int64_t N, std::string& err) {
+  using T = typename std::remove_reference<decltype(*eng.M.zs)>::type;
+  if constexpr (!std::is_same<T, float>::value) {
+    err = "tensor gradient path needs dtype F32";
+    return BNUTS_ERR_UNSUPPORTED;
+  } else {
+    auto& M = eng.M;
+    if (M.D > 128) { err = "tensor gradient path supports D <= 128 in this build"; return BNUTS_ERR_UNSUPPORTED; }
+    // X must be exactly representable in bf16 (the data operand of the MMA is not split)
+    const size_t n = size_t(N) * M.D;
+    std::vector<uint16_t> xb(n);
+    for (size_t i = 0; i < n; ++i) {
+      if (xd == BNUTS_X_BF16) { xb[i] = static_cast<const uint16_t*>(Xh)[i]; continue; }
+      const double v = xd == BNUTS_X_F64 ? static_cast<const double*>(Xh)[i] : double(static_cast<const float*>(Xh)[i]);
+      const uint16_t h = bf16_bits(float(v));
+      if (double(bf16_val(h)) != v) {
+        err = "tensor gradient path needs X on the bf16 grid (element not representable); use BNUTS_GRAD_DETERMINISTIC";
+        return BNUTS_ERR_UNSUPPORTED;
+      }
+      xb[i] = h;
+    }
+    int32_t rc = logistic_tc_build(tc, xb.data(), y, N, M.C, M.D, M.Dp, err);
+    if (rc) return rc;
+    // staging owned by the engine: bf16 hi/lo of q, partial outputs
+    M.Dt = tc.Dt;
+    M.stage_bh = eng.x.template alloc<uint16_t>(size_t(M.C) * tc.Dt);
+    M.stage_bl = eng.x.template alloc<uint16_t>(size_t(M.C) * tc.Dt);
+    eng.x.zero(M.stage_bh, size_t(M.C) * tc.Dt * 2);
+    eng.x.zero(M.stage_bl, size_t(M.C) * tc.Dt * 2);
+    eng.alloc_stage(tc.nsplit);
+    tc.bh = M.stage_bh; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.L = M.stage_l;
+    rc = logistic_tc_maps(tc, err);
+    if (rc) return rc;
+    eng.model.Npad = tc.Npad;
+    return 0;
+  }
+}
+
+}  // namespace bn

@@ -1,0 +1,147 @@
+"""GPU parity tests proper: the CUDA engine, through the C ABI, against the CPU oracle.
+
+Deterministic gradient path: bit-for-bit in fp64 and fp32, free-running (no teacher
+forcing) over search + windowed warmup + sampling.  Tensor-core path (fp32 variant):
+per-leapfrog positions/gradients within 1e-5 relative (BASELINE.json north_star) and
+teacher-forced tree decisions.
+"""
+import numpy as np
+import pytest
+
+from conftest import run_protocol, assert_bitwise, make_logistic, set_model
+
+pytestmark = pytest.mark.gpu
+F64, F32 = 0, 1
+DET, TENSOR = 1, 2
+TOL32 = 1e-5   # north_star: 1e-5 relative for the fp32 variant
+
+
+@pytest.mark.parametrize("dtype", [F64, F32])
+@pytest.mark.parametrize("kind", ["iid", "funnel", "gauss", "logit"])
+def test_cuda_full_protocol_bitwise(bn, oracle_lib, cuda_lib, kind, dtype):
+    a = run_protocol(bn, oracle_lib, kind, dtype)
+    b = run_protocol(bn, cuda_lib, kind, dtype, gradient_path=DET)
+    assert_bitwise(a, b)
+
+
+@pytest.mark.parametrize("dtype", [F64, F32])
+def test_cuda_ragged_funnel_bitwise(bn, oracle_lib, cuda_lib, dtype):
+    outs = []
+    for lib in (oracle_lib, cuda_lib):
+        e = bn.Engine(300, 100, dtype=dtype, max_depth=8, lib=lib, seed=5)
+        e.model_funnel()
+        e.set_positions(None)
+        e.set_stepsize(np.linspace(0.02, 0.9, 300))
+        ch, st, sel = e.sample(25, want_index=True)
+        outs.append([ch, st, sel])
+    assert_bitwise(outs[0], outs[1])
+    st = outs[0][1]
+    assert (st["term_left"] == st["term_right"]).any() and len(np.unique(st["depth"])) >= 5
+
+
+def test_cuda_odd_shapes_bitwise(bn, oracle_lib, cuda_lib):
+    """D not a multiple of 32, a single chain, C not a multiple of the CTA size."""
+    for (C, D) in [(1, 1), (5, 33), (130, 7)]:
+        a = run_protocol(bn, oracle_lib, "gauss", F64, C=C, D=D, max_depth=5, stages=((22, 1),), n_draws=15)
+        b = run_protocol(bn, cuda_lib, "gauss", F64, C=C, D=D, max_depth=5, stages=((22, 1),), n_draws=15, gradient_path=DET)
+        assert_bitwise(a, b)
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(b, axis=-1), 1e-30)
+
+
+@pytest.mark.parametrize("N,D,C", [(2000, 100, 200), (128, 64, 128), (1000, 17, 3), (5000, 128, 257)])
+def test_tensor_gradient_within_tolerance(bn, oracle_lib, cuda_lib, N, D, C):
+    X, y, beta = make_logistic(N, D)
+    rng = np.random.default_rng(1)
+    q = beta[None, :] + rng.normal(size=(C, D)) * 0.3
+    q[0] = 0.0
+    ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0, row_blocks=1); ref.set_positions(q)
+    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0); tc.set_positions(q)
+    _, g0, l0 = ref.get_state()
+    _, g1, l1 = tc.get_state()
+    assert np.max(_rel(g1, g0)) < TOL32, np.max(_rel(g1, g0))
+    assert np.max(np.abs(l1 - l0) / np.abs(l0)) < TOL32
+    # known answer at beta = 0: grad = X'(y - 1/2), l = -N log 2
+    np.testing.assert_allclose(g1[0], (y - 0.5) @ X, rtol=1e-5, atol=1e-4)
+    assert l1[0] == pytest.approx(-N * np.log(2), rel=1e-6)
+
+
+def test_tensor_per_leapfrog_parity(bn, oracle_lib, cuda_lib):
+    N, D, C = 3000, 100, 256
+    X, y, beta = make_logistic(N, D)
+    rng = np.random.default_rng(2)
+    q = beta[None, :] + rng.normal(size=(C, D)) * 0.05
+    p = rng.normal(size=(C, D)) * np.sqrt(N) * 0.5
+    ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0); ref.set_positions(q)
+    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0); tc.set_positions(q)
+    for eps, n in [(1e-3, 1), (2e-3, 4), (-1e-3, 3)]:
+        a = ref.leapfrog(p, eps, n); b = tc.leapfrog(p, eps, n)
+        assert np.max(_rel(b[0], a[0])) < TOL32
+        assert np.max(_rel(b[1], a[1])) < 5 * TOL32      # momentum accumulates n gradient errors
+        assert np.max(_rel(b[2], a[2])) < 5 * TOL32
+
+
+def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib):
+    """Restart both sides from the oracle's state every transition, same injected
+    momentum and directions; decisions may differ only when a compared quantity is
+    within fp32 rounding of its threshold."""
+    N, D, C, T = 2000, 50, 128, 12
+    X, y, beta = make_logistic(N, D)
+    rng = np.random.default_rng(3)
+    ref = bn.Engine(C, D, dtype=F32, lib=oracle_lib, max_depth=6); ref.model_logistic(X, y, 1.0)
+    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, max_depth=6, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0)
+    q = beta[None, :] + rng.normal(size=(C, D)) * 0.05
+    agree = total = 0
+    for t in range(T):
+        p = rng.normal(size=(1, C, D))
+        dirs = rng.integers(0, 2 ** 32, size=(1, C), dtype=np.uint64).astype(np.uint32)
+        for e in (ref, tc):
+            e.seed(77, t); e.set_positions(q); e.set_stepsize(0.02); e.inject(1, dirs, p)
+        ca, sa, ia = ref.sample(1, want_index=True)
+        cb, sb, ib = tc.sample(1, want_index=True)
+        same = (sa["depth"] == sb["depth"]) & (sa["steps"] == sb["steps"]) & (sa["term_left"] == sb["term_left"]) & \
+               (sa["term_right"] == sb["term_right"]) & (ia == ib)
+        agree += int(same.sum()); total += same.size
+        ok = same[:, 0]
+        assert np.max(_rel(cb[ok, 0], ca[ok, 0])) < 1e-4
+        q = ca[:, 0]
+    assert agree >= 0.97 * total, (agree, total)
+
+
+def test_tensor_full_size_known_answers(bn, cuda_lib):
+    """BASELINE config 3 shape (N=1e6, D=100): size-independent properties instead of an oracle run."""
+    N, D, C = 1_000_000, 100, 256
+    X, y, beta = make_logistic(N, D)
+    rng = np.random.default_rng(4)
+    q = np.zeros((C, D)); q[1:5] = beta + rng.normal(size=(4, D)) * 0.02
+    q[5:] = q[1 + (np.arange(C - 5) % 4)]            # replicate chains 1-4 across slots
+    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0); tc.set_positions(q)
+    _, g, l = tc.get_state()
+    # beta = 0: exact answer from one fp64 mat-vec
+    np.testing.assert_allclose(g[0], (y - 0.5) @ X, rtol=1e-5, atol=1e-3)
+    assert l[0] == pytest.approx(-N * np.log(2), rel=1e-6)
+    # four random chains against numpy fp64
+    eta = X @ q[1:5].T
+    gref = ((y[:, None] - 1 / (1 + np.exp(-eta))).T @ X) - q[1:5]
+    lref = (y[:, None] * eta - np.logaddexp(0, eta)).sum(0) - 0.5 * (q[1:5] ** 2).sum(1)
+    assert np.max(_rel(g[1:5], gref)) < TOL32
+    assert np.max(np.abs(l[1:5] - lref) / np.abs(lref)) < 1e-6
+    # a chain's result does not depend on which slot/tile it sits in
+    for k in range(5, C):
+        assert g[k].tobytes() == g[1 + (k - 5) % 4].tobytes() and l[k] == l[1 + (k - 5) % 4]
+
+
+def test_cuda_sampling_moments_funnel_free_running(bn, cuda_lib):
+    """Posterior check on the device engine alone: funnel v ~ N(0, 3^2) within Monte-Carlo error."""
+    C, D = 512, 10
+    e = bn.Engine(C, D, dtype=F64, lib=cuda_lib, seed=8)
+    e.model_funnel(); e.set_positions(None); e.find_initial_stepsize()
+    for N, mk in [(75, 0), (25, 1), (50, 1), (100, 1), (50, 0)]:
+        e.warmup_stage(N, mk, delta=0.95, keep=False)
+    ch, st = e.sample(200)
+    v = ch[:, :, 0]
+    assert abs(v.mean()) < 0.5 and 2.2 < v.std() < 3.5
+    c = e.counters()
+    assert c["leapfrogs"] >= st["steps"].sum() and c["kernel_launches"] > 0

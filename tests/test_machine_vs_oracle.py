@@ -1,0 +1,75 @@
+"""The product's per-chain state machine, vector loops and host engine (compiled
+for the host by tests/hostemu) against the recursive oracle: everything bit-for-bit."""
+import numpy as np
+import pytest
+
+from conftest import run_protocol, assert_bitwise, set_model
+
+F64, F32 = 0, 1
+
+
+@pytest.mark.parametrize("dtype", [F64, F32])
+@pytest.mark.parametrize("kind", ["iid", "funnel", "gauss", "logit"])
+def test_full_protocol_bitwise(bn, oracle_lib, hostemu_lib, kind, dtype):
+    a = run_protocol(bn, oracle_lib, kind, dtype)
+    b = run_protocol(bn, hostemu_lib, kind, dtype)
+    assert_bitwise(a, b)
+
+
+@pytest.mark.parametrize("dtype", [F64, F32])
+def test_ragged_trees_divergences_and_max_depth(bn, oracle_lib, hostemu_lib, dtype):
+    """Funnel with a coarse fixed step: deep ragged trees, divergences and max-depth hits."""
+    outs = []
+    for lib in (oracle_lib, hostemu_lib):
+        e = bn.Engine(24, 10, dtype=dtype, max_depth=7, lib=lib, seed=5)
+        e.model_funnel()
+        e.set_positions(None)
+        e.set_stepsize(np.linspace(0.05, 1.2, 24))
+        ch, st, sel = e.sample(80, want_index=True)
+        outs.append([ch, st, sel, e.get_state()[0]])
+    assert_bitwise(outs[0], outs[1])
+    st = outs[0][1]
+    assert (st["term_left"] == st["term_right"]).any(), "no divergence exercised"
+    assert ((st["term_left"] == 1) & (st["term_right"] == 0)).any(), "max depth never reached"
+    assert ((st["term_left"] < st["term_right"])).any(), "no turning termination"
+    assert len(np.unique(st["depth"])) >= 4
+
+
+def test_injected_momenta_and_directions(bn, oracle_lib, hostemu_lib):
+    rng = np.random.default_rng(2)
+    Cn, D, T = 5, 33, 7
+    p = rng.normal(size=(T, Cn, D))
+    dirs = rng.integers(0, 2 ** 32, size=(T, Cn), dtype=np.uint64).astype(np.uint32)
+    outs = []
+    for lib in (oracle_lib, hostemu_lib):
+        e = bn.Engine(Cn, D, max_depth=6, lib=lib)
+        set_model(e, "gauss", D)
+        e.set_positions(rng.normal(size=(Cn, D)) * 0 + 0.3)
+        e.set_stepsize(0.21)
+        e.inject(T, dirs, p)
+        outs.append(list(e.sample(T + 3, want_index=True)))   # last 3 transitions fall back to Philox
+    assert_bitwise(outs[0], outs[1])
+
+
+def test_nonfinite_start_is_reported_per_chain(bn, oracle_lib, hostemu_lib):
+    for lib in (oracle_lib, hostemu_lib):
+        e = bn.Engine(3, 4, lib=lib)
+        e.model_funnel()
+        q = np.zeros((3, 4)); q[1, 0] = -800.0; q[1, 1] = 1e200   # exp(800)*1e400 -> non-finite
+        rc = e.set_positions(q, allow_nonfinite=True)
+        assert rc == -4
+        assert list(e.chain_status()) == [0, -4, 0]
+        with pytest.raises(bn.BnutsError):
+            e.set_positions(q)
+
+
+def test_chain_offset_makes_sharding_invisible(bn, hostemu_lib):
+    """Chains are keyed by global id: two engines of 3 chains == one engine of 6."""
+    def run(C, off):
+        e = bn.Engine(C, 8, max_depth=5, lib=hostemu_lib, seed=3, chain_offset=off)
+        e.model_funnel(); e.set_positions(None); e.set_stepsize(0.3)
+        return e.sample(20)
+    full = run(6, 0)
+    a, b = run(3, 0), run(3, 3)
+    assert np.concatenate([a[0], b[0]]).tobytes() == full[0].tobytes()
+    assert np.concatenate([a[1], b[1]]).tobytes() == full[1].tobytes()
