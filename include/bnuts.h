@@ -152,6 +152,10 @@ int32_t bnuts_sample(bnuts_engine* e, int32_t N,
                      int32_t* selected_index);
 
 int32_t bnuts_counters(bnuts_engine* e, bnuts_counter_block* out);
+/* Measurement hook (no reference counterpart): when enabled, every launch of the
+ * batched gradient kernel inside the run loop is bracketed by CUDA events on the
+ * engine's stream.  Returns and resets the accumulated device time and launch count. */
+int32_t bnuts_profile(bnuts_engine* e, int32_t enable, double* gradient_ms, int64_t* gradient_launches);
 /* per-chain numerical status: 0 ok, else a bnuts_status */
 int32_t bnuts_chain_status(bnuts_engine* e, int32_t* status /* [C] */);
 

@@ -56,7 +56,7 @@ EXPORTS = [
     "bnuts_model_gaussian", "bnuts_model_logistic", "bnuts_set_positions", "bnuts_get_state",
     "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed",
     "bnuts_inject", "bnuts_leapfrog", "bnuts_find_initial_stepsize", "bnuts_warmup_stage", "bnuts_sample",
-    "bnuts_counters", "bnuts_chain_status",
+    "bnuts_counters", "bnuts_profile", "bnuts_chain_status",
 ]
 
 _P = C.c_void_p
@@ -98,6 +98,7 @@ def load_library(path=None):
     lib.bnuts_sample.argtypes = [_P, C.c_int32, _P, C.c_int64, C.c_int64, _P, C.c_int64, _P]
     lib.bnuts_counters.argtypes = [_P, C.POINTER(CounterBlock)]
     lib.bnuts_chain_status.argtypes = [_P, _P]
+    lib.bnuts_profile.argtypes = [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for n in EXPORTS:
         if n != "bnuts_last_error":
             getattr(lib, n).restype = C.c_int32
@@ -232,6 +233,10 @@ class Engine:
                   allow=(-6,) if allow_fail else ())
         return chain, stats, eps
 
+    def sample_device_only(self, N):
+        """N transitions with no host output (draws/statistics stay on the device)."""
+        self._chk(self.lib.bnuts_sample(self.h, N, None, self.D, N * self.D, None, N, None))
+
     def sample(self, N, want_index=False, out=None):
         if out is None:
             chain = np.empty((self.C, N, self.D)); stats = np.zeros((self.C, N), dtype=TREE_STATS_DTYPE)
@@ -245,6 +250,12 @@ class Engine:
         cb = CounterBlock()
         self._chk(self.lib.bnuts_counters(self.h, C.byref(cb)))
         return {k: getattr(cb, k) for k, _ in CounterBlock._fields_}
+
+    def profile(self, enable=True):
+        """Returns (gradient_ms, gradient_launches) accumulated since the last call, then (re)arms."""
+        ms = C.c_double(); n = C.c_int64()
+        self._chk(self.lib.bnuts_profile(self.h, 1 if enable else 0, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def chain_status(self):
         s = np.zeros(self.C, dtype=np.int32)

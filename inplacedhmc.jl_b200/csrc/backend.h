@@ -32,6 +32,7 @@ template <class T> struct EngineMem {
   T* stage_q;            // [C][Dp]   position to evaluate
   T* stage_g;            // [NB][C][Dp] gradient (partials over NB row blocks / splits)
   T* stage_l;            // [NB][C]   log-density partials
+  double* stage_ld;      // [NB][C]   Float64 log-density partials (tensor path), or null
   int32_t stage_nb;      // NB
   uint16_t* stage_bh;    // [C][Dt]   bf16 high part of q (tensor path), or null
   uint16_t* stage_bl;    // [C][Dt]   bf16 low part
@@ -277,7 +278,13 @@ template <class T, class LP> struct Backend {
           g[d] = fma_(-M.tau, q[d], acc);
         }
         T ls = T(0);
-        for (int b = 0; b < M.stage_nb; ++b) ls = ls + M.stage_l[(int64_t)b * M.C + c];
+        if (M.stage_ld) {  // tensor path: partials are ~1e5 in magnitude, summed in Float64
+          double lsd = 0.0;
+          for (int b = 0; b < M.stage_nb; ++b) lsd = lsd + M.stage_ld[(int64_t)b * M.C + c];
+          ls = T(lsd);
+        } else {
+          for (int b = 0; b < M.stage_nb; ++b) ls = ls + M.stage_l[(int64_t)b * M.C + c];
+        }
         l = fma_(T(-0.5) * M.tau, dot(q, q), ls);
         break;
       }

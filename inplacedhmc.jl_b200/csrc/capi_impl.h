@@ -114,6 +114,9 @@ int32_t bnuts_counters(bnuts_engine* e, bnuts_counter_block* out) {
   if (!out) return BNUTS_ERR_INVALID_ARGUMENT;
   BN_DISPATCH(e, get_counters(out));
 }
+int32_t bnuts_profile(bnuts_engine* e, int32_t enable, double* ms, int64_t* launches) {
+  BN_DISPATCH(e, x.profile(enable, ms, launches));
+}
 int32_t bnuts_chain_status(bnuts_engine* e, int32_t* st) {
   if (!st) return BNUTS_ERR_INVALID_ARGUMENT;
   BN_DISPATCH(e, chain_status(st));

@@ -90,7 +90,7 @@ template <class T, class X> struct EngineCore {
   void destroy() {
     x.sync();
     void* ptrs[] = {M.zs, M.zlq, M.st_rho, M.st_psf, M.m_rho, M.m_psm, M.m_psp, M.ps_cur, M.Minv, M.W, M.cs,
-                    M.stage_q, M.stage_g, M.stage_l, M.stage_bh, M.stage_bl, M.draws, d_stats, d_sel, d_eps_hist,
+                    M.stage_q, M.stage_g, M.stage_l, M.stage_ld, M.stage_bh, M.stage_bl, M.draws, d_stats, d_sel, d_eps_hist,
                     d_inj_dirs, d_inj_p, d_tmp_cd, d_tmp_c, model.P, model.X, model.y, model.Xb, model.yf};
     for (void* p : ptrs) if (p) x.free(p);
     x.shutdown();
@@ -99,7 +99,8 @@ template <class T, class X> struct EngineCore {
   // ---------------------------------------------------------------- models
   void free_model() {
     void** ps[] = {(void**)&model.P, (void**)&model.X, (void**)&model.y, (void**)&model.Xb, (void**)&model.yf,
-                   (void**)&M.stage_q, (void**)&M.stage_g, (void**)&M.stage_l, (void**)&M.stage_bh, (void**)&M.stage_bl};
+                   (void**)&M.stage_q, (void**)&M.stage_g, (void**)&M.stage_l, (void**)&M.stage_ld, (void**)&M.stage_bh,
+                   (void**)&M.stage_bl};
     for (void** p : ps) if (*p) { x.free(*p); *p = nullptr; }
     model = ModelCtx<T>();
     M.stage_nb = 0;

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "engine_core.h"
 #include "logistic_tc.h"
@@ -179,6 +180,36 @@ struct CudaExec {
   int32_t* d_status = nullptr;
   int device = 0;
   LogisticTC tc;
+  // measurement hook: CUDA-event pairs around the batched gradient launches
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  size_t ev_used = 0;
+  double prof_ms = 0.0;
+  int64_t prof_n = 0;
+  void prof_fold() {
+    if (ev_used == 0) return;
+    note(cudaStreamSynchronize(stream), "profile sync");
+    for (size_t i = 0; i + 1 < ev_used; i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) { prof_ms += ms; prof_n += 1; }
+    }
+    ev_used = 0;
+  }
+  int32_t profile(int32_t enable, double* ms, int64_t* n) {
+    prof_fold();
+    if (ms) *ms = prof_ms;
+    if (n) *n = prof_n;
+    prof_ms = 0.0; prof_n = 0;
+    profiling = enable != 0;
+    return 0;
+  }
+  cudaEvent_t next_event() {
+    if (ev_used == ev.size()) {
+      if (ev.size() >= 16384) prof_fold();
+      else { cudaEvent_t e; note(cudaEventCreate(&e), "event create"); ev.push_back(e); }
+    }
+    return ev[ev_used++];
+  }
 
   void note(cudaError_t e, const char* where) {
     if (e != cudaSuccess && first_err == cudaSuccess) { first_err = e; first_where = where; }
@@ -199,6 +230,7 @@ struct CudaExec {
     if (d_scal) cudaFree(d_scal);
     if (h_scal) cudaFreeHost(h_scal);
     if (d_status) cudaFree(d_status);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
   }
   template <class U> U* alloc(size_t n) {
     void* p = nullptr;
@@ -233,6 +265,11 @@ struct CudaExec {
     return (int64_t)h_scal[0];
   }
   template <class E> void gradient(E& eng) {
+    if (profiling) note(cudaEventRecord(next_event(), stream), "event record");
+    gradient_launch(eng);
+    if (profiling) note(cudaEventRecord(next_event(), stream), "event record");
+  }
+  template <class E> void gradient_launch(E& eng) {
     auto& M = eng.M;
     using T = typename std::remove_reference<decltype(*M.zs)>::type;
     if (eng.model.kind == MODEL_GAUSSIAN) {

@@ -20,8 +20,8 @@
 // accumulated in fp32; the TMEM accumulator of GEMM2 is flushed every
 // `flush_every` row blocks and summed outside the tensor core.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2-5 elementwise/epilogue (TMEM lane group = warp % 4).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// warps 2-9 elementwise/epilogue (TMEM lane group = warp % 4, two warps per group).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -33,7 +33,7 @@ namespace bn {
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
 constexpr int ROWS = 128;            // data rows per block (GEMM1 N, GEMM2 K)
 constexpr int CHAINS = 128;          // chains per CTA (MMA M)
 constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 64 bf16 (one SW128 box)
@@ -174,7 +174,7 @@ template <int DT> struct SmemPlan {
 template <int DT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
-              const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ y, float* G, float* L, int C, int Dp,
+              const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ y, float* G, double* Ld, int C, int Dp,
               long long N, int nblk_total, int nsplit, int flush_every) {
   using P = SmemPlan<DT>;
   constexpr int NS = P::NS;
@@ -205,9 +205,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (threadIdx.x == 0) {
     mbar_init(bar_b, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 128); mbar_init(&sr_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 256); mbar_init(&sr_empty[i], 1); }
     mbar_init(g_full, 1);
-    mbar_init(g_empty, 128);
+    mbar_init(g_empty, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -288,49 +288,56 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
     }
   } else {
-    // ===================================================== elementwise + epilogue (128 threads)
-    const int q = warp & 3;                       // TMEM lane group of this warp
+    // ===================================================== elementwise + epilogue (8 warps)
+    // TMEM lane group q = warp % 4 (hardware rule); the two warps of a lane group split
+    // the 128 data rows of a block: half h handles S columns [64h, 64h+64).
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
     const int chain = tile * CHAINS + q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     double lsum = 0.0;
     int period = 0, in_period = 0;
-    const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    const float NLOG2E = -1.4426950408889634f, LN2 = 0.6931471805599453f;
     for (int i = 0; i < nb; ++i) {
       const int st = i % NS, buf = i & 1, u = i >> 1;
       mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);   // y of this block is visible
       mbar_wait(&s_full[buf], (uint32_t)u & 1u);
       tc_fence_after();
-      const float* ys = sY + st * ROWS;
-      const long long row0 = (long long)(b0 + i) * ROWS;
-      const int nvalid = (N - row0 >= ROWS) ? ROWS : (int)(N - row0);
+      const float4* ys4 = reinterpret_cast<const float4*>(sY + st * ROWS);
       const uint32_t tS = tmem_S + (uint32_t)buf * 128u + lane_sel;
       float bsum = 0.f;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int ch = 2 * h + cc;
         uint32_t v[32];
         tmem_ld32(tS + (uint32_t)ch * 32u, v);
         tmem_ld_wait();
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float rr[2];
+        for (int g8 = 0; g8 < 4; ++g8) {       // 8 elements share one lg2 (log of a product)
+          const float4 ya = ys4[ch * 8 + g8 * 2], yb = ys4[ch * 8 + g8 * 2 + 1];
+          const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+          float prod = 1.f;
+          float rr[8];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float eta = __uint_as_float(v[j + e]);
-            const float yy = ys[ch * 32 + j + e];
-            const float t = ex2_approx(-fabsf(eta) * LOG2E);
+          for (int e = 0; e < 8; ++e) {
+            const float eta = __uint_as_float(v[g8 * 8 + e]);
+            const float t = ex2_approx(fabsf(eta) * NLOG2E);
             const float d = 1.0f + t;
+            prod *= d;
             const float s = rcp_approx(d);
             const float sig = eta >= 0.f ? s : t * s;
-            const float sp = fmaxf(eta, 0.f) + LN2 * lg2_approx(d);
-            rr[e] = yy - sig;
-            const float lt = fmaf(yy, eta, -sp);
-            bsum += (ch * 32 + j + e < nvalid) ? lt : 0.f;
+            rr[e] = yy[e] - sig;
+            bsum = fmaf(eta, yy[e] - (eta > 0.f ? 1.f : 0.f), bsum);   // y*eta - max(eta, 0)
           }
-          const uint32_t h = pack_bf16(rr[0], rr[1]);
-          const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xffff0000u);
-          hi[j >> 1] = h;
-          lo[j >> 1] = pack_bf16(rr[0] - h0, rr[1] - h1);
+          bsum = fmaf(-LN2, lg2_approx(prod), bsum);                    // - sum log(1 + t)
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const uint32_t hh = pack_bf16(rr[e], rr[e + 1]);
+            const float h0 = __uint_as_float(hh << 16), h1 = __uint_as_float(hh & 0xffff0000u);
+            hi[(g8 * 8 + e) >> 1] = hh;
+            lo[(g8 * 8 + e) >> 1] = pack_bf16(rr[e] - h0, rr[e + 1] - h1);
+          }
         }
         tmem_st16(tS + (uint32_t)ch * 32u, hi);
         tmem_st16(tS + (uint32_t)ch * 32u + 16u, lo);
@@ -347,17 +354,21 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         tc_fence_after();
         float* g = G + ((size_t)split * C + (size_t)chain) * Dp;
 #pragma unroll 1
-        for (int ch = 0; ch < DT / 32; ++ch) {
+        for (int cc = 0; cc < DT / 64; ++cc) {
+          const int ch = h * (DT / 64) + cc;
           uint32_t v[32];
           tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, v);
           tmem_ld_wait();
           if (chain < C) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 32; j += 4) {
               const int d = ch * 32 + j;
               if (d < Dp) {
-                const float add = __uint_as_float(v[j]);
-                g[d] = (period == 0) ? add : g[d] + add;
+                float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3]));
+                float4* gp = reinterpret_cast<float4*>(g + d);
+                if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+                *gp = a;
               }
             }
           }
@@ -368,12 +379,20 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         in_period = 0;
       }
     }
-    if (chain < C) {
+    // rows >= N of the last block are zero padding: eta = 0, y = 0 -> each contributed -log 2
+    if (h == 1 && b1 == nblk_total) lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
+    // combine the two halves of each chain and publish
+    float* lpart = reinterpret_cast<float*>(smem + P::OFF_Y);   // y stages are dead by now
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    double* lp = reinterpret_cast<double*>(lpart);
+    if (h == 1) lp[q * 32 + lane] = lsum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (h == 0 && chain < C) {
       if (nb == 0) {
         float* g = G + ((size_t)split * C + (size_t)chain) * Dp;
         for (int d = 0; d < Dp; ++d) g[d] = 0.f;
       }
-      L[(size_t)split * C + chain] = (float)lsum;
+      Ld[(size_t)split * C + chain] = lsum + lp[q * 32 + lane];
     }
   }
   tc_fence_before();
@@ -426,7 +445,7 @@ template <int DT> void launch(LogisticTC& tc, cudaStream_t s) {
   std::memcpy(&mX, tc.tmaps[0], sizeof(CUtensorMap));
   std::memcpy(&mH, tc.tmaps[1], sizeof(CUtensorMap));
   std::memcpy(&mL, tc.tmaps[2], sizeof(CUtensorMap));
-  k_logistic_tc<DT><<<grid, TC_THREADS, P::TOTAL + 1024, s>>>(mX, mH, mL, tc.yf, tc.G, tc.L, tc.C, tc.Dp, (long long)tc.N,
+  k_logistic_tc<DT><<<grid, TC_THREADS, P::TOTAL + 1024, s>>>(mX, mH, mL, tc.yf, tc.G, tc.Ld, tc.C, tc.Dp, (long long)tc.N,
                                                               (int)(tc.Npad / ROWS), tc.nsplit, tc.flush_every);
 }
 

@@ -24,7 +24,7 @@ struct LogisticTC {
   // borrowed from the engine
   const uint16_t* bh = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
   float* G = nullptr;        // [nsplit][C][Dp]
-  float* L = nullptr;        // [nsplit][C]
+  double* Ld = nullptr;      // [nsplit][C] log-density partials (Float64: ~1e5..1e6 in magnitude)
   // opaque tensor maps (3 x CUtensorMap, 128 B each, 64 B aligned)
   alignas(64) unsigned char tmaps[3][128];
   bool ready = false;
@@ -71,7 +71,9 @@ int32_t logistic_tc_setup(LogisticTC& tc, E& eng, const void* Xh, int32_t xd, co
     eng.x.zero(M.stage_bh, size_t(M.C) * tc.Dt * 2);
     eng.x.zero(M.stage_bl, size_t(M.C) * tc.Dt * 2);
     eng.alloc_stage(tc.nsplit);
-    tc.bh = M.stage_bh; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.L = M.stage_l;
+    M.stage_ld = eng.x.template alloc<double>(size_t(M.C) * tc.nsplit);
+    eng.x.zero(M.stage_ld, size_t(M.C) * tc.nsplit * sizeof(double));
+    tc.bh = M.stage_bh; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.Ld = M.stage_ld;
     rc = logistic_tc_maps(tc, err);
     if (rc) return rc;
     eng.model.Npad = tc.Npad;

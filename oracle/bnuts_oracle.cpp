@@ -771,6 +771,12 @@ int32_t bnuts_counters(bnuts_engine* e, bnuts_counter_block* out) {
   if (!out) return BNUTS_ERR_INVALID_ARGUMENT;
   DISPATCH(e, ([&] { *out = E.counters; return 0; })(), ([&] { *out = E.counters; return 0; })());
 }
+int32_t bnuts_profile(bnuts_engine* e, int32_t, double* ms, int64_t* n) {
+  if (!e) return BNUTS_ERR_INVALID_ARGUMENT;
+  if (ms) *ms = 0.0;
+  if (n) *n = 0;
+  return 0;
+}
 int32_t bnuts_chain_status(bnuts_engine* e, int32_t* st) {
   if (!st) return BNUTS_ERR_INVALID_ARGUMENT;
   DISPATCH(e, ([&] { std::copy(E.status.begin(), E.status.end(), st); return 0; })(),
