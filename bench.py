@@ -5,8 +5,10 @@
   python bench.py --gpus N --steps K --warmup W            our CUDA engine
   python bench.py --impl reference ...                      CPU restatement of the reference on host cores
 
-A "step" is one NUTS transition of every chain (one bnuts_sample(1) call): momentum
-refresh, tree building (leapfrog + gradient per leaf), selection, statistics.
+A "step" is `--transitions` NUTS transitions of every chain (one bnuts_sample call):
+momentum refresh, tree building (leapfrog + gradient per leaf), selection, statistics.
+Chains run their transitions asynchronously inside the call (a chain starts its next
+tree as soon as it finishes one); idle chains occupy no rows of the gradient kernel.
 `value` = leapfrog steps (Σ TreeStatisticsNUTS.steps, src/NUTS.jl:238-239) of all
 chains on all GPUs ÷ device time of the K timed steps, state resident in HBM.
 `e2e` = the same through the C ABI with host buffers: positions are uploaded and
@@ -127,7 +129,8 @@ def main():
     ap.add_argument("--chains", type=int, default=4096)
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=100)
-    ap.add_argument("--adapt", type=int, default=40, help="dual-averaging transitions before timing (untimed)")
+    ap.add_argument("--adapt", type=int, default=100, help="dual-averaging transitions before timing (untimed)")
+    ap.add_argument("--transitions", type=int, default=4, help="NUTS transitions per chain per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,8 +176,9 @@ def main():
     e.find_initial_stepsize()
     if a.adapt > 0:
         e.warmup_stage(a.adapt, bn.METRIC_NONE, keep=False)
+    T = a.transitions
     for _ in range(a.warmup):
-        e.sample_device_only(1)
+        e.sample_device_only(T)
 
     # ---------------- timed region 1: device-resident
     clocks = ClockSampler(local); clocks.start()
@@ -183,7 +187,7 @@ def main():
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
-        e.sample_device_only(1)
+        e.sample_device_only(T)
     ev1.record(); barrier()
     ms = allmax(ev0.elapsed_time(ev1))
     grad_ms, grad_n = e.profile(False)
@@ -196,15 +200,15 @@ def main():
     # ---------------- timed region 2: through the C ABI with host buffers
     qh = torch.empty((C, D), dtype=torch.float64).pin_memory().numpy()
     qh[:] = e.get_state()[0]
-    chain = torch.empty((C, 1, D), dtype=torch.float64).pin_memory().numpy()
-    stats = np.zeros((C, 1), dtype=bn.TREE_STATS_DTYPE)
+    chain = torch.empty((C, T, D), dtype=torch.float64).pin_memory().numpy()
+    stats = np.zeros((C, T), dtype=bn.TREE_STATS_DTYPE)
     barrier()
     t0 = time.perf_counter(); leap_e2e = 0
     for _ in range(a.steps):
         e.set_positions(qh)                       # H2D of this step's input positions (+ their gradient)
-        e.sample(1, out=(chain, stats))           # D2H of the draws and tree statistics
+        e.sample(T, out=(chain, stats))           # D2H of the draws and tree statistics
         leap_e2e += int(stats["steps"].sum())
-        qh[:] = chain[:, 0]
+        qh[:] = chain[:, T - 1]
     barrier()
     dt = allmax(time.perf_counter() - t0)
     e2e = allsum(leap_e2e) / dt
@@ -229,7 +233,10 @@ def main():
                    "chains_per_gpu": C, "parallelism": "chains sharded, no collective",
                    "l2": "inputs larger than L2 (X is %d MB bf16)" % (N * 128 * 2 // 2**20),
                    "init": "beta* + 2e-3 N(0,1); initial step size search + %d dual-averaging transitions untimed" % a.adapt,
-                   "step": "one NUTS transition of every chain"},
+                   "step": "%d NUTS transitions of every chain (async within the call)" % T,
+                   "mean_tree_depth": float(stats["depth"].mean()), "mean_leapfrogs_per_transition": float(stats["steps"].mean()),
+                   "lockstep_steps_timed": int(c1["lockstep_steps"] - c0["lockstep_steps"]),
+                   "active_row_fraction": float(leap / max(1, (c1["lockstep_steps"] - c0["lockstep_steps"]) * C * world))},
         "gpu_launches": int(launches),
         "leapfrogs_timed": int(leap),
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",

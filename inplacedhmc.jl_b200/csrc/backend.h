@@ -34,8 +34,14 @@ template <class T> struct EngineMem {
   T* stage_l;            // [NB][C]   log-density partials
   double* stage_ld;      // [NB][C]   Float64 log-density partials (tensor path), or null
   int32_t stage_nb;      // NB
-  uint16_t* stage_bh;    // [C][Dt]   bf16 high part of q (tensor path), or null
-  uint16_t* stage_bl;    // [C][Dt]   bf16 low part
+  uint16_t* stage_bh;    // [C][Dt]   bf16 high / middle / low 8 mantissa bits of q (tensor path), or null
+  uint16_t* stage_bm;
+  uint16_t* stage_bl;
+  // active-chain compaction: a chain that requests a gradient takes the next free
+  // staging row, so the batched kernels only see rows [0, stage_rows)
+  int32_t* stage_row;            // [C] row of each chain in the current request
+  unsigned long long* stage_count;  // rows handed out in the current lockstep step
+  int32_t stage_rows;            // rows of the request being consumed (stride of the partials)
   int32_t Dt;            // padded K of the tensor path
   T tau;                 // logistic prior precision
   // per-call outputs
@@ -61,6 +67,13 @@ struct SerialLanes {
   BN_HD int acc(int d) const { return d & 31; }
   BN_HD bool lane0() const { return true; }
   BN_HD void sync() const {}
+  BN_HD int alloc_row(unsigned long long* counter) const {
+#if defined(__CUDA_ARCH__)
+    return (int)atomicAdd(counter, 1ull);
+#else
+    return (int)__atomic_fetch_add(counter, 1ull, __ATOMIC_RELAXED);
+#endif
+  }
   template <class T> BN_HD T reduce(T* part) const {
     for (int off = 16; off >= 1; off >>= 1) {
       T nw[32];
@@ -82,6 +95,14 @@ struct WarpLanes {
 #if defined(__CUDA_ARCH__)
     __syncwarp();
 #endif
+  }
+  BN_HD int alloc_row(unsigned long long* counter) const {
+    int r = 0;
+#if defined(__CUDA_ARCH__)
+    if (lane == 0) r = (int)atomicAdd(counter, 1ull);
+    r = __shfl_sync(0xffffffffu, r, 0);
+#endif
+    return r;
   }
   template <class T> BN_HD T reduce(T* part) const {
     T v = part[0];
@@ -137,23 +158,38 @@ template <class T, class LP> struct Backend {
     lp.sync();
   }
 
+  // take a staging row for this chain's gradient request (batched targets only)
+  BN_HD int take_row() const {
+    if (!M.stage_q) return -1;
+    const int row = lp.alloc_row(M.stage_count);
+    if (lp.lane0()) M.stage_row[c] = row;
+    return row;
+  }
+  // publish one coordinate of the position to evaluate; the tensor path also gets the
+  // exact three-term bf16 split of the fp32 value (3 x 8 mantissa bits)
+  BN_HD void stage_put(int row, int d, T qd) const {
+    M.stage_q[(int64_t)row * M.Dp + d] = qd;
+    if (M.stage_bh) {
+      const float qf = (float)qd;
+      const uint16_t h = bf16_bits(qf);
+      const float r1 = qf - bf16_val(h);
+      const uint16_t m = bf16_bits(r1);
+      const int64_t o = (int64_t)row * M.Dt + d;
+      M.stage_bh[o] = h; M.stage_bm[o] = m; M.stage_bl[o] = bf16_bits(r1 - bf16_val(m));
+    }
+  }
+
   // ≙ src/kinetic_energy.jl:144-150: pₘ = p + ½ϵ∇ℓ ; q′ = q + ϵ M⁻¹ pₘ
   BN_HD void pre_kick_drift(int src, int dst, T eh, T eps) const {
     const T* q = zq(src); const T* p = zp(src); const T* g = zg(src);
     T* qn = zq(dst); T* pn = zp(dst);
     const T* Mi = cv(M.Minv);
-    T* sq = M.stage_q ? cv(M.stage_q) : nullptr;
+    const int row = take_row();
     for (int d = lp.first(); d < M.D; d += lp.stride()) {
       const T pm = fma_(eh, g[d], p[d]);
       const T qd = fma_(eps * Mi[d], pm, q[d]);
       pn[d] = pm; qn[d] = qd;
-      if (sq) sq[d] = qd;
-      if (M.stage_bh) {
-        const float qf = (float)qd;
-        const uint16_t h = bf16_bits(qf);
-        M.stage_bh[(int64_t)c * M.Dt + d] = h;
-        M.stage_bl[(int64_t)c * M.Dt + d] = bf16_bits(qf - bf16_val(h));
-      }
+      if (row >= 0) stage_put(row, d, qd);
     }
     lp.sync();
   }
@@ -263,15 +299,16 @@ template <class T, class LP> struct Backend {
         break;
       }
       case MODEL_GAUSSIAN: {
-        const T* sg = M.stage_g + (int64_t)c * M.Dp;
+        const T* sg = M.stage_g + (int64_t)M.stage_row[c] * M.Dp;
         for (int d = lp.first(); d < M.D; d += lp.stride()) g[d] = sg[d];
         lp.sync();
         l = T(0.5) * dot(q, g);
         break;
       }
       case MODEL_LOGISTIC: {
-        const int64_t bs = (int64_t)M.C * M.Dp;
-        const T* sg = M.stage_g + (int64_t)c * M.Dp;
+        const int64_t row = M.stage_row[c], rows = M.stage_rows;
+        const int64_t bs = rows * M.Dp;
+        const T* sg = M.stage_g + row * M.Dp;
         for (int d = lp.first(); d < M.D; d += lp.stride()) {
           T acc = T(0);
           for (int b = 0; b < M.stage_nb; ++b) acc = acc + sg[b * bs + d];
@@ -280,10 +317,10 @@ template <class T, class LP> struct Backend {
         T ls = T(0);
         if (M.stage_ld) {  // tensor path: partials are ~1e5 in magnitude, summed in Float64
           double lsd = 0.0;
-          for (int b = 0; b < M.stage_nb; ++b) lsd = lsd + M.stage_ld[(int64_t)b * M.C + c];
+          for (int b = 0; b < M.stage_nb; ++b) lsd = lsd + M.stage_ld[b * rows + row];
           ls = T(lsd);
         } else {
-          for (int b = 0; b < M.stage_nb; ++b) ls = ls + M.stage_l[(int64_t)b * M.C + c];
+          for (int b = 0; b < M.stage_nb; ++b) ls = ls + M.stage_l[b * rows + row];
         }
         l = fma_(T(-0.5) * M.tau, dot(q, q), ls);
         break;
@@ -319,17 +356,11 @@ template <class T, class LP> struct Backend {
   // set_positions: q -> slot (and staging); ≙ src/warmup.jl:119 / random_position! :73
   BN_HD void load_position(int slot, uint64_t seed, uint32_t gchain) const {
     T* q = zq(slot);
-    T* sq = M.stage_q ? cv(M.stage_q) : nullptr;
+    const int row = take_row();
     for (int d = lp.first(); d < M.D; d += lp.stride()) {
       const T qd = M.pos_in ? T(M.pos_in[(int64_t)c * M.D + d]) : T(init_position(seed, gchain, (uint32_t)d));
       q[d] = qd;
-      if (sq) sq[d] = qd;
-      if (M.stage_bh) {
-        const float qf = (float)qd;
-        const uint16_t h = bf16_bits(qf);
-        M.stage_bh[(int64_t)c * M.Dt + d] = h;
-        M.stage_bl[(int64_t)c * M.Dt + d] = bf16_bits(qf - bf16_val(h));
-      }
+      if (row >= 0) stage_put(row, d, qd);
     }
     lp.sync();
   }

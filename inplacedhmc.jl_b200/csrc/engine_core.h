@@ -90,7 +90,7 @@ template <class T, class X> struct EngineCore {
   void destroy() {
     x.sync();
     void* ptrs[] = {M.zs, M.zlq, M.st_rho, M.st_psf, M.m_rho, M.m_psm, M.m_psp, M.ps_cur, M.Minv, M.W, M.cs,
-                    M.stage_q, M.stage_g, M.stage_l, M.stage_ld, M.stage_bh, M.stage_bl, M.draws, d_stats, d_sel, d_eps_hist,
+                    M.stage_q, M.stage_g, M.stage_l, M.stage_ld, M.stage_bh, M.stage_bm, M.stage_bl, M.stage_row, M.draws, d_stats, d_sel, d_eps_hist,
                     d_inj_dirs, d_inj_p, d_tmp_cd, d_tmp_c, model.P, model.X, model.y, model.Xb, model.yf};
     for (void* p : ptrs) if (p) x.free(p);
     x.shutdown();
@@ -100,7 +100,7 @@ template <class T, class X> struct EngineCore {
   void free_model() {
     void** ps[] = {(void**)&model.P, (void**)&model.X, (void**)&model.y, (void**)&model.Xb, (void**)&model.yf,
                    (void**)&M.stage_q, (void**)&M.stage_g, (void**)&M.stage_l, (void**)&M.stage_ld, (void**)&M.stage_bh,
-                   (void**)&M.stage_bl};
+                   (void**)&M.stage_bm, (void**)&M.stage_bl, (void**)&M.stage_row};
     for (void** p : ps) if (*p) { x.free(*p); *p = nullptr; }
     model = ModelCtx<T>();
     M.stage_nb = 0;
@@ -110,15 +110,21 @@ template <class T, class X> struct EngineCore {
     model.kind = kind; M.model_kind = kind;
     return 0;
   }
-  void alloc_stage(int nb) {
+  // partial_rows = rows of the partial-output buffers (>= nb * C)
+  void alloc_stage(int nb, size_t partial_rows = 0) {
     const size_t CD = size_t(M.C) * M.Dp;
+    if (partial_rows < size_t(nb) * M.C) partial_rows = size_t(nb) * M.C;
     M.stage_nb = nb;
+    M.stage_rows = M.C;
     M.stage_q = x.template alloc<T>(CD);
-    M.stage_g = x.template alloc<T>(CD * nb);
-    M.stage_l = x.template alloc<T>(size_t(M.C) * nb);
+    M.stage_g = x.template alloc<T>(partial_rows * M.Dp);
+    M.stage_l = x.template alloc<T>(partial_rows);
+    M.stage_row = x.template alloc<int32_t>(M.C);
+    M.stage_count = x.counter();
     x.zero(M.stage_q, CD * sizeof(T));
-    x.zero(M.stage_g, CD * nb * sizeof(T));
-    x.zero(M.stage_l, size_t(M.C) * nb * sizeof(T));
+    x.zero(M.stage_g, partial_rows * M.Dp * sizeof(T));
+    x.zero(M.stage_l, partial_rows * sizeof(T));
+    x.zero(M.stage_row, size_t(M.C) * sizeof(int32_t));
   }
   int32_t model_gaussian(const double* P) {
     if (!P) return fail(BNUTS_ERR_INVALID_ARGUMENT, "precision is NULL");
@@ -203,16 +209,22 @@ template <class T, class X> struct EngineCore {
   // ---------------------------------------------------------------- run loop
   // Lockstep: [batched gradient] -> advance (consume leaf, merges, next leapfrog) -> ...
   // until every chain is idle.  Elementwise targets run inside advance().
+  // Only chains with a gradient request occupy staging rows (active-chain
+  // compaction), so the batched kernel cost follows the number of active chains.
   int32_t run(bool pending) {
     const bool batched = model.batched();
     const int iters = batched ? 1 : (1 << 30);
+    int64_t np = pending ? x.read_count() : 0;
     for (;;) {
-      if (pending && batched) { x.gradient(*this); counters.kernel_launches += 1; }
-      const int64_t np = x.advance(M, rp, iters);
+      if (np > 0 && batched) {
+        M.stage_nb = x.gradient(*this, (int)np);
+        M.stage_rows = (int32_t)np;
+        counters.kernel_launches += 1;
+      }
+      np = x.advance(M, rp, iters);
       counters.kernel_launches += 1;
       counters.lockstep_steps += 1;
-      pending = np > 0;
-      if (!pending) break;
+      if (np <= 0) break;
     }
     return x.check(err);
   }

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(EngineMem<T> M, RunPara
   if (c >= M.C) return;
   const int lane = (int)(threadIdx.x & 31);
   const bool p = advance_chain(M, rp, c, WarpLanes{lane}, iters);
-  if (p && lane == 0) atomicAdd(pending, 1ull);
+  if (p && lane == 0 && !M.stage_q) atomicAdd(pending, 1ull);  // batched targets count through take_row()
 }
 
 template <class T> __global__ void __launch_bounds__(ADV_THREADS) k_metric(EngineMem<T> M, int N, double lambda) {
@@ -251,8 +251,15 @@ struct CudaExec {
   }
   static int warp_grid(int C) { return (C * 32 + ADV_THREADS - 1) / ADV_THREADS; }
 
+  unsigned long long* counter() { return d_scal; }
+  int64_t read_count() {
+    note(cudaMemcpyAsync(h_scal, d_scal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "count d2h");
+    note(cudaStreamSynchronize(stream), "count sync");
+    return first_err == cudaSuccess ? (int64_t)h_scal[0] : 0;
+  }
   template <class T> void prepare(const EngineMem<T>& M, const RunParams<T>& rp, const PrepareArgs& a) {
     note(cudaSetDevice(device), "cudaSetDevice");
+    note(cudaMemsetAsync(d_scal, 0, sizeof(unsigned long long), stream), "memset");
     k_prepare<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, a);
   }
   template <class T> int64_t advance(const EngineMem<T>& M, const RunParams<T>& rp, int iters) {
@@ -264,30 +271,34 @@ struct CudaExec {
     if (first_err != cudaSuccess) return 0;
     return (int64_t)h_scal[0];
   }
-  template <class E> void gradient(E& eng) {
+  // evaluate the staged rows [0, rows); returns the number of partial blocks written per row
+  template <class E> int gradient(E& eng, int rows) {
     if (profiling) note(cudaEventRecord(next_event(), stream), "event record");
-    gradient_launch(eng);
+    const int nb = gradient_launch(eng, rows);
     if (profiling) note(cudaEventRecord(next_event(), stream), "event record");
+    return nb;
   }
-  template <class E> void gradient_launch(E& eng) {
+  template <class E> int gradient_launch(E& eng, int rows) {
     auto& M = eng.M;
     using T = typename std::remove_reference<decltype(*M.zs)>::type;
+    int nb = 1;
     if (eng.model.kind == MODEL_GAUSSIAN) {
-      dim3 grid((M.D + 63) / 64, (M.C + 63) / 64);
-      k_grad_gaussian<T><<<grid, 256, 0, stream>>>(eng.model.P, M.stage_q, M.stage_g, M.C, M.D, M.Dp);
+      dim3 grid((M.D + 63) / 64, (rows + 63) / 64);
+      k_grad_gaussian<T><<<grid, 256, 0, stream>>>(eng.model.P, M.stage_q, M.stage_g, rows, M.D, M.Dp);
     } else if (eng.model.kind == MODEL_LOGISTIC) {
-      if (eng.model.tensor) { tc.run(stream); }
+      if (eng.model.tensor) { tc.run(stream, rows); nb = tc.last_nsplit; }
       else {
-        const int nb = eng.model.row_blocks;
+        nb = eng.model.row_blocks;
         const int64_t R = (eng.model.N + nb - 1) / nb;
         const size_t smem = ((size_t)M.D * 64 + (size_t)8 * M.D + 8) * sizeof(T);
         note(cudaFuncSetAttribute(k_grad_logistic<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-        dim3 grid((M.C + 31) / 32, nb);
+        dim3 grid((rows + 31) / 32, nb);
         k_grad_logistic<T><<<grid, 32, smem, stream>>>(eng.model.X, eng.model.y, M.stage_q, M.stage_g, M.stage_l,
-                                                      eng.model.N, M.D, M.Dp, M.C, R);
+                                                      eng.model.N, M.D, M.Dp, rows, R);
       }
     }
     note(cudaGetLastError(), "gradient kernel");
+    return nb;
   }
   template <class E> int32_t logistic_tensor_setup(E& eng, const void* Xh, int32_t xd, const double* y, int64_t N, std::string& err) {
     return logistic_tc_setup(tc, eng, Xh, xd, y, N, err);

@@ -15,13 +15,15 @@
 //   GEMM1  S[128 chains x 128 rows]  = Bt[128 x Dt] · Xblk[128 rows x Dt]ᵀ   (A, B from smem, K-major)
 //   GEMM2  Gt[128 chains x Dt]      += R[128 x 128 rows] · Xblk[128 rows x Dt] (A from TMEM, B = same smem
 //                                                                               tile read MN-major)
-// fp32 accuracy on bf16 tensor cores: X is exact in bf16 (checked at set-up), the
-// per-chain operands are split in two bf16 terms (β = βh + βl, r = rh + rl) and
-// accumulated in fp32; the TMEM accumulator of GEMM2 is flushed every
-// `flush_every` row blocks and summed outside the tensor core.
+// fp32 accuracy on bf16 tensor cores: X is exact in bf16 (checked at set-up); the
+// fp32 position is split exactly in three bf16 terms (β = βh + βm + βl, 3 x 8
+// mantissa bits), the residual in two (r = rh + rl), all accumulated in fp32; the
+// TMEM accumulator of GEMM2 is double-buffered, drained every `flush_every` row
+// blocks and summed outside the tensor core (bounds accumulator rounding drift).
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2-9 elementwise/epilogue (TMEM lane group = warp % 4, two warps per group).
+// Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// warps 2-17 elementwise/epilogue: TMEM lane group = warp % 4 (hardware rule), the
+// four warps of a lane group each own one 32-row quarter of every 128-row block.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -33,7 +35,7 @@ namespace bn {
 
 namespace {
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 576;       // 2 control warps + 16 elementwise warps
 constexpr int ROWS = 128;            // data rows per block (GEMM1 N, GEMM2 K)
 constexpr int CHAINS = 128;          // chains per CTA (MMA M)
 constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 64 bf16 (one SW128 box)
@@ -161,28 +163,28 @@ template <int DT> struct SmemPlan {
   static constexpr int KC = DT / 64;
   static constexpr int B_BYTES = KC * CHUNK_BYTES;   // one β term
   static constexpr int X_BYTES = KC * CHUNK_BYTES;   // one X stage
-  static constexpr int NS = (DT == 128) ? 4 : 6;
-  static constexpr int OFF_BH = 0;
-  static constexpr int OFF_BL = B_BYTES;
-  static constexpr int OFF_X = 2 * B_BYTES;
+  static constexpr int NS = (DT == 128) ? 3 : 6;
+  static constexpr int OFF_B = 0;                    // 3 terms
+  static constexpr int OFF_X = 3 * B_BYTES;
   static constexpr int OFF_Y = OFF_X + NS * X_BYTES;
   static constexpr int OFF_BAR = OFF_Y + NS * ROWS * 4;
-  static constexpr int NBAR = 1 + 2 * NS + 6 + 2;
+  static constexpr int NBAR = 1 + 2 * NS + 6 + 4;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
 };
 
 template <int DT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
-              const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ y, float* G, double* Ld, int C, int Dp,
-              long long N, int nblk_total, int nsplit, int flush_every) {
+              const __grid_constant__ CUtensorMap tmBm, const __grid_constant__ CUtensorMap tmBl,
+              const float* __restrict__ y, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total,
+              int nsplit, int flush_every) {
   using P = SmemPlan<DT>;
   constexpr int NS = P::NS;
   constexpr int KC = P::KC;
+  constexpr int GBUF = (DT == 128) ? 128 : 64;     // TMEM columns per accumulator buffer
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SW128 needs 1024 B alignment
-  unsigned char* sBh = smem + P::OFF_BH;
-  unsigned char* sBl = smem + P::OFF_BL;
+  unsigned char* sB = smem + P::OFF_B;
   unsigned char* sX = smem + P::OFF_X;
   float* sY = reinterpret_cast<float*>(smem + P::OFF_Y);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
@@ -192,8 +194,8 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint64_t* s_full = x_empty + NS;      // [2] GEMM1 done
   uint64_t* r_full = s_full + 2;        // [2] residual written to TMEM
   uint64_t* sr_empty = r_full + 2;      // [2] GEMM2 done with the buffer
-  uint64_t* g_full = sr_empty + 2;      // accumulator complete for this flush period
-  uint64_t* g_empty = g_full + 1;       // accumulator drained
+  uint64_t* g_full = sr_empty + 2;      // [2] accumulator buffer complete for its flush period
+  uint64_t* g_empty = g_full + 2;       // [2] accumulator buffer drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -201,13 +203,15 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int b0 = (int)(((long long)nblk_total * split) / nsplit);
   const int b1 = (int)(((long long)nblk_total * (split + 1)) / nsplit);
   const int nb = b1 - b0;
+  const int fe = flush_every > 0 ? flush_every : 0x7fffffff;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_b, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 256); mbar_init(&sr_empty[i], 1); }
-    mbar_init(g_full, 1);
-    mbar_init(g_empty, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 512); mbar_init(&sr_empty[i], 1);
+      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 512);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -219,15 +223,16 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_S = tmem;              // 2 x 128 columns (S, overwritten in place by R)
-  const uint32_t tmem_G = tmem + 256;        // DT columns
+  const uint32_t tmem_G = tmem + 256;        // 2 x GBUF columns
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0 && nb > 0) {
-      mbar_expect_tx(bar_b, 2 * P::B_BYTES);
+      mbar_expect_tx(bar_b, 3 * P::B_BYTES);
       for (int kc = 0; kc < KC; ++kc) {
-        tma_load_2d(&tmBh, sBh + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
-        tma_load_2d(&tmBl, sBl + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+        tma_load_2d(&tmBh, sB + 0 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+        tma_load_2d(&tmBm, sB + 1 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+        tma_load_2d(&tmBl, sB + 2 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
       }
       for (int i = 0; i < nb; ++i) {
         const int st = i % NS;
@@ -244,7 +249,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (lane == 0 && nb > 0) {
       constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
       constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DT >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
-      const uint32_t aBh = smem_u32(sBh), aBl = smem_u32(sBl), aX = smem_u32(sX);
+      const uint32_t aB = smem_u32(sB), aX = smem_u32(sX);
       mbar_wait(bar_b, 0);
       auto gemm1 = [&](int i) {
         const int st = i % NS, buf = i & 1, u = i >> 1;
@@ -254,9 +259,10 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         const uint32_t xt = aX + (uint32_t)st * P::X_BYTES;
         const uint32_t d = tmem_S + (uint32_t)buf * 128u;
 #pragma unroll
-        for (int kk = 0; kk < DT / 16; ++kk) mma_ss(d, desc_kmajor(aBh, kk), desc_kmajor(xt, kk), IDESC1, kk > 0 ? 1u : 0u);
+        for (int term = 0; term < 3; ++term)
 #pragma unroll
-        for (int kk = 0; kk < DT / 16; ++kk) mma_ss(d, desc_kmajor(aBl, kk), desc_kmajor(xt, kk), IDESC1, 1u);
+          for (int kk = 0; kk < DT / 16; ++kk)
+            mma_ss(d, desc_kmajor(aB + (uint32_t)term * P::B_BYTES, kk), desc_kmajor(xt, kk), IDESC1, (term | kk) ? 1u : 0u);
         tc_commit(&s_full[buf]);
       };
       gemm1(0);
@@ -264,135 +270,126 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       for (int i = 0; i < nb; ++i) {
         if (i + 1 < nb) gemm1(i + 1);
         const int st = i % NS, buf = i & 1, u = i >> 1;
+        const int gb = period & 1;
         mbar_wait(&r_full[buf], (uint32_t)u & 1u);
-        if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
+        if (in_period == 0 && period >= 2) mbar_wait(&g_empty[gb], (uint32_t)((period >> 1) - 1) & 1u);
         tc_fence_after();
         const uint32_t xt = aX + (uint32_t)st * P::X_BYTES;
         const uint32_t a = tmem_S + (uint32_t)buf * 128u;
+        const uint32_t dG = tmem_G + (uint32_t)gb * GBUF;
 #pragma unroll
-        for (int kk = 0; kk < ROWS / 16; ++kk)
-          mma_ts(tmem_G, a + (uint32_t)(kk >> 1) * 32u + (uint32_t)(kk & 1) * 8u, desc_mnmajor(xt, kk), IDESC2,
-                 (in_period > 0 || kk > 0) ? 1u : 0u);
+        for (int term = 0; term < 2; ++term)
 #pragma unroll
-        for (int kk = 0; kk < ROWS / 16; ++kk)
-          mma_ts(tmem_G, a + (uint32_t)(kk >> 1) * 32u + (uint32_t)(kk & 1) * 8u + 16u, desc_mnmajor(xt, kk), IDESC2, 1u);
+          for (int kk = 0; kk < ROWS / 16; ++kk)
+            mma_ts(dG, a + (uint32_t)(kk >> 1) * 32u + (uint32_t)(kk & 1) * 8u + (uint32_t)term * 16u, desc_mnmajor(xt, kk),
+                   IDESC2, (in_period > 0 || term > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&x_empty[st]);
         tc_commit(&sr_empty[buf]);
         ++in_period;
-        const bool last = (i + 1 == nb);
-        if (last || (flush_every > 0 && in_period == flush_every)) {
-          tc_commit(g_full);
+        if (i + 1 == nb || in_period == fe) {
+          tc_commit(&g_full[gb]);
           ++period;
           in_period = 0;
         }
       }
     }
   } else {
-    // ===================================================== elementwise + epilogue (8 warps)
-    // TMEM lane group q = warp % 4 (hardware rule); the two warps of a lane group split
-    // the 128 data rows of a block: half h handles S columns [64h, 64h+64).
-    const int q = warp & 3;
-    const int h = (warp - 2) >> 2;
-    const int chain = tile * CHAINS + q * 32 + lane;
+    // ===================================================== elementwise + epilogue (16 warps)
+    const int q = warp & 3;                 // TMEM lane group
+    const int qr = (warp - 2) >> 2;         // row quarter of each block: S columns [32 qr, 32 qr + 32)
+    const int row = tile * CHAINS + q * 32 + lane;   // staging row = chain slot
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     double lsum = 0.0;
-    int period = 0, in_period = 0;
+    int period = 0, in_period = 0, drain_pending = -1;
     const float NLOG2E = -1.4426950408889634f, LN2 = 0.6931471805599453f;
+    float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
+    // drain accumulator buffer of period pd and add it to the partial gradient in global memory
+    auto drain = [&](int pd) {
+      const int gb = pd & 1;
+      mbar_wait(&g_full[gb], (uint32_t)(pd >> 1) & 1u);
+      tc_fence_after();
+      if (qr < DT / 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_G + (uint32_t)gb * GBUF + lane_sel + (uint32_t)qr * 32u, v);
+        tmem_ld_wait();
+        if (row < nrows) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int d = qr * 32 + j;
+            if (d < Dp) {
+              float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              float4* gp = reinterpret_cast<float4*>(gout + d);
+              if (pd > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+              *gp = a;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&g_empty[gb]);
+    };
     for (int i = 0; i < nb; ++i) {
       const int st = i % NS, buf = i & 1, u = i >> 1;
       mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);   // y of this block is visible
       mbar_wait(&s_full[buf], (uint32_t)u & 1u);
       tc_fence_after();
-      const float4* ys4 = reinterpret_cast<const float4*>(sY + st * ROWS);
-      const uint32_t tS = tmem_S + (uint32_t)buf * 128u + lane_sel;
+      const float4* ys4 = reinterpret_cast<const float4*>(sY + st * ROWS) + qr * 8;
+      const uint32_t tS = tmem_S + (uint32_t)buf * 128u + lane_sel + (uint32_t)qr * 32u;
       float bsum = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int ch = 2 * h + cc;
-        uint32_t v[32];
-        tmem_ld32(tS + (uint32_t)ch * 32u, v);
-        tmem_ld_wait();
-        uint32_t hi[16], lo[16];
+      uint32_t v[32];
+      tmem_ld32(tS, v);
+      tmem_ld_wait();
+      uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {       // 8 elements share one lg2 (log of a product)
-          const float4 ya = ys4[ch * 8 + g8 * 2], yb = ys4[ch * 8 + g8 * 2 + 1];
-          const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-          float prod = 1.f;
-          float rr[8];
+      for (int g8 = 0; g8 < 4; ++g8) {       // 8 elements share one lg2 (log of a product)
+        const float4 ya = ys4[g8 * 2], yb = ys4[g8 * 2 + 1];
+        const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+        float prod = 1.f;
+        float rr[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float eta = __uint_as_float(v[g8 * 8 + e]);
-            const float t = ex2_approx(fabsf(eta) * NLOG2E);
-            const float d = 1.0f + t;
-            prod *= d;
-            const float s = rcp_approx(d);
-            const float sig = eta >= 0.f ? s : t * s;
-            rr[e] = yy[e] - sig;
-            bsum = fmaf(eta, yy[e] - (eta > 0.f ? 1.f : 0.f), bsum);   // y*eta - max(eta, 0)
-          }
-          bsum = fmaf(-LN2, lg2_approx(prod), bsum);                    // - sum log(1 + t)
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            const uint32_t hh = pack_bf16(rr[e], rr[e + 1]);
-            const float h0 = __uint_as_float(hh << 16), h1 = __uint_as_float(hh & 0xffff0000u);
-            hi[(g8 * 8 + e) >> 1] = hh;
-            lo[(g8 * 8 + e) >> 1] = pack_bf16(rr[e] - h0, rr[e + 1] - h1);
-          }
+        for (int e = 0; e < 8; ++e) {
+          const float eta = __uint_as_float(v[g8 * 8 + e]);
+          const float t = ex2_approx(fabsf(eta) * NLOG2E);
+          const float d = 1.0f + t;
+          prod *= d;
+          const float s = rcp_approx(d);
+          const float sig = eta >= 0.f ? s : t * s;
+          rr[e] = yy[e] - sig;
+          bsum = fmaf(eta, yy[e] - (eta > 0.f ? 1.f : 0.f), bsum);   // y*eta - max(eta, 0)
         }
-        tmem_st16(tS + (uint32_t)ch * 32u, hi);
-        tmem_st16(tS + (uint32_t)ch * 32u + 16u, lo);
+        bsum = fmaf(-LN2, lg2_approx(prod), bsum);                    // - sum log(1 + t)
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const uint32_t hh = pack_bf16(rr[e], rr[e + 1]);
+          const float h0 = __uint_as_float(hh << 16), h1 = __uint_as_float(hh & 0xffff0000u);
+          hi[(g8 * 8 + e) >> 1] = hh;
+          lo[(g8 * 8 + e) >> 1] = pack_bf16(rr[e] - h0, rr[e + 1] - h1);
+        }
       }
+      tmem_st16(tS, hi);
+      tmem_st16(tS + 16u, lo);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&r_full[buf]);
       lsum += (double)bsum;
+      // the previous period's accumulator is drained one block late so its GEMM2 has retired
+      if (drain_pending >= 0) { drain(drain_pending); drain_pending = -1; }
       ++in_period;
-      const bool last = (i + 1 == nb);
-      if (last || (flush_every > 0 && in_period == flush_every)) {
-        // drain the GEMM2 accumulator of this period and add it outside the tensor core
-        mbar_wait(g_full, (uint32_t)period & 1u);
-        tc_fence_after();
-        float* g = G + ((size_t)split * C + (size_t)chain) * Dp;
-#pragma unroll 1
-        for (int cc = 0; cc < DT / 64; ++cc) {
-          const int ch = h * (DT / 64) + cc;
-          uint32_t v[32];
-          tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, v);
-          tmem_ld_wait();
-          if (chain < C) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int d = ch * 32 + j;
-              if (d < Dp) {
-                float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                       __uint_as_float(v[j + 3]));
-                float4* gp = reinterpret_cast<float4*>(g + d);
-                if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
-                *gp = a;
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(g_empty);
-        ++period;
-        in_period = 0;
-      }
+      if (i + 1 == nb) { drain(period); ++period; }
+      else if (in_period == fe) { drain_pending = period; ++period; in_period = 0; }
     }
     // rows >= N of the last block are zero padding: eta = 0, y = 0 -> each contributed -log 2
-    if (h == 1 && b1 == nblk_total) lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
-    // combine the two halves of each chain and publish
-    float* lpart = reinterpret_cast<float*>(smem + P::OFF_Y);   // y stages are dead by now
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    double* lp = reinterpret_cast<double*>(lpart);
-    if (h == 1) lp[q * 32 + lane] = lsum;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (h == 0 && chain < C) {
-      if (nb == 0) {
-        float* g = G + ((size_t)split * C + (size_t)chain) * Dp;
-        for (int d = 0; d < Dp; ++d) g[d] = 0.f;
-      }
-      Ld[(size_t)split * C + chain] = lsum + lp[q * 32 + lane];
+    if (qr == 0 && b1 == nblk_total) lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
+    // combine the four row quarters of each chain and publish
+    double* lp = reinterpret_cast<double*>(sX);   // X stages are dead by now
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (qr > 0) lp[(qr - 1) * 128 + q * 32 + lane] = lsum;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (qr == 0 && row < nrows) {
+      if (nb == 0) for (int d = 0; d < Dp; ++d) gout[d] = 0.f;
+      const int k = q * 32 + lane;
+      Ld[(size_t)split * nrows + row] = ((lsum + lp[k]) + lp[128 + k]) + lp[256 + k];
     }
   }
   tc_fence_before();
@@ -432,28 +429,44 @@ bool encode_map(void* out, const void* base, uint64_t rows, uint64_t cols) {
   return r == CUDA_SUCCESS;
 }
 
-template <int DT> void launch(LogisticTC& tc, cudaStream_t s) {
+template <int DT> void launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
   using P = SmemPlan<DT>;
   static bool attr_done = false;
   if (!attr_done) {
     tc.last = cudaFuncSetAttribute(k_logistic_tc<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL + 1024);
     attr_done = true;
   }
-  const int tiles = (tc.C + CHAINS - 1) / CHAINS;
-  dim3 grid(tiles, tc.nsplit);
-  CUtensorMap mX, mH, mL;
-  std::memcpy(&mX, tc.tmaps[0], sizeof(CUtensorMap));
-  std::memcpy(&mH, tc.tmaps[1], sizeof(CUtensorMap));
-  std::memcpy(&mL, tc.tmaps[2], sizeof(CUtensorMap));
-  k_logistic_tc<DT><<<grid, TC_THREADS, P::TOTAL + 1024, s>>>(mX, mH, mL, tc.yf, tc.G, tc.Ld, tc.C, tc.Dp, (long long)tc.N,
-                                                              (int)(tc.Npad / ROWS), tc.nsplit, tc.flush_every);
+  const int tiles = (nrows + CHAINS - 1) / CHAINS;
+  dim3 grid(tiles, nsplit);
+  CUtensorMap m[4];
+  for (int i = 0; i < 4; ++i) std::memcpy(&m[i], tc.tmaps[i], sizeof(CUtensorMap));
+  k_logistic_tc<DT><<<grid, TC_THREADS, P::TOTAL + 1024, s>>>(m[0], m[1], m[2], m[3], tc.yf, tc.G, tc.Ld, nrows, tc.Dp,
+                                                              (long long)tc.N, (int)(tc.Npad / ROWS), nsplit, tc.flush_every);
 }
 
 }  // namespace
 
-void LogisticTC::run(cudaStream_t s) {
-  if (!ready) return;
-  if (Dt == 64) launch<64>(*this, s); else launch<128>(*this, s);
+// number of row splits for `nrows` active rows: fill the SMs in as few full waves as possible
+int LogisticTC::plan_splits(int nrows) const {
+  const int tiles = (nrows + CHAINS - 1) / CHAINS;
+  const int64_t nblk = Npad / ROWS;
+  if (force_nsplit > 0) return (int)std::min<int64_t>(force_nsplit, nblk);
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ns = 1; ns <= max_splits; ++ns) {
+    if (ns > nblk) break;
+    const int ctas = tiles * ns;
+    const int waves = (ctas + sms - 1) / sms;
+    const double eff = (double)ctas / ((double)waves * sms);
+    const double score = eff * (1.0 - 0.01 * waves);   // prefer few waves (per-CTA set-up, partial traffic)
+    if (score > best_eff + 1e-9) { best_eff = score; best = ns; }
+  }
+  return best;
+}
+void LogisticTC::run(cudaStream_t s, int nrows) {
+  if (!ready || nrows <= 0) return;
+  last_nsplit = plan_splits(nrows);
+  if (Dt == 64) launch<64>(*this, s, nrows, last_nsplit); else launch<128>(*this, s, nrows, last_nsplit);
 }
 void LogisticTC::destroy() {
   if (Xb) cudaFree(Xb);
@@ -469,6 +482,8 @@ int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, i
   tc.Npad = (N + ROWS - 1) / ROWS * ROWS;
   const char* fe = std::getenv("BNUTS_TC_FLUSH");
   if (fe) tc.flush_every = std::atoi(fe);
+  const char* se = std::getenv("BNUTS_TC_NSPLIT");
+  tc.force_nsplit = se ? std::atoi(se) : 0;
   std::vector<uint16_t> xp(size_t(tc.Npad) * tc.Dt, 0);
   for (int64_t i = 0; i < N; ++i) std::memcpy(&xp[size_t(i) * tc.Dt], &Xh[size_t(i) * D], size_t(D) * 2);
   std::vector<float> yp(size_t(tc.Npad), 0.f);
@@ -479,26 +494,28 @@ int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, i
   }
   cudaMemcpy(tc.Xb, xp.data(), xp.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(tc.yf, yp.data(), yp.size() * 4, cudaMemcpyHostToDevice);
-  // split plan: one wave of CTAs over the SMs
-  int dev = 0, sms = 148;
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles = (C + CHAINS - 1) / CHAINS;
-  int ns = sms / tiles;
-  if (ns < 1) ns = 1;
+  cudaDeviceGetAttribute(&tc.sms, cudaDevAttrMultiProcessorCount, dev);
+  if (tc.sms <= 0) tc.sms = 148;
+  // staging rows needed for the partial outputs: max over nrows of nsplit(nrows) * nrows
+  tc.max_splits = 3 * tc.sms;
   const int64_t nblk = tc.Npad / ROWS;
-  if (ns > nblk) ns = (int)nblk;
-  const char* se = std::getenv("BNUTS_TC_NSPLIT");
-  if (se) ns = std::atoi(se);
-  if (ns < 1) ns = 1;
-  tc.nsplit = ns;
+  if (tc.max_splits > nblk) tc.max_splits = (int)nblk;
+  int64_t worst = C;
+  for (int tiles = 1; tiles <= (C + CHAINS - 1) / CHAINS; ++tiles) {
+    const int nr = std::min<int>(C, tiles * CHAINS);
+    worst = std::max<int64_t>(worst, (int64_t)tc.plan_splits(nr) * nr);
+  }
+  tc.partial_rows = worst;
   return 0;
 }
 
 int32_t logistic_tc_maps(LogisticTC& tc, std::string& err) {
   const uint64_t crow = (uint64_t)tc.C;
   if (!encode_map(tc.tmaps[0], tc.Xb, (uint64_t)tc.Npad, (uint64_t)tc.Dt) ||
-      !encode_map(tc.tmaps[1], tc.bh, crow, (uint64_t)tc.Dt) || !encode_map(tc.tmaps[2], tc.bl, crow, (uint64_t)tc.Dt)) {
+      !encode_map(tc.tmaps[1], tc.bh, crow, (uint64_t)tc.Dt) || !encode_map(tc.tmaps[2], tc.bm, crow, (uint64_t)tc.Dt) ||
+      !encode_map(tc.tmaps[3], tc.bl, crow, (uint64_t)tc.Dt)) {
     err = "cuTensorMapEncodeTiled failed";
     return BNUTS_ERR_CUDA;
   }

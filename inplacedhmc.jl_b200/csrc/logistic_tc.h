@@ -16,21 +16,23 @@ struct LogisticTC {
   // problem
   int32_t C = 0, D = 0, Dp = 0, Dt = 0;
   int64_t N = 0, Npad = 0;
-  int32_t nsplit = 1;
   int32_t flush_every = 8;   // row blocks per TMEM-accumulator flush (0 = only at the end)
+  int32_t sms = 148, max_splits = 1, force_nsplit = 0, last_nsplit = 1;
+  int64_t partial_rows = 0;  // rows needed in the partial-output buffers
   // device buffers owned here
   uint16_t* Xb = nullptr;    // [Npad][Dt] bf16
   float* yf = nullptr;       // [Npad]
   // borrowed from the engine
-  const uint16_t* bh = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
-  float* G = nullptr;        // [nsplit][C][Dp]
+  const uint16_t* bh = nullptr; const uint16_t* bm = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
+  float* G = nullptr;        // [nsplit][rows][Dp]
   double* Ld = nullptr;      // [nsplit][C] log-density partials (Float64: ~1e5..1e6 in magnitude)
-  // opaque tensor maps (3 x CUtensorMap, 128 B each, 64 B aligned)
-  alignas(64) unsigned char tmaps[3][128];
+  // opaque tensor maps (4 x CUtensorMap, 128 B each, 64 B aligned): X, βh, βm, βl
+  alignas(64) unsigned char tmaps[4][128];
   bool ready = false;
   cudaError_t last = cudaSuccess;
 
-  void run(cudaStream_t s);
+  int plan_splits(int nrows) const;
+  void run(cudaStream_t s, int nrows);
   void destroy();
 };
 
@@ -66,14 +68,15 @@ int32_t logistic_tc_setup(LogisticTC& tc, E& eng, const void* Xh, int32_t xd, co
     if (rc) return rc;
     // staging owned by the engine: bf16 hi/lo of q, partial outputs
     M.Dt = tc.Dt;
-    M.stage_bh = eng.x.template alloc<uint16_t>(size_t(M.C) * tc.Dt);
-    M.stage_bl = eng.x.template alloc<uint16_t>(size_t(M.C) * tc.Dt);
-    eng.x.zero(M.stage_bh, size_t(M.C) * tc.Dt * 2);
-    eng.x.zero(M.stage_bl, size_t(M.C) * tc.Dt * 2);
-    eng.alloc_stage(tc.nsplit);
-    M.stage_ld = eng.x.template alloc<double>(size_t(M.C) * tc.nsplit);
-    eng.x.zero(M.stage_ld, size_t(M.C) * tc.nsplit * sizeof(double));
-    tc.bh = M.stage_bh; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.Ld = M.stage_ld;
+    const size_t nbt = size_t(M.C) * tc.Dt;
+    M.stage_bh = eng.x.template alloc<uint16_t>(nbt);
+    M.stage_bm = eng.x.template alloc<uint16_t>(nbt);
+    M.stage_bl = eng.x.template alloc<uint16_t>(nbt);
+    eng.x.zero(M.stage_bh, nbt * 2); eng.x.zero(M.stage_bm, nbt * 2); eng.x.zero(M.stage_bl, nbt * 2);
+    eng.alloc_stage(1, size_t(tc.partial_rows));
+    M.stage_ld = eng.x.template alloc<double>(size_t(tc.partial_rows));
+    eng.x.zero(M.stage_ld, size_t(tc.partial_rows) * sizeof(double));
+    tc.bh = M.stage_bh; tc.bm = M.stage_bm; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.Ld = M.stage_ld;
     rc = logistic_tc_maps(tc, err);
     if (rc) return rc;
     eng.model.Npad = tc.Npad;

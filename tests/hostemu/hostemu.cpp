@@ -27,20 +27,27 @@ struct HostExec {
   int32_t check(std::string&) { return 0; }
   int32_t profile(int32_t, double* ms, int64_t* n) { if (ms) *ms = 0; if (n) *n = 0; return 0; }
 
+  unsigned long long count = 0;
+  unsigned long long* counter() { return &count; }
+  int64_t read_count() { return (int64_t)count; }
   template <class T> void prepare(const EngineMem<T>& M, const RunParams<T>& rp, const PrepareArgs& a) {
+    count = 0;
     for (int c = 0; c < M.C; ++c) prepare_chain(M, rp, a, c, SerialLanes{});
   }
   template <class T> int64_t advance(const EngineMem<T>& M, const RunParams<T>& rp, int iters) {
     int64_t np = 0;
+    count = 0;
 #pragma omp parallel for schedule(dynamic) reduction(+ : np)
     for (int c = 0; c < M.C; ++c) np += advance_chain(M, rp, c, SerialLanes{}, iters) ? 1 : 0;
     return np;
   }
   // deterministic batched gradients, same summation order as the CUDA kernels
-  template <class E> void gradient(E& eng) {
+  // evaluates staged rows [0, rows); returns the number of partial blocks per row
+  template <class E> int gradient(E& eng, int rows) {
     auto& M = eng.M;
     using T = typename std::remove_reference<decltype(*M.zs)>::type;
-    const int C = M.C, D = M.D, Dp = M.Dp;
+    const int C = rows, D = M.D, Dp = M.Dp;
+    int nbr = 1;
     if (eng.model.kind == MODEL_GAUSSIAN) {
 #pragma omp parallel for
       for (int c = 0; c < C; ++c)
@@ -52,6 +59,7 @@ struct HostExec {
     } else if (eng.model.kind == MODEL_LOGISTIC) {
       const int64_t N = eng.model.N;
       const int nb = eng.model.row_blocks;
+      nbr = nb;
       const int64_t R = (N + nb - 1) / nb;
 #pragma omp parallel for collapse(2)
       for (int b = 0; b < nb; ++b)
@@ -73,6 +81,7 @@ struct HostExec {
           M.stage_l[size_t(b) * C + c] = pl;
         }
     }
+    return nbr;
   }
   template <class E> int32_t logistic_tensor_setup(E&, const void*, int32_t, const double*, int64_t, std::string& err) {
     err = "tensor path is CUDA-only";

@@ -51,11 +51,16 @@ def _rel(a, b):
     return np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(b, axis=-1), 1e-30)
 
 
+def _f32(x):
+    """inputs of the fp32 variant are fp32 numbers: both sides must see the same values"""
+    return np.asarray(x, dtype=np.float32).astype(np.float64)
+
+
 @pytest.mark.parametrize("N,D,C", [(2000, 100, 200), (128, 64, 128), (1000, 17, 3), (5000, 128, 257)])
 def test_tensor_gradient_within_tolerance(bn, oracle_lib, cuda_lib, N, D, C):
     X, y, beta = make_logistic(N, D)
     rng = np.random.default_rng(1)
-    q = beta[None, :] + rng.normal(size=(C, D)) * 0.3
+    q = _f32(beta[None, :] + rng.normal(size=(C, D)) * 0.3)
     q[0] = 0.0
     ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0, row_blocks=1); ref.set_positions(q)
     tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0); tc.set_positions(q)
@@ -72,8 +77,8 @@ def test_tensor_per_leapfrog_parity(bn, oracle_lib, cuda_lib):
     N, D, C = 3000, 100, 256
     X, y, beta = make_logistic(N, D)
     rng = np.random.default_rng(2)
-    q = beta[None, :] + rng.normal(size=(C, D)) * 0.05
-    p = rng.normal(size=(C, D)) * np.sqrt(N) * 0.5
+    q = _f32(beta[None, :] + rng.normal(size=(C, D)) * 0.05)
+    p = _f32(rng.normal(size=(C, D)) * np.sqrt(N) * 0.5)
     ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0); ref.set_positions(q)
     tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0); tc.set_positions(q)
     for eps, n in [(1e-3, 1), (2e-3, 4), (-1e-3, 3)]:
@@ -92,10 +97,10 @@ def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib):
     rng = np.random.default_rng(3)
     ref = bn.Engine(C, D, dtype=F32, lib=oracle_lib, max_depth=6); ref.model_logistic(X, y, 1.0)
     tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, max_depth=6, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0)
-    q = beta[None, :] + rng.normal(size=(C, D)) * 0.05
+    q = _f32(beta[None, :] + rng.normal(size=(C, D)) * 0.05)
     agree = total = 0
     for t in range(T):
-        p = rng.normal(size=(1, C, D))
+        p = _f32(rng.normal(size=(1, C, D)))
         dirs = rng.integers(0, 2 ** 32, size=(1, C), dtype=np.uint64).astype(np.uint32)
         for e in (ref, tc):
             e.seed(77, t); e.set_positions(q); e.set_stepsize(0.02); e.inject(1, dirs, p)
@@ -106,7 +111,7 @@ def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib):
         agree += int(same.sum()); total += same.size
         ok = same[:, 0]
         assert np.max(_rel(cb[ok, 0], ca[ok, 0])) < 1e-4
-        q = ca[:, 0]
+        q = ca[:, 0]        # fp32 oracle output: exactly representable
     assert agree >= 0.97 * total, (agree, total)
 
 
@@ -115,7 +120,8 @@ def test_tensor_full_size_known_answers(bn, cuda_lib):
     N, D, C = 1_000_000, 100, 256
     X, y, beta = make_logistic(N, D)
     rng = np.random.default_rng(4)
-    q = np.zeros((C, D)); q[1:5] = beta + rng.normal(size=(4, D)) * 0.02
+    q = np.zeros((C, D)); q[1:3] = _f32(beta + rng.normal(size=(2, D)) * 0.02)
+    q[3:5] = _f32(beta + rng.normal(size=(2, D)) * 0.002)   # inside the posterior bulk (sd ~ 2/sqrt(N))
     q[5:] = q[1 + (np.arange(C - 5) % 4)]            # replicate chains 1-4 across slots
     tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0); tc.set_positions(q)
     _, g, l = tc.get_state()
@@ -126,7 +132,12 @@ def test_tensor_full_size_known_answers(bn, cuda_lib):
     eta = X @ q[1:5].T
     gref = ((y[:, None] - 1 / (1 + np.exp(-eta))).T @ X) - q[1:5]
     lref = (y[:, None] * eta - np.logaddexp(0, eta)).sum(0) - 0.5 * (q[1:5] ** 2).sum(1)
-    assert np.max(_rel(g[1:5], gref)) < TOL32
+    # the north-star tolerance is relative to the gradient of the same fp32 inputs; near the
+    # mode |grad| is ~1e2..1e3 while the terms being summed are ~N/2, so also bound the error
+    # by the fp32 conditioning floor N * eps32
+    err = np.linalg.norm(g[1:5] - gref, axis=1)
+    assert np.all(err < np.maximum(TOL32 * np.linalg.norm(gref, axis=1), 3 * N * 6e-8)), (err, np.linalg.norm(gref, axis=1))
+    assert np.max(_rel(g[1:3], gref[:2])) < TOL32
     assert np.max(np.abs(l[1:5] - lref) / np.abs(lref)) < 1e-6
     # a chain's result does not depend on which slot/tile it sits in
     for k in range(5, C):
