@@ -18,8 +18,9 @@
 // fp32 accuracy on bf16 tensor cores: X is exact in bf16 (checked at set-up); the
 // fp32 position is split exactly in three bf16 terms (β = βh + βm + βl, 3 x 8
 // mantissa bits), the residual in two (r = rh + rl), all accumulated in fp32; the
-// TMEM accumulator of GEMM2 is double-buffered, drained every `flush_every` row
-// blocks and summed outside the tensor core (bounds accumulator rounding drift).
+// TMEM accumulator of GEMM2 is drained every `flush_every` row blocks and summed
+// outside the tensor core (bounds accumulator rounding drift).  Three S/R buffers in
+// TMEM give the elementwise warps two block-times of slack behind the tensor pipe.
 //
 // Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
 // warps 2-17 elementwise/epilogue: TMEM lane group = warp % 4 (hardware rule), the
@@ -163,27 +164,28 @@ template <int DT> struct SmemPlan {
   static constexpr int KC = DT / 64;
   static constexpr int B_BYTES = KC * CHUNK_BYTES;   // one β term
   static constexpr int X_BYTES = KC * CHUNK_BYTES;   // one X stage
-  static constexpr int NS = (DT == 128) ? 3 : 6;
+  static constexpr int NS = (DT == 128) ? 4 : 6;     // X stages
+  static constexpr int NSB = 3;                      // S/R buffers in TMEM
   static constexpr int OFF_B = 0;                    // 3 terms
   static constexpr int OFF_X = 3 * B_BYTES;
   static constexpr int OFF_Y = OFF_X + NS * X_BYTES;
   static constexpr int OFF_BAR = OFF_Y + NS * ROWS * 4;
-  static constexpr int NBAR = 1 + 2 * NS + 6 + 4;
+  static constexpr int NBAR = 1 + 2 * NS + 3 * NSB + 2;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
 };
 
+// dk = round16(D): K of GEMM1 and N of GEMM2 (columns >= dk of the 64-wide chunks are never read)
 template <int DT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBm, const __grid_constant__ CUtensorMap tmBl,
-              const float* __restrict__ y, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total,
+              const float* __restrict__ y, float* G, double* Ld, int nrows, int Dp, int dk, long long N, int nblk_total,
               int nsplit, int flush_every) {
   using P = SmemPlan<DT>;
   constexpr int NS = P::NS;
   constexpr int KC = P::KC;
-  constexpr int GBUF = (DT == 128) ? 128 : 64;     // TMEM columns per accumulator buffer
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SW128 needs 1024 B alignment
+  constexpr int NSB = P::NSB;
+  extern __shared__ __align__(1024) unsigned char smem[];   // SW128 tiles need 1024 B alignment (checked below)
   unsigned char* sB = smem + P::OFF_B;
   unsigned char* sX = smem + P::OFF_X;
   float* sY = reinterpret_cast<float*>(smem + P::OFF_Y);
@@ -191,11 +193,11 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint64_t* bar_b = bars;               // β tiles landed
   uint64_t* x_full = bars + 1;          // [NS]
   uint64_t* x_empty = x_full + NS;      // [NS]
-  uint64_t* s_full = x_empty + NS;      // [2] GEMM1 done
-  uint64_t* r_full = s_full + 2;        // [2] residual written to TMEM
-  uint64_t* sr_empty = r_full + 2;      // [2] GEMM2 done with the buffer
-  uint64_t* g_full = sr_empty + 2;      // [2] accumulator buffer complete for its flush period
-  uint64_t* g_empty = g_full + 2;       // [2] accumulator buffer drained
+  uint64_t* s_full = x_empty + NS;      // [NSB] GEMM1 done
+  uint64_t* r_full = s_full + NSB;      // [NSB] residual written to TMEM
+  uint64_t* sr_empty = r_full + NSB;    // [NSB] GEMM2 done with the buffer
+  uint64_t* g_full = sr_empty + NSB;    // accumulator complete for its flush period
+  uint64_t* g_empty = g_full + 1;       // accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -204,14 +206,15 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int b1 = (int)(((long long)nblk_total * (split + 1)) / nsplit);
   const int nb = b1 - b0;
   const int fe = flush_every > 0 ? flush_every : 0x7fffffff;
+  const int nk = dk >> 4;
 
   if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) asm volatile("trap;");
     mbar_init(bar_b, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 512); mbar_init(&sr_empty[i], 1);
-      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 512);
-    }
+    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 512); mbar_init(&sr_empty[i], 1); }
+    mbar_init(g_full, 1);
+    mbar_init(g_empty, 512);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -222,8 +225,8 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_S = tmem;              // 2 x 128 columns (S, overwritten in place by R)
-  const uint32_t tmem_G = tmem + 256;        // 2 x GBUF columns
+  const uint32_t tmem_S = tmem;              // NSB x 128 columns (S, overwritten in place by R)
+  const uint32_t tmem_G = tmem + NSB * 128;  // dk <= 128 columns
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -247,12 +250,12 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0 && nb > 0) {
-      constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
-      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DT >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
       const uint32_t aB = smem_u32(sB), aX = smem_u32(sX);
       mbar_wait(bar_b, 0);
       auto gemm1 = [&](int i) {
-        const int st = i % NS, buf = i & 1, u = i >> 1;
+        const int st = i % NS, buf = i % NSB, u = i / NSB;
         mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
         if (u >= 1) mbar_wait(&sr_empty[buf], (uint32_t)(u - 1) & 1u);
         tc_fence_after();
@@ -260,34 +263,32 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         const uint32_t d = tmem_S + (uint32_t)buf * 128u;
 #pragma unroll
         for (int term = 0; term < 3; ++term)
-#pragma unroll
-          for (int kk = 0; kk < DT / 16; ++kk)
+          for (int kk = 0; kk < nk; ++kk)
             mma_ss(d, desc_kmajor(aB + (uint32_t)term * P::B_BYTES, kk), desc_kmajor(xt, kk), IDESC1, (term | kk) ? 1u : 0u);
         tc_commit(&s_full[buf]);
       };
       gemm1(0);
+      if (nb > 1) gemm1(1);
       int period = 0, in_period = 0;
       for (int i = 0; i < nb; ++i) {
-        if (i + 1 < nb) gemm1(i + 1);
-        const int st = i % NS, buf = i & 1, u = i >> 1;
-        const int gb = period & 1;
+        if (i + 2 < nb) gemm1(i + 2);
+        const int st = i % NS, buf = i % NSB, u = i / NSB;
         mbar_wait(&r_full[buf], (uint32_t)u & 1u);
-        if (in_period == 0 && period >= 2) mbar_wait(&g_empty[gb], (uint32_t)((period >> 1) - 1) & 1u);
+        if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
         tc_fence_after();
         const uint32_t xt = aX + (uint32_t)st * P::X_BYTES;
         const uint32_t a = tmem_S + (uint32_t)buf * 128u;
-        const uint32_t dG = tmem_G + (uint32_t)gb * GBUF;
 #pragma unroll
         for (int term = 0; term < 2; ++term)
 #pragma unroll
           for (int kk = 0; kk < ROWS / 16; ++kk)
-            mma_ts(dG, a + (uint32_t)(kk >> 1) * 32u + (uint32_t)(kk & 1) * 8u + (uint32_t)term * 16u, desc_mnmajor(xt, kk),
+            mma_ts(tmem_G, a + (uint32_t)(kk >> 1) * 32u + (uint32_t)(kk & 1) * 8u + (uint32_t)term * 16u, desc_mnmajor(xt, kk),
                    IDESC2, (in_period > 0 || term > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&x_empty[st]);
         tc_commit(&sr_empty[buf]);
         ++in_period;
         if (i + 1 == nb || in_period == fe) {
-          tc_commit(&g_full[gb]);
+          tc_commit(g_full);
           ++period;
           in_period = 0;
         }
@@ -300,37 +301,11 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int row = tile * CHAINS + q * 32 + lane;   // staging row = chain slot
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     double lsum = 0.0;
-    int period = 0, in_period = 0, drain_pending = -1;
+    int period = 0, in_period = 0;
     const float NLOG2E = -1.4426950408889634f, LN2 = 0.6931471805599453f;
     float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
-    // drain accumulator buffer of period pd and add it to the partial gradient in global memory
-    auto drain = [&](int pd) {
-      const int gb = pd & 1;
-      mbar_wait(&g_full[gb], (uint32_t)(pd >> 1) & 1u);
-      tc_fence_after();
-      if (qr < DT / 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_G + (uint32_t)gb * GBUF + lane_sel + (uint32_t)qr * 32u, v);
-        tmem_ld_wait();
-        if (row < nrows) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int d = qr * 32 + j;
-            if (d < Dp) {
-              float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                     __uint_as_float(v[j + 3]));
-              float4* gp = reinterpret_cast<float4*>(gout + d);
-              if (pd > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
-              *gp = a;
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&g_empty[gb]);
-    };
     for (int i = 0; i < nb; ++i) {
-      const int st = i % NS, buf = i & 1, u = i >> 1;
+      const int st = i % NS, buf = i % NSB, u = i / NSB;
       mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);   // y of this block is visible
       mbar_wait(&s_full[buf], (uint32_t)u & 1u);
       tc_fence_after();
@@ -350,15 +325,16 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float eta = __uint_as_float(v[g8 * 8 + e]);
-          const float t = ex2_approx(fabsf(eta) * NLOG2E);
+          const float t = ex2_approx(fabsf(eta) * NLOG2E);          // exp(-|eta|)
           const float d = 1.0f + t;
           prod *= d;
-          const float s = rcp_approx(d);
-          const float sig = eta >= 0.f ? s : t * s;
-          rr[e] = yy[e] - sig;
-          bsum = fmaf(eta, yy[e] - (eta > 0.f ? 1.f : 0.f), bsum);   // y*eta - max(eta, 0)
+          const float w = t * rcp_approx(d);                         // sigmoid(-|eta|) in (0, 1/2]
+          // sigma = eta >= 0 ? 1 - w : w ;  r = y - sigma = (y - [eta >= 0]) + copysign(w, eta)
+          const float ys = yy[e] - (eta >= 0.f ? 1.f : 0.f);
+          rr[e] = ys + __uint_as_float(__float_as_uint(w) | (__float_as_uint(eta) & 0x80000000u));
+          bsum = fmaf(eta, ys, bsum);                                // y*eta - max(eta, 0)
         }
-        bsum = fmaf(-LN2, lg2_approx(prod), bsum);                    // - sum log(1 + t)
+        bsum = fmaf(-LN2, lg2_approx(prod), bsum);                   // - sum log(1 + exp(-|eta|))
 #pragma unroll
         for (int e = 0; e < 8; e += 2) {
           const uint32_t hh = pack_bf16(rr[e], rr[e + 1]);
@@ -373,11 +349,33 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       tc_fence_before();
       mbar_arrive(&r_full[buf]);
       lsum += (double)bsum;
-      // the previous period's accumulator is drained one block late so its GEMM2 has retired
-      if (drain_pending >= 0) { drain(drain_pending); drain_pending = -1; }
       ++in_period;
-      if (i + 1 == nb) { drain(period); ++period; }
-      else if (in_period == fe) { drain_pending = period; ++period; in_period = 0; }
+      if (i + 1 == nb || in_period == fe) {
+        // drain the GEMM2 accumulator of this period and add it outside the tensor core
+        mbar_wait(g_full, (uint32_t)period & 1u);
+        tc_fence_after();
+        if (qr * 32 < dk) {
+          tmem_ld32(tmem_G + lane_sel + (uint32_t)qr * 32u, v);
+          tmem_ld_wait();
+          if (row < nrows) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int d = qr * 32 + j;
+              if (d < dk) {
+                float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3]));
+                float4* gp = reinterpret_cast<float4*>(gout + d);
+                if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+                *gp = a;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(g_empty);
+        ++period;
+        in_period = 0;
+      }
     }
     // rows >= N of the last block are zero padding: eta = 0, y = 0 -> each contributed -log 2
     if (qr == 0 && b1 == nblk_total) lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
@@ -433,15 +431,15 @@ template <int DT> void launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsp
   using P = SmemPlan<DT>;
   static bool attr_done = false;
   if (!attr_done) {
-    tc.last = cudaFuncSetAttribute(k_logistic_tc<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL + 1024);
+    tc.last = cudaFuncSetAttribute(k_logistic_tc<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     attr_done = true;
   }
   const int tiles = (nrows + CHAINS - 1) / CHAINS;
   dim3 grid(tiles, nsplit);
   CUtensorMap m[4];
   for (int i = 0; i < 4; ++i) std::memcpy(&m[i], tc.tmaps[i], sizeof(CUtensorMap));
-  k_logistic_tc<DT><<<grid, TC_THREADS, P::TOTAL + 1024, s>>>(m[0], m[1], m[2], m[3], tc.yf, tc.G, tc.Ld, nrows, tc.Dp,
-                                                              (long long)tc.N, (int)(tc.Npad / ROWS), nsplit, tc.flush_every);
+  k_logistic_tc<DT><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.yf, tc.G, tc.Ld, nrows, tc.Dp, tc.dk,
+                                                       (long long)tc.N, (int)(tc.Npad / ROWS), nsplit, tc.flush_every);
 }
 
 }  // namespace
@@ -479,6 +477,7 @@ int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, i
   tc.destroy();
   tc.C = C; tc.D = D; tc.Dp = Dp; tc.N = N;
   tc.Dt = (D <= 64) ? 64 : 128;
+  tc.dk = (D + 15) / 16 * 16;
   tc.Npad = (N + ROWS - 1) / ROWS * ROWS;
   const char* fe = std::getenv("BNUTS_TC_FLUSH");
   if (fe) tc.flush_every = std::atoi(fe);

@@ -1,0 +1,22 @@
+"""Gradient-kernel time vs active rows (run under gpurun)."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import inplacedhmc_jl_b200 as bn
+from bench import synth
+N, D = 1_000_000, 100
+bits, y, beta = synth(N, D)
+for C in [int(c) for c in os.environ.get("CS", "4096,2048,1024,512,128,16").split(",")]:
+    e = bn.Engine(C, D, dtype=bn.F32, gradient_path=bn.GRAD_TENSOR); e.model_logistic(bits, y, 1.0)
+    rng = np.random.default_rng(1)
+    e.set_positions(beta[None, :] + rng.normal(size=(C, D)) * 2e-3)
+    p = rng.normal(size=(C, D))
+    e.leapfrog(p, 1e-3, 3)
+    e.profile(True)
+    torch.cuda.synchronize(); t = time.perf_counter(); e.leapfrog(p, 1e-3, 20); torch.cuda.synchronize(); dt = time.perf_counter() - t
+    ms, n = e.profile(False)
+    fl = 4.0 * N * D * C
+    print(f"C={C:5d}: grad kernel {ms/n*1e3:8.1f} us/launch ({fl/(ms/n*1e-3)/1e12:7.1f} TFLOP/s alg), lockstep step {dt/20*1e3:7.3f} ms wall", flush=True)
+    e.close()
