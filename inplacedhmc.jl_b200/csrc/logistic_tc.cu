@@ -174,14 +174,17 @@ template <int DT> struct SmemPlan {
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
 };
 
-// dk = round16(D): K of GEMM1 and N of GEMM2 (columns >= dk of the 64-wide chunks are never read)
-template <int DT>
+// NK = round16(D)/16: K steps of GEMM1; dk = 16 NK is also N of GEMM2 (columns >= dk of the
+// 64-wide smem chunks are never read).  NK is a template parameter so the single MMA-issuing
+// thread runs fully unrolled code with constant descriptor offsets (it is latency-critical).
+template <int DT, int NK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBm, const __grid_constant__ CUtensorMap tmBl,
-              const float* __restrict__ y, float* G, double* Ld, int nrows, int Dp, int dk, long long N, int nblk_total,
+              const float* __restrict__ y, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total,
               int nsplit, int flush_every) {
   using P = SmemPlan<DT>;
+  constexpr int dk = NK * 16;
   constexpr int NS = P::NS;
   constexpr int KC = P::KC;
   constexpr int NSB = P::NSB;
@@ -206,7 +209,6 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int b1 = (int)(((long long)nblk_total * (split + 1)) / nsplit);
   const int nb = b1 - b0;
   const int fe = flush_every > 0 ? flush_every : 0x7fffffff;
-  const int nk = dk >> 4;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) asm volatile("trap;");
@@ -250,21 +252,28 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0 && nb > 0) {
-      const uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
-      const uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
-      const uint32_t aB = smem_u32(sB), aX = smem_u32(sX);
+      constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t aX = smem_u32(sX);
+      // descriptors of the three β tiles are loop invariant; per-k offsets are compile-time constants
+      uint64_t dB[3];
+#pragma unroll
+      for (int term = 0; term < 3; ++term) dB[term] = desc_kmajor(smem_u32(sB) + (uint32_t)term * P::B_BYTES, 0);
       mbar_wait(bar_b, 0);
       auto gemm1 = [&](int i) {
         const int st = i % NS, buf = i % NSB, u = i / NSB;
         mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
         if (u >= 1) mbar_wait(&sr_empty[buf], (uint32_t)(u - 1) & 1u);
         tc_fence_after();
-        const uint32_t xt = aX + (uint32_t)st * P::X_BYTES;
+        const uint64_t dX = desc_kmajor(aX + (uint32_t)st * P::X_BYTES, 0);
         const uint32_t d = tmem_S + (uint32_t)buf * 128u;
 #pragma unroll
         for (int term = 0; term < 3; ++term)
-          for (int kk = 0; kk < nk; ++kk)
-            mma_ss(d, desc_kmajor(aB + (uint32_t)term * P::B_BYTES, kk), desc_kmajor(xt, kk), IDESC1, (term | kk) ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < NK; ++kk) {
+            const uint64_t off = (uint64_t)(((kk >> 2) * CHUNK_BYTES + (kk & 3) * 32) >> 4);
+            mma_ss(d, dB[term] + off, dX + off, IDESC1, (term | kk) ? 1u : 0u);
+          }
         tc_commit(&s_full[buf]);
       };
       gemm1(0);
@@ -276,14 +285,15 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         mbar_wait(&r_full[buf], (uint32_t)u & 1u);
         if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
         tc_fence_after();
-        const uint32_t xt = aX + (uint32_t)st * P::X_BYTES;
+        const uint64_t dXm = desc_mnmajor(aX + (uint32_t)st * P::X_BYTES, 0);
         const uint32_t a = tmem_S + (uint32_t)buf * 128u;
+        const uint32_t acc0 = in_period > 0 ? 1u : 0u;
 #pragma unroll
         for (int term = 0; term < 2; ++term)
 #pragma unroll
           for (int kk = 0; kk < ROWS / 16; ++kk)
-            mma_ts(tmem_G, a + (uint32_t)(kk >> 1) * 32u + (uint32_t)(kk & 1) * 8u + (uint32_t)term * 16u, desc_mnmajor(xt, kk),
-                   IDESC2, (in_period > 0 || term > 0 || kk > 0) ? 1u : 0u);
+            mma_ts(tmem_G, a + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8 + term * 16), dXm + (uint64_t)(kk * 2048 >> 4), IDESC2,
+                   (term | kk) ? 1u : acc0);
         tc_commit(&x_empty[st]);
         tc_commit(&sr_empty[buf]);
         ++in_period;
@@ -427,19 +437,19 @@ bool encode_map(void* out, const void* base, uint64_t rows, uint64_t cols) {
   return r == CUDA_SUCCESS;
 }
 
-template <int DT> void launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
+template <int DT, int NK> void launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
   using P = SmemPlan<DT>;
   static bool attr_done = false;
   if (!attr_done) {
-    tc.last = cudaFuncSetAttribute(k_logistic_tc<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    tc.last = cudaFuncSetAttribute(k_logistic_tc<DT, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     attr_done = true;
   }
   const int tiles = (nrows + CHAINS - 1) / CHAINS;
   dim3 grid(tiles, nsplit);
   CUtensorMap m[4];
   for (int i = 0; i < 4; ++i) std::memcpy(&m[i], tc.tmaps[i], sizeof(CUtensorMap));
-  k_logistic_tc<DT><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.yf, tc.G, tc.Ld, nrows, tc.Dp, tc.dk,
-                                                       (long long)tc.N, (int)(tc.Npad / ROWS), nsplit, tc.flush_every);
+  k_logistic_tc<DT, NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.yf, tc.G, tc.Ld, nrows, tc.Dp,
+                                                           (long long)tc.N, (int)(tc.Npad / ROWS), nsplit, tc.flush_every);
 }
 
 }  // namespace
@@ -464,7 +474,16 @@ int LogisticTC::plan_splits(int nrows) const {
 void LogisticTC::run(cudaStream_t s, int nrows) {
   if (!ready || nrows <= 0) return;
   last_nsplit = plan_splits(nrows);
-  if (Dt == 64) launch<64>(*this, s, nrows, last_nsplit); else launch<128>(*this, s, nrows, last_nsplit);
+  switch (dk / 16) {
+    case 1: launch<64, 1>(*this, s, nrows, last_nsplit); break;
+    case 2: launch<64, 2>(*this, s, nrows, last_nsplit); break;
+    case 3: launch<64, 3>(*this, s, nrows, last_nsplit); break;
+    case 4: launch<64, 4>(*this, s, nrows, last_nsplit); break;
+    case 5: launch<128, 5>(*this, s, nrows, last_nsplit); break;
+    case 6: launch<128, 6>(*this, s, nrows, last_nsplit); break;
+    case 7: launch<128, 7>(*this, s, nrows, last_nsplit); break;
+    default: launch<128, 8>(*this, s, nrows, last_nsplit); break;
+  }
 }
 void LogisticTC::destroy() {
   if (Xb) cudaFree(Xb);

@@ -16,7 +16,7 @@ struct LogisticTC {
   // problem
   int32_t C = 0, D = 0, Dp = 0, Dt = 0, dk = 0;   // Dt: smem tile width (64|128), dk = round16(D): MMA K / N
   int64_t N = 0, Npad = 0;
-  int32_t flush_every = 16;  // row blocks per TMEM-accumulator flush (0 = only at the end)
+  int32_t flush_every = 32;  // row blocks per TMEM-accumulator flush (0 = only at the end)
   int32_t sms = 148, max_splits = 1, force_nsplit = 0, last_nsplit = 1;
   int64_t partial_rows = 0;  // rows needed in the partial-output buffers
   // device buffers owned here
