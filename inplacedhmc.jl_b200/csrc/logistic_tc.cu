@@ -216,9 +216,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (smem_u32(smem) & 1023u) asm volatile("trap;");
     mbar_init(bar_b, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 512); mbar_init(&sr_empty[i], 1); }
+    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 256); mbar_init(&sr_empty[i], 1); }
     mbar_init(g_full, 1);
-    mbar_init(g_empty, 512);
+    mbar_init(g_empty, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -299,7 +299,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         tc_commit(&x_empty[st]);
         tc_commit(&sr_empty[buf]);
         ++in_period;
-        if (i + 1 == nb || in_period == fe) {
+        if (i + 1 == nb || (i % fe) == fe - 1) {
           tc_commit(g_full);
           ++period;
           in_period = 0;
@@ -308,95 +308,109 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     }
   } else {
     // ===================================================== elementwise + epilogue (16 warps)
-    const int q = warp & 3;                 // TMEM lane group
-    const int qr = (warp - 2) >> 2;         // row quarter of each block: S columns [32 qr, 32 qr + 32)
+    // Two groups of 8 warps ping-pong over the row blocks (group g takes blocks i = g mod 2), so
+    // on every scheduler one group computes while the other sits in its TMEM load/store/sync
+    // phase.  Inside a group: TMEM lane group q = warp % 4 (hardware rule), column half h.
+    const int ew = warp - 2;
+    const int grp = ew >> 3;
+    const int h = (ew >> 2) & 1;
+    const int q = warp & 3;
     const int row = tile * CHAINS + q * 32 + lane;   // staging row = chain slot
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     double lsum = 0.0;
-    int period = 0, in_period = 0;
     const float NLOG2E = -1.4426950408889634f, LN2 = 0.6931471805599453f;
     float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
-    for (int i = 0; i < nb; ++i) {
+    for (int i = grp; i < nb; i += 2) {
       const int st = i % NS, buf = i % NSB, u = i / NSB;
       mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);   // y of this block is visible
       mbar_wait(&s_full[buf], (uint32_t)u & 1u);
       tc_fence_after();
-      const float4* ys4 = reinterpret_cast<const float4*>(sY + st * ROWS) + qr * 8;
-      const uint32_t tS = tmem_S + (uint32_t)buf * 128u + lane_sel + (uint32_t)qr * 32u;
       float bsum = 0.f;
-      uint32_t v[32];
-      tmem_ld32(tS, v);
-      tmem_ld_wait();
-      uint32_t hi[16], lo[16];
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int ch = 2 * h + cc;
+        const float4* ys4 = reinterpret_cast<const float4*>(sY + st * ROWS) + ch * 8;
+        const uint32_t tS = tmem_S + (uint32_t)buf * 128u + lane_sel + (uint32_t)ch * 32u;
+        uint32_t v[32];
+        tmem_ld32(tS, v);
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {       // 8 elements share one lg2 (log of a product)
-        const float4 ya = ys4[g8 * 2], yb = ys4[g8 * 2 + 1];
-        const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-        float prod = 1.f;
-        float rr[8];
+        for (int g8 = 0; g8 < 4; ++g8) {       // 8 elements share one lg2 (log of a product)
+          const float4 ya = ys4[g8 * 2], yb = ys4[g8 * 2 + 1];
+          const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+          float prod = 1.f;
+          float rr[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float eta = __uint_as_float(v[g8 * 8 + e]);
-          const float t = ex2_approx(fabsf(eta) * NLOG2E);          // exp(-|eta|)
-          const float d = 1.0f + t;
-          prod *= d;
-          const float w = t * rcp_approx(d);                         // sigmoid(-|eta|) in (0, 1/2]
-          // sigma = eta >= 0 ? 1 - w : w ;  r = y - sigma = (y - [eta >= 0]) + copysign(w, eta)
-          const float ys = yy[e] - (eta >= 0.f ? 1.f : 0.f);
-          rr[e] = ys + __uint_as_float(__float_as_uint(w) | (__float_as_uint(eta) & 0x80000000u));
-          bsum = fmaf(eta, ys, bsum);                                // y*eta - max(eta, 0)
+          for (int e = 0; e < 8; ++e) {
+            const float eta = __uint_as_float(v[g8 * 8 + e]);
+            const float t = ex2_approx(fabsf(eta) * NLOG2E);          // exp(-|eta|)
+            const float d = 1.0f + t;
+            prod *= d;
+            const float w = t * rcp_approx(d);                         // sigmoid(-|eta|) in (0, 1/2]
+            // sigma = eta >= 0 ? 1 - w : w ;  r = y - sigma = (y - [eta >= 0]) + copysign(w, eta)
+            const float ys = yy[e] - (eta >= 0.f ? 1.f : 0.f);
+            rr[e] = ys + __uint_as_float(__float_as_uint(w) | (__float_as_uint(eta) & 0x80000000u));
+            bsum = fmaf(eta, ys, bsum);                                // y*eta - max(eta, 0)
+          }
+          bsum = fmaf(-LN2, lg2_approx(prod), bsum);                   // - sum log(1 + exp(-|eta|))
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const uint32_t hh = pack_bf16(rr[e], rr[e + 1]);
+            const float h0 = __uint_as_float(hh << 16), h1 = __uint_as_float(hh & 0xffff0000u);
+            hi[(g8 * 8 + e) >> 1] = hh;
+            lo[(g8 * 8 + e) >> 1] = pack_bf16(rr[e] - h0, rr[e + 1] - h1);
+          }
         }
-        bsum = fmaf(-LN2, lg2_approx(prod), bsum);                   // - sum log(1 + exp(-|eta|))
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-          const uint32_t hh = pack_bf16(rr[e], rr[e + 1]);
-          const float h0 = __uint_as_float(hh << 16), h1 = __uint_as_float(hh & 0xffff0000u);
-          hi[(g8 * 8 + e) >> 1] = hh;
-          lo[(g8 * 8 + e) >> 1] = pack_bf16(rr[e] - h0, rr[e + 1] - h1);
-        }
+        tmem_st16(tS, hi);
+        tmem_st16(tS + 16u, lo);
       }
-      tmem_st16(tS, hi);
-      tmem_st16(tS + 16u, lo);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&r_full[buf]);
       lsum += (double)bsum;
-      ++in_period;
-      if (i + 1 == nb || in_period == fe) {
-        // drain the GEMM2 accumulator of this period and add it outside the tensor core
+      if (i + 1 == nb || (i % fe) == fe - 1) {
+        // this block closes flush period i / fe: drain the GEMM2 accumulator and add it outside
+        // the tensor core (the other group keeps working on block i + 1 meanwhile)
+        const int period = i / fe;
         mbar_wait(g_full, (uint32_t)period & 1u);
         tc_fence_after();
-        if (qr * 32 < dk) {
-          tmem_ld32(tmem_G + lane_sel + (uint32_t)qr * 32u, v);
-          tmem_ld_wait();
-          if (row < nrows) {
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ch = 2 * h + cc;
+          if (ch * 32 < dk) {
+            uint32_t v[32];
+            tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, v);
+            tmem_ld_wait();
+            if (row < nrows) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int d = qr * 32 + j;
-              if (d < dk) {
-                float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                       __uint_as_float(v[j + 3]));
-                float4* gp = reinterpret_cast<float4*>(gout + d);
-                if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
-                *gp = a;
+              for (int j = 0; j < 32; j += 4) {
+                const int d = ch * 32 + j;
+                if (d < dk) {
+                  float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                         __uint_as_float(v[j + 3]));
+                  float4* gp = reinterpret_cast<float4*>(gout + d);
+                  if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+                  *gp = a;
+                }
               }
             }
           }
         }
         tc_fence_before();
         mbar_arrive(g_empty);
-        ++period;
-        in_period = 0;
       }
     }
     // rows >= N of the last block are zero padding: eta = 0, y = 0 -> each contributed -log 2
-    if (qr == 0 && b1 == nblk_total) lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
-    // combine the four row quarters of each chain and publish
+    if (h == 0 && grp == ((nb - 1) & 1) && nb > 0 && b1 == nblk_total)
+      lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
+    // combine the four partial sums of each chain (2 groups x 2 column halves) and publish
     double* lp = reinterpret_cast<double*>(sX);   // X stages are dead by now
+    const int part = grp * 2 + h;
     asm volatile("bar.sync 1, 512;" ::: "memory");
-    if (qr > 0) lp[(qr - 1) * 128 + q * 32 + lane] = lsum;
+    if (part > 0) lp[(part - 1) * 128 + q * 32 + lane] = lsum;
     asm volatile("bar.sync 1, 512;" ::: "memory");
-    if (qr == 0 && row < nrows) {
+    if (part == 0 && row < nrows) {
       if (nb == 0) for (int d = 0; d < Dp; ++d) gout[d] = 0.f;
       const int k = q * 32 + lane;
       Ld[(size_t)split * nrows + row] = ((lsum + lp[k]) + lp[128 + k]) + lp[256 + k];
