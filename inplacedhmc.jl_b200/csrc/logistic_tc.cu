@@ -253,7 +253,10 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0 && nb > 0) {
+    // The whole warp runs this loop convergently so descriptors and addresses stay in uniform
+    // registers; only the tcgen05.mma / tcgen05.commit instructions are issued by lane 0.
+    if (nb > 0) {
+      const bool lead = (lane == 0);
       constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
       constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
       const uint32_t aX = smem_u32(sX);
@@ -274,9 +277,10 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
           for (int kk = 0; kk < NK; ++kk) {
             const uint64_t off = (uint64_t)(((kk >> 2) * CHUNK_BYTES + (kk & 3) * 32) >> 4);
-            mma_ss(d, dB[term] + off, dX + off, IDESC1, (term | kk) ? 1u : 0u);
+            if (lead) mma_ss(d, dB[term] + off, dX + off, IDESC1, (term | kk) ? 1u : 0u);
           }
-        tc_commit(&s_full[buf]);
+        if (lead) tc_commit(&s_full[buf]);
+        __syncwarp();
       };
       gemm1(0);
       if (nb > 1) gemm1(1);
@@ -294,16 +298,17 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         for (int term = 0; term < 2; ++term)
 #pragma unroll
           for (int kk = 0; kk < ROWS / 16; ++kk)
-            mma_ts(tmem_G, a + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8 + term * 16), dXm + (uint64_t)(kk * 2048 >> 4), IDESC2,
-                   (term | kk) ? 1u : acc0);
-        tc_commit(&x_empty[st]);
-        tc_commit(&sr_empty[buf]);
+            if (lead)
+              mma_ts(tmem_G, a + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8 + term * 16), dXm + (uint64_t)(kk * 2048 >> 4), IDESC2,
+                     (term | kk) ? 1u : acc0);
+        if (lead) { tc_commit(&x_empty[st]); tc_commit(&sr_empty[buf]); }
         ++in_period;
         if (i + 1 == nb || (i % fe) == fe - 1) {
-          tc_commit(g_full);
+          if (lead) tc_commit(g_full);
           ++period;
           in_period = 0;
         }
+        __syncwarp();
       }
     }
   } else {
