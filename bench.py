@@ -123,14 +123,14 @@ def run_reference(a, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=4096)
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=100)
     ap.add_argument("--adapt", type=int, default=100, help="dual-averaging transitions before timing (untimed)")
-    ap.add_argument("--transitions", type=int, default=4, help="NUTS transitions per chain per step")
+    ap.add_argument("--transitions", type=int, default=16, help="NUTS transitions per chain per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -213,6 +213,9 @@ def main():
     dt = allmax(time.perf_counter() - t0)
     e2e = allsum(leap_e2e) / dt
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = {}
@@ -228,7 +231,7 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 (bf16x2-split operands on tcgen05, fp32 accumulate)", "data": "synthetic",
+        "dtype": "f32 (exact bf16 operand splits on tcgen05, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": "c3: Bayesian logistic regression N=%d D=%d, %d chains total, max_depth 10" % (N, D, C * world),
                    "chains_per_gpu": C, "parallelism": "chains sharded, no collective",
                    "l2": "inputs larger than L2 (X is %d MB bf16)" % (N * 128 * 2 // 2**20),
@@ -250,8 +253,6 @@ def main():
         v, cores, sample = cpu_leapfrog_rate(bits, y, D, budget_s=15.0)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(out))
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
