@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--chains", type=int, default=4096)
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=100)
-    ap.add_argument("--adapt", type=int, default=100, help="dual-averaging transitions before timing (untimed)")
+    ap.add_argument("--adapt", type=int, default=40, help="length of the first/last step-size-only warmup stage (untimed)")
     ap.add_argument("--transitions", type=int, default=16, help="NUTS transitions per chain per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -174,8 +174,14 @@ def main():
     q0 = beta[None, :] + rng.normal(size=(C, D)) * 2e-3
     e.set_positions(q0)
     e.find_initial_stepsize()
+    # ≙ default_warmup_stages (src/warmup.jl:361-372) with shorter windows: step size only, then
+    # step size + per-chain diagonal metric in doubling windows, then step size only
+    t_w = time.perf_counter()
     if a.adapt > 0:
-        e.warmup_stage(a.adapt, bn.METRIC_NONE, keep=False)
+        for n, mk in ((a.adapt, bn.METRIC_NONE), (25, bn.METRIC_DIAG), (50, bn.METRIC_DIAG), (100, bn.METRIC_DIAG),
+                      (a.adapt, bn.METRIC_NONE)):
+            e.warmup_stage(n, mk, keep=False)
+    t_w = time.perf_counter() - t_w
     T = a.transitions
     for _ in range(a.warmup):
         e.sample_device_only(T)
@@ -235,7 +241,7 @@ def main():
         "config": {"workload": "c3: Bayesian logistic regression N=%d D=%d, %d chains total, max_depth 10" % (N, D, C * world),
                    "chains_per_gpu": C, "parallelism": "chains sharded, no collective",
                    "l2": "inputs larger than L2 (X is %d MB bf16)" % (N * 128 * 2 // 2**20),
-                   "init": "beta* + 2e-3 N(0,1); initial step size search + %d dual-averaging transitions untimed" % a.adapt,
+                   "init": "beta* + 2e-3 N(0,1); untimed warmup: step size search, stages %d|25,50,100 (diag metric)|%d, %.1f s" % (a.adapt, a.adapt, t_w),
                    "step": "%d NUTS transitions of every chain (async within the call)" % T,
                    "mean_tree_depth": float(stats["depth"].mean()), "mean_leapfrogs_per_transition": float(stats["steps"].mean()),
                    "lockstep_steps_timed": int(c1["lockstep_steps"] - c0["lockstep_steps"]),
