@@ -232,8 +232,9 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained")
     peak_src = "measured sustained (MEASURED_PEAKS.json)" if peak_tf else "fallback 1400 (B200_PROFILING.md)"
     peak_tf = peak_tf or 1400.0
-    flops_per_launch = 4.0 * N * D * C           # algorithmic: X·B and Xᵀ·R, true D, 2 flop per MAC
-    ach = flops_per_launch / (grad_ms / max(grad_n, 1) * 1e-3) / 1e12 if grad_n else None
+    rows = c1["gradient_rows"] - c0["gradient_rows"]   # active chains summed over the gradient launches
+    # algorithmic flops: X·B and Xᵀ·R with the true D, 2 flop per MAC, only rows that were requested
+    ach = 4.0 * N * D * rows / (grad_ms * 1e-3) / 1e12 if grad_n else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -250,7 +251,7 @@ def main():
         "leapfrogs_timed": int(leap),
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (ach / peak_tf) if ach else None, "traffic": None, "kernel": "k_logistic_tc",
-                     "launches": int(grad_n), "avg_launch_ms": grad_ms / max(grad_n, 1), "peak_source": peak_src,
+                     "launches": int(grad_n), "avg_launch_ms": grad_ms / max(grad_n, 1), "avg_rows_per_launch": rows / max(grad_n, 1), "peak_source": peak_src,
                      "kernel_share_of_step": grad_ms / ms},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(qh.nbytes), "d2h_bytes_per_step": int(chain.nbytes + stats.nbytes)},
         "clocks": clk,

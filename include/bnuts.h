@@ -82,6 +82,7 @@ typedef struct {
   int64_t lockstep_steps;   /* kernel-level leapfrog rounds launched */
   int64_t kernel_launches;  /* launches of this library's kernels */
   int64_t divergences;
+  int64_t gradient_rows;    /* staging rows evaluated by the batched gradient kernel (active chains summed over launches) */
 } bnuts_counter_block;
 
 int32_t bnuts_create(const bnuts_config* cfg, bnuts_engine** out);

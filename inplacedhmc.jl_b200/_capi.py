@@ -43,7 +43,7 @@ class StepsizeSearchParams(C.Structure):
 
 class CounterBlock(C.Structure):
     _fields_ = [("leapfrogs", C.c_int64), ("transitions", C.c_int64), ("lockstep_steps", C.c_int64),
-                ("kernel_launches", C.c_int64), ("divergences", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("divergences", C.c_int64), ("gradient_rows", C.c_int64)]
 
 
 # ≙ TreeStatisticsNUTS (src/NUTS.jl:229-242): 32-byte record

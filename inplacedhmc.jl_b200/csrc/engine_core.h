@@ -220,6 +220,7 @@ template <class T, class X> struct EngineCore {
         M.stage_nb = x.gradient(*this, (int)np);
         M.stage_rows = (int32_t)np;
         counters.kernel_launches += 1;
+        counters.gradient_rows += np;
       }
       np = x.advance(M, rp, iters);
       counters.kernel_launches += 1;
