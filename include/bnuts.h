@@ -101,6 +101,14 @@ int32_t bnuts_model_gaussian(bnuts_engine* e, const double* precision /* [D][D] 
 int32_t bnuts_model_logistic(bnuts_engine* e, const void* X, int32_t x_dtype, const double* y,
                              int64_t N, double prior_precision, int32_t row_blocks);
 
+/* Tensor-core logistic path only; no reference counterpart (the reference's first warmup stage,
+ * FindLocalOptimum src/warmup.jl:152-186, is what produces such a point).  beta_ref [D] near the
+ * posterior mode lets the kernel evaluate X·beta as X·beta_ref (stored) + X·(beta − beta_ref) with
+ * two instead of three bf16 terms for the fp32 position.  The point is checked: if the gradient
+ * there exceeds sqrt(N·D)/2 the call fails with BNUTS_ERR_INVALID_ARGUMENT and the exact
+ * three-term path stays in force.  beta_ref == NULL returns to the three-term path. */
+int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double* beta_ref);
+
 /* ≙ initialize_warmup_state(q = …), src/warmup.jl:100-129: sets q and evaluates
  * ℓ, ∇ℓ.  q == NULL draws U[-2,2]^D (src/warmup.jl:73) from Philox. */
 int32_t bnuts_set_positions(bnuts_engine* e, const double* q /* [C][D] */);

@@ -53,7 +53,7 @@ assert TREE_STATS_DTYPE.itemsize == 32
 
 EXPORTS = [
     "bnuts_create", "bnuts_destroy", "bnuts_last_error", "bnuts_model_iid_normal", "bnuts_model_funnel",
-    "bnuts_model_gaussian", "bnuts_model_logistic", "bnuts_set_positions", "bnuts_get_state",
+    "bnuts_model_gaussian", "bnuts_model_logistic", "bnuts_logistic_set_reference", "bnuts_set_positions", "bnuts_get_state",
     "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed",
     "bnuts_inject", "bnuts_leapfrog", "bnuts_find_initial_stepsize", "bnuts_warmup_stage", "bnuts_sample",
     "bnuts_counters", "bnuts_profile", "bnuts_chain_status",
@@ -83,6 +83,7 @@ def load_library(path=None):
         getattr(lib, n).argtypes = [_P]
     lib.bnuts_model_gaussian.argtypes = [_P, _P]
     lib.bnuts_model_logistic.argtypes = [_P, _P, C.c_int32, _P, C.c_int64, C.c_double, C.c_int32]
+    lib.bnuts_logistic_set_reference.argtypes = [_P, _P]
     lib.bnuts_set_positions.argtypes = [_P, _P]
     lib.bnuts_get_state.argtypes = [_P, _P, _P, _P]
     lib.bnuts_set_metric_diag.argtypes = [_P, _P]
@@ -169,6 +170,12 @@ class Engine:
         y = _f64(y, (X.shape[0],))
         self._chk(self.lib.bnuts_model_logistic(self.h, _ptr(X), x_dtype, _ptr(y), X.shape[0], prior_precision,
                                                 row_blocks))
+
+    def logistic_set_reference(self, beta_ref=None):
+        """Tensor-core logistic path: evaluate X·β as X·β_ref + X·(β − β_ref) (two bf16 terms instead of
+        three).  β_ref must sit near the posterior mode (checked); None returns to the exact path."""
+        b = _f64(beta_ref, (self.D,))
+        self._chk(self.lib.bnuts_logistic_set_reference(self.h, _ptr(b)))
 
     # ---- state
     def set_positions(self, q=None, allow_nonfinite=False):

@@ -43,6 +43,8 @@ template <class T> struct EngineMem {
   unsigned long long* stage_count;  // rows handed out in the current lockstep step
   int32_t stage_rows;            // rows of the request being consumed (stride of the partials)
   int32_t Dt;            // padded K of the tensor path
+  const T* beta_ref;     // [Dp] reference point of the tensor path (staged operand is q − beta_ref), or null
+  const double* lin_w;   // [Dp] tensor path: the kernel's log-density partials omit ½ Σ_d lin_w[d] q[d]
   T tau;                 // logistic prior precision
   // per-call outputs
   double* draws;         // [C][N][D]
@@ -170,7 +172,7 @@ template <class T, class LP> struct Backend {
   BN_HD void stage_put(int row, int d, T qd) const {
     M.stage_q[(int64_t)row * M.Dp + d] = qd;
     if (M.stage_bh) {
-      const float qf = (float)qd;
+      const float qf = (float)qd - (M.beta_ref ? (float)M.beta_ref[d] : 0.f);
       const uint16_t h = bf16_bits(qf);
       const float r1 = qf - bf16_val(h);
       const uint16_t m = bf16_bits(r1);
@@ -318,6 +320,15 @@ template <class T, class LP> struct Backend {
         if (M.stage_ld) {  // tensor path: partials are ~1e5 in magnitude, summed in Float64
           double lsd = 0.0;
           for (int b = 0; b < M.stage_nb; ++b) lsd = lsd + M.stage_ld[b * rows + row];
+          if (M.lin_w) {  // linear part of Σ log σ(η̃): ½ Σ_i η̃_i = ½ colsum(X̃)·q
+            double part[LP::NACC];
+            for (int i = 0; i < LP::NACC; ++i) part[i] = 0.0;
+            for (int d = lp.first(); d < M.D; d += lp.stride()) {
+              double& a = part[lp.acc(d)];
+              a = fma_(M.lin_w[d], (double)q[d], a);
+            }
+            lsd = fma_(0.5, lp.reduce(part), lsd);
+          }
           ls = T(lsd);
         } else {
           for (int b = 0; b < M.stage_nb; ++b) ls = ls + M.stage_l[b * rows + row];

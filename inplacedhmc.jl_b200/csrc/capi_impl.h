@@ -69,6 +69,7 @@ int32_t bnuts_model_logistic(bnuts_engine* e, const void* X, int32_t xd, const d
                              int32_t rb) {
   BN_DISPATCH(e, model_logistic(X, xd, y, N, tau, rb));
 }
+int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double* beta_ref) { BN_DISPATCH(e, logistic_set_reference(beta_ref)); }
 int32_t bnuts_set_positions(bnuts_engine* e, const double* q) { BN_DISPATCH(e, set_positions(q)); }
 int32_t bnuts_get_state(bnuts_engine* e, double* q, double* g, double* l) { BN_DISPATCH(e, get_state(q, g, l)); }
 int32_t bnuts_set_metric_diag(bnuts_engine* e, const double* m) { BN_DISPATCH(e, set_metric(m)); }

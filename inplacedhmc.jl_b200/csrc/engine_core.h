@@ -104,6 +104,7 @@ template <class T, class X> struct EngineCore {
     for (void** p : ps) if (*p) { x.free(*p); *p = nullptr; }
     model = ModelCtx<T>();
     M.stage_nb = 0;
+    M.beta_ref = nullptr; M.lin_w = nullptr;
   }
   int32_t model_simple(int kind) {
     free_model();
@@ -173,6 +174,13 @@ template <class T, class X> struct EngineCore {
     M.tau = T(tau);
     model.kind = MODEL_LOGISTIC; M.model_kind = MODEL_LOGISTIC;
     return x.check(err);
+  }
+
+  // reference point of the tensor-core logistic path (numerical device, see include/bnuts.h)
+  int32_t logistic_set_reference(const double* beta_ref) {
+    if (model.kind != MODEL_LOGISTIC || !model.tensor)
+      return fail(BNUTS_ERR_UNSUPPORTED, "reference point applies to the tensor-core logistic path only");
+    return x.logistic_reference(*this, beta_ref, err);
   }
 
   // ---------------------------------------------------------------- state setters

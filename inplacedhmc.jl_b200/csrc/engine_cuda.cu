@@ -303,6 +303,9 @@ struct CudaExec {
   template <class E> int32_t logistic_tensor_setup(E& eng, const void* Xh, int32_t xd, const double* y, int64_t N, std::string& err) {
     return logistic_tc_setup(tc, eng, Xh, xd, y, N, err);
   }
+  template <class E> int32_t logistic_reference(E& eng, const double* beta_ref, std::string& err) {
+    return logistic_tc_set_reference(tc, eng, beta_ref, err);
+  }
   template <class T> void metric_update(const EngineMem<T>& M, int N, double lambda) {
     k_metric<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, N, lambda);
   }

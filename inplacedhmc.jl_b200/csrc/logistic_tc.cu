@@ -6,6 +6,11 @@
 //     H = X·B            (N x C, never materialised)
 //     R = y − σ(H),  ℓ_c = Σ_i [y_i H_ic − softplus(H_ic)]
 //     G = Xᵀ·R           (D x C)
+// evaluated in the sign-folded form: with X̃_i = (2y_i − 1)·X_i (a sign flip of bf16 rows,
+// done once at set-up) and H̃ = X̃·B,
+//     ℓ_c = Σ_i log σ(H̃_ic),   G = X̃ᵀ·σ(−H̃)
+// so the kernel never touches y.  Σ_i min(H̃,0) is taken as ½(Σ H̃ − Σ|H̃|); the linear part
+// Σ_i H̃_ic = colsum(X̃)·β_c is added by the consumer (backend.h model_grad) in Float64.
 // One CTA owns a tile of 128 chains and a contiguous range of 128-row blocks of X.
 // Chains are the MMA M dimension, so TMEM lane = chain: each elementwise thread
 // owns one chain, the sum over data rows is a serial per-thread accumulation and
@@ -17,7 +22,11 @@
 //                                                                               tile read MN-major)
 // fp32 accuracy on bf16 tensor cores: X is exact in bf16 (checked at set-up); the
 // fp32 position is split exactly in three bf16 terms (β = βh + βm + βl, 3 x 8
-// mantissa bits), the residual in two (r = rh + rl), all accumulated in fp32; the
+// mantissa bits).  With a reference point β₀ near the mode (bnuts_logistic_set_reference)
+// the kernel evaluates H̃ = H̃₀ + X̃·(β − β₀): H̃₀ = X̃·β₀ is stored, split in three bf16
+// terms, in three spare K columns of X̃ (the matching β columns hold 1), and β − β₀ is small
+// enough that two bf16 terms carry it (nterms = 2).  The residual is split in two
+// (r = rh + rl), all accumulated in fp32; the
 // TMEM accumulator of GEMM2 is drained every `flush_every` row blocks and summed
 // outside the tensor core (bounds accumulator rounding drift).  Three S/R buffers in
 // TMEM give the elementwise warps two block-times of slack behind the tensor pipe.
@@ -81,6 +90,18 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// one elected lane of a converged warp (the form ptxas turns into ELECT + a predicated instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -162,6 +183,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return r;
 }
 
+// 1/d for d in (1,2], two lanes at a time.  SW = 0: MUFU.RCP.  SW = 1: FMA-pipe only (quadratic
+// minimax seed 32/99 d^2 - 144/99 d + 210/99, relative error 1.01e-2, then y <- y + y(e + e^2 + e^3),
+// e = 1 - d y: 1.3e-7 after rounding),
+// used for a fraction of the elements to take load off the MUFU pipe.
+__device__ __forceinline__ float2 rcp2(float2 d, bool sw) {
+  if (!sw) {
+    return make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  } else {
+    const float2 c2 = make_float2(0.32323232f, 0.32323232f), c1 = make_float2(-1.45454545f, -1.45454545f),
+                 c0 = make_float2(2.12121212f, 2.12121212f), one = make_float2(1.f, 1.f);
+    const float2 md = make_float2(-d.x, -d.y);
+    float2 y = __ffma2_rn(__ffma2_rn(c2, d, c1), d, c0);
+    const float2 e = __ffma2_rn(md, y, one);
+    const float2 p = __ffma2_rn(__ffma2_rn(e, e, e), e, e);   // e + e^2 + e^3
+    y = __ffma2_rn(y, p, y);
+    return y;
+  }
+}
+#ifndef BNUTS_TC_RCPSW
+#define BNUTS_TC_RCPSW 0x00   // bit k set: pair k of every 8 pairs uses the FMA-pipe reciprocal
+#endif
+constexpr int RCPSW = BNUTS_TC_RCPSW;
+
 template <int DT> struct SmemPlan {
   static constexpr int KC = DT / 64;
   static constexpr int B_BYTES = KC * CHUNK_BYTES;   // one β term
@@ -170,9 +214,8 @@ template <int DT> struct SmemPlan {
   static constexpr int NSB = 3;                      // S/R buffers in TMEM
   static constexpr int OFF_B = 0;                    // 3 terms
   static constexpr int OFF_X = 3 * B_BYTES;
-  static constexpr int OFF_Y = OFF_X + NS * X_BYTES;
-  static constexpr int OFF_BAR = OFF_Y + NS * ROWS * 4;
-  static constexpr int NBAR = 1 + 2 * NS + 3 * NSB + 2;
+  static constexpr int OFF_BAR = OFF_X + NS * X_BYTES;
+  static constexpr int NBAR = 1 + 2 * NS + 2 * NSB + 2;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
 };
 
@@ -183,8 +226,8 @@ template <int DT, int NK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBm, const __grid_constant__ CUtensorMap tmBl,
-              const float* __restrict__ y, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total,
-              int nsplit, int flush_every) {
+              float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total, int nsplit, int flush_every,
+              int nterms) {
   using P = SmemPlan<DT>;
   constexpr int dk = NK * 16;
   constexpr int NS = P::NS;
@@ -193,15 +236,13 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   extern __shared__ __align__(1024) unsigned char smem[];   // SW128 tiles need 1024 B alignment (checked below)
   unsigned char* sB = smem + P::OFF_B;
   unsigned char* sX = smem + P::OFF_X;
-  float* sY = reinterpret_cast<float*>(smem + P::OFF_Y);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
   uint64_t* bar_b = bars;               // β tiles landed
   uint64_t* x_full = bars + 1;          // [NS]
   uint64_t* x_empty = x_full + NS;      // [NS]
   uint64_t* s_full = x_empty + NS;      // [NSB] GEMM1 done
   uint64_t* r_full = s_full + NSB;      // [NSB] residual written to TMEM
-  uint64_t* sr_empty = r_full + NSB;    // [NSB] GEMM2 done with the buffer
-  uint64_t* g_full = sr_empty + NSB;    // accumulator complete for its flush period
+  uint64_t* g_full = r_full + NSB;      // accumulator complete for its flush period
   uint64_t* g_empty = g_full + 1;       // accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
 
@@ -216,7 +257,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (smem_u32(smem) & 1023u) asm volatile("trap;");
     mbar_init(bar_b, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 256); mbar_init(&sr_empty[i], 1); }
+    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 256); }
     mbar_init(g_full, 1);
     mbar_init(g_empty, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -245,10 +286,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         const int st = i % NS;
         const uint32_t ph = (uint32_t)(i / NS) & 1u;
         mbar_wait(&x_empty[st], ph ^ 1u);
-        mbar_expect_tx(&x_full[st], P::X_BYTES + ROWS * 4);
+        mbar_expect_tx(&x_full[st], P::X_BYTES);
         for (int kc = 0; kc < KC; ++kc)
           tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK_BYTES, &x_full[st], kc * 64, (b0 + i) * ROWS);
-        bulk_load_1d(sY + st * ROWS, y + (size_t)(b0 + i) * ROWS, ROWS * 4, &x_full[st]);
       }
     }
   } else if (warp == 1) {
@@ -256,7 +296,6 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // The whole warp runs this loop convergently so descriptors and addresses stay in uniform
     // registers; only the tcgen05.mma / tcgen05.commit instructions are issued by lane 0.
     if (nb > 0) {
-      const bool lead = (lane == 0);
       constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
       constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
       const uint32_t aX = smem_u32(sX);
@@ -266,20 +305,24 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       for (int term = 0; term < 3; ++term) dB[term] = desc_kmajor(smem_u32(sB) + (uint32_t)term * P::B_BYTES, 0);
       mbar_wait(bar_b, 0);
       auto gemm1 = [&](int i) {
-        const int st = i % NS, buf = i % NSB, u = i / NSB;
+        const int st = i % NS, buf = i % NSB;
         mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
-        if (u >= 1) mbar_wait(&sr_empty[buf], (uint32_t)(u - 1) & 1u);
+        // No wait for the S/R buffer: its previous user is GEMM2(i - 3), issued earlier by this same
+        // thread, and tcgen05.mma instructions of one thread execute in issue order; the elementwise
+        // warps' accesses to it were ordered before that GEMM2 by r_full.
         tc_fence_after();
         const uint64_t dX = desc_kmajor(aX + (uint32_t)st * P::X_BYTES, 0);
         const uint32_t d = tmem_S + (uint32_t)buf * 128u;
 #pragma unroll
         for (int term = 0; term < 3; ++term)
+          if (term < nterms) {
 #pragma unroll
-          for (int kk = 0; kk < NK; ++kk) {
-            const uint64_t off = (uint64_t)(((kk >> 2) * CHUNK_BYTES + (kk & 3) * 32) >> 4);
-            if (lead) mma_ss(d, dB[term] + off, dX + off, IDESC1, (term | kk) ? 1u : 0u);
+            for (int kk = 0; kk < NK; ++kk) {
+              const uint64_t off = (uint64_t)(((kk >> 2) * CHUNK_BYTES + (kk & 3) * 32) >> 4);
+              if (elect_one()) mma_ss(d, dB[term] + off, dX + off, IDESC1, (term | kk) ? 1u : 0u);
+            }
           }
-        if (lead) tc_commit(&s_full[buf]);
+        if (elect_one()) tc_commit(&s_full[buf]);
         __syncwarp();
       };
       gemm1(0);
@@ -298,13 +341,13 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         for (int term = 0; term < 2; ++term)
 #pragma unroll
           for (int kk = 0; kk < ROWS / 16; ++kk)
-            if (lead)
+            if (elect_one())
               mma_ts(tmem_G, a + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8 + term * 16), dXm + (uint64_t)(kk * 2048 >> 4), IDESC2,
                      (term | kk) ? 1u : acc0);
-        if (lead) { tc_commit(&x_empty[st]); tc_commit(&sr_empty[buf]); }
+        if (elect_one()) tc_commit(&x_empty[st]);
         ++in_period;
         if (i + 1 == nb || (i % fe) == fe - 1) {
-          if (lead) tc_commit(g_full);
+          if (elect_one()) tc_commit(g_full);
           ++period;
           in_period = 0;
         }
@@ -323,57 +366,55 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int row = tile * CHAINS + q * 32 + lane;   // staging row = chain slot
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     double lsum = 0.0;
-    const float NLOG2E = -1.4426950408889634f, LN2 = 0.6931471805599453f;
+    const float2 L2E2 = make_float2(1.4426950408889634f, 1.4426950408889634f);
+    const float2 ONE2 = make_float2(1.0f, 1.0f), MHALF2 = make_float2(-0.5f, -0.5f), HALF2 = make_float2(0.5f, 0.5f);
+    const float2 MONE2 = make_float2(-1.0f, -1.0f);
+    const float LN2 = 0.6931471805599453f;
     float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
     for (int i = grp; i < nb; i += 2) {
-      const int st = i % NS, buf = i % NSB, u = i / NSB;
-      mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);   // y of this block is visible
+      const int buf = i % NSB, u = i / NSB;
       mbar_wait(&s_full[buf], (uint32_t)u & 1u);
       tc_fence_after();
-      float bsum = 0.f;
+      float bsum = 0.f;   // sum over this thread's 64 elements of  log2(1 + 2^-|u|)
+      float asum = 0.f;   // sum of |eta|
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int ch = 2 * h + cc;
-        const float4* ys4 = reinterpret_cast<const float4*>(sY + st * ROWS) + ch * 8;
         const uint32_t tS = tmem_S + (uint32_t)buf * 128u + lane_sel + (uint32_t)ch * 32u;
         uint32_t v[32];
         tmem_ld32(tS, v);
         tmem_ld_wait();
         uint32_t hi[16], lo[16];
+        float2 prod = ONE2;
+        float as0 = 0.f, as1 = 0.f;
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {       // 8 elements share one lg2 (log of a product)
-          const float4 ya = ys4[g8 * 2], yb = ys4[g8 * 2 + 1];
-          const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-          float prod = 1.f;
-          float rr[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float eta = __uint_as_float(v[g8 * 8 + e]);
-            const float t = ex2_approx(fabsf(eta) * NLOG2E);          // exp(-|eta|)
-            const float d = 1.0f + t;
-            prod *= d;
-            const float w = t * rcp_approx(d);                         // sigmoid(-|eta|) in (0, 1/2]
-            // sigma = eta >= 0 ? 1 - w : w ;  r = y - sigma = (y - [eta >= 0]) + copysign(w, eta)
-            const float ys = yy[e] - (eta >= 0.f ? 1.f : 0.f);
-            rr[e] = ys + __uint_as_float(__float_as_uint(w) | (__float_as_uint(eta) & 0x80000000u));
-            bsum = fmaf(eta, ys, bsum);                                // y*eta - max(eta, 0)
-          }
-          bsum = fmaf(-LN2, lg2_approx(prod), bsum);                   // - sum log(1 + exp(-|eta|))
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            const uint32_t hh = pack_bf16(rr[e], rr[e + 1]);
-            const float h0 = __uint_as_float(hh << 16), h1 = __uint_as_float(hh & 0xffff0000u);
-            hi[(g8 * 8 + e) >> 1] = hh;
-            lo[(g8 * 8 + e) >> 1] = pack_bf16(rr[e] - h0, rr[e + 1] - h1);
-          }
+        for (int j = 0; j < 16; ++j) {
+          // eta = H~ (natural units); t = exp(-|eta|) in (0,1]; d = 1 + t in (1,2]
+          const float e0 = __uint_as_float(v[2 * j]), e1 = __uint_as_float(v[2 * j + 1]);
+          const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
+          const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
+          prod = __fmul2_rn(prod, d2);                       // 32 factors in (1,2]: no overflow
+          as0 += fabsf(e0); as1 += fabsf(e1);
+          // rc = 1/d = sigma(|eta|) in [1/2,1);  sigma(-eta) = 1/2 - copysign(rc - 1/2, eta)
+          const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
+          const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
+                                        __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
+          const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
+          const uint32_t hh = pack_bf16(r2.x, r2.y);
+          const float2 hv = make_float2(__uint_as_float(hh << 16), __uint_as_float(hh & 0xffff0000u));
+          const float2 l2 = __ffma2_rn(hv, MONE2, r2);
+          hi[j] = hh;
+          lo[j] = pack_bf16(l2.x, l2.y);
         }
+        bsum += lg2_approx(prod.x * prod.y);
+        asum += as0 + as1;
         tmem_st16(tS, hi);
         tmem_st16(tS + 16u, lo);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&r_full[buf]);
-      lsum += (double)bsum;
+      lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);      // sum log sigma(eta) minus the linear part (added by the consumer)
       if (i + 1 == nb || (i % fe) == fe - 1) {
         // this block closes flush period i / fe: drain the GEMM2 accumulator and add it outside
         // the tensor core (the other group keeps working on block i + 1 meanwhile)
@@ -391,7 +432,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const int d = ch * 32 + j;
-                if (d < dk) {
+                if (d < dk && d < Dp) {   // dk can exceed the row stride Dp when the reference columns spill over
                   float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                          __uint_as_float(v[j + 3]));
                   float4* gp = reinterpret_cast<float4*>(gout + d);
@@ -469,8 +510,8 @@ template <int DT, int NK> void launch(LogisticTC& tc, cudaStream_t s, int nrows,
   dim3 grid(tiles, nsplit);
   CUtensorMap m[4];
   for (int i = 0; i < 4; ++i) std::memcpy(&m[i], tc.tmaps[i], sizeof(CUtensorMap));
-  k_logistic_tc<DT, NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.yf, tc.G, tc.Ld, nrows, tc.Dp,
-                                                           (long long)tc.N, (int)(tc.Npad / ROWS), nsplit, tc.flush_every);
+  k_logistic_tc<DT, NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
+                                                           (int)(tc.Npad / ROWS), nsplit, tc.flush_every, tc.nterms);
 }
 
 }  // namespace
@@ -508,31 +549,82 @@ void LogisticTC::run(cudaStream_t s, int nrows) {
 }
 void LogisticTC::destroy() {
   if (Xb) cudaFree(Xb);
-  if (yf) cudaFree(yf);
-  Xb = nullptr; yf = nullptr; ready = false;
+  if (colsum) cudaFree(colsum);
+  if (beta_ref) cudaFree(beta_ref);
+  Xb = nullptr; colsum = nullptr; beta_ref = nullptr; ready = false; nterms = 3;
+}
+
+namespace {
+// one thread per data row: H~0_i = sum_d X~_id beta_ref_d in Float64, rounded once to fp32 and
+// split exactly in three bf16 terms stored in columns D..D+2 of the row
+__global__ void k_write_reference(uint16_t* Xb, const float* __restrict__ beta_ref, long long N, int D, int Dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  uint16_t* xr = Xb + i * Dt;
+  uint16_t t0 = 0, t1 = 0, t2 = 0;
+  if (beta_ref) {
+    double acc = 0.0;
+    for (int d = 0; d < D; ++d) acc = fma((double)bf16_val(xr[d]), (double)beta_ref[d], acc);
+    const float e = (float)acc;
+    t0 = bf16_bits(e);
+    const float r1 = e - bf16_val(t0);
+    t1 = bf16_bits(r1);
+    t2 = bf16_bits(r1 - bf16_val(t1));
+  }
+  xr[D] = t0; xr[D + 1] = t1; xr[D + 2] = t2;
+}
+__global__ void k_init_stage(uint16_t* bh, int C, int D, int Dt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (int k = 0; k < 3; ++k) bh[(size_t)c * Dt + D + k] = 0x3F80;   // 1.0
+}
+}  // namespace
+
+void logistic_tc_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev) {
+  if (!tc.aug) return;
+  k_write_reference<<<(unsigned)((tc.N + 255) / 256), 256, 0, s>>>(tc.Xb, beta_ref_dev, (long long)tc.N, tc.D, tc.Dt);
+}
+void logistic_tc_init_stage(LogisticTC& tc, cudaStream_t s, uint16_t* bh) {
+  if (!tc.aug) return;
+  k_init_stage<<<(tc.C + 127) / 128, 128, 0, s>>>(bh, tc.C, tc.D, tc.Dt);
 }
 
 int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, int64_t N, int32_t C, int32_t D, int32_t Dp,
                           std::string& err) {
   tc.destroy();
   tc.C = C; tc.D = D; tc.Dp = Dp; tc.N = N;
-  tc.Dt = (D <= 64) ? 64 : 128;
-  tc.dk = (D + 15) / 16 * 16;
+  tc.aug = (D + 3 <= 128) ? 1 : 0;
+  tc.dk = (D + (tc.aug ? 3 : 0) + 15) / 16 * 16;
+  tc.Dt = (tc.dk <= 64) ? 64 : 128;
   tc.Npad = (N + ROWS - 1) / ROWS * ROWS;
   const char* fe = std::getenv("BNUTS_TC_FLUSH");
   if (fe) tc.flush_every = std::atoi(fe);
   const char* se = std::getenv("BNUTS_TC_NSPLIT");
   tc.force_nsplit = se ? std::atoi(se) : 0;
+  // sign-folded design matrix: row i multiplied by (2 y_i - 1) (flip of the bf16 sign bit)
   std::vector<uint16_t> xp(size_t(tc.Npad) * tc.Dt, 0);
-  for (int64_t i = 0; i < N; ++i) std::memcpy(&xp[size_t(i) * tc.Dt], &Xh[size_t(i) * D], size_t(D) * 2);
-  std::vector<float> yp(size_t(tc.Npad), 0.f);
-  for (int64_t i = 0; i < N; ++i) yp[size_t(i)] = float(y[i]);
-  if (cudaMalloc(&tc.Xb, xp.size() * 2) != cudaSuccess || cudaMalloc(&tc.yf, yp.size() * 4) != cudaSuccess) {
+  std::vector<double> cs(size_t(Dp), 0.0);
+  for (int64_t i = 0; i < N; ++i) {
+    if (y[i] != 0.0 && y[i] != 1.0) {
+      err = "tensor gradient path needs y in {0, 1}; use BNUTS_GRAD_DETERMINISTIC";
+      return BNUTS_ERR_UNSUPPORTED;
+    }
+    const uint16_t flip = (y[i] == 0.0) ? 0x8000 : 0;
+    uint16_t* dst = &xp[size_t(i) * tc.Dt];
+    const uint16_t* src = &Xh[size_t(i) * D];
+    for (int d = 0; d < D; ++d) {
+      dst[d] = src[d] ^ flip;
+      cs[d] += double(bf16_val(dst[d]));
+    }
+  }
+  if (cudaMalloc(&tc.Xb, xp.size() * 2) != cudaSuccess || cudaMalloc(&tc.colsum, cs.size() * 8) != cudaSuccess ||
+      cudaMalloc(&tc.beta_ref, size_t(Dp) * 4) != cudaSuccess) {
     err = "device allocation failed (tensor path X)";
     return BNUTS_ERR_CUDA;
   }
   cudaMemcpy(tc.Xb, xp.data(), xp.size() * 2, cudaMemcpyHostToDevice);
-  cudaMemcpy(tc.yf, yp.data(), yp.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(tc.colsum, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemset(tc.beta_ref, 0, size_t(Dp) * 4);
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&tc.sms, cudaDevAttrMultiProcessorCount, dev);

@@ -2,6 +2,7 @@
 // kernel (logistic_tc.cu).  fp32 engine only; X must lie on the bf16 grid.
 #pragma once
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include <type_traits>
@@ -14,14 +15,17 @@ namespace bn {
 
 struct LogisticTC {
   // problem
-  int32_t C = 0, D = 0, Dp = 0, Dt = 0, dk = 0;   // Dt: smem tile width (64|128), dk = round16(D): MMA K / N
+  int32_t C = 0, D = 0, Dp = 0, Dt = 0, dk = 0;   // Dt: smem tile width (64|128), dk: MMA K / N (multiple of 16)
+  int32_t aug = 0;           // 1: columns D..D+2 of X~ are reserved for the reference-point term (dk = round16(D+3))
+  int32_t nterms = 3;        // bf16 terms of the position operand: 3 (exact split) or 2 (with a reference point)
   int64_t N = 0, Npad = 0;
   int32_t flush_every = 32;  // row blocks per TMEM-accumulator flush (0 = only at the end)
   int32_t sms = 148, max_splits = 1, force_nsplit = 0, last_nsplit = 1;
   int64_t partial_rows = 0;  // rows needed in the partial-output buffers
   // device buffers owned here
-  uint16_t* Xb = nullptr;    // [Npad][Dt] bf16
-  float* yf = nullptr;       // [Npad]
+  uint16_t* Xb = nullptr;    // [Npad][Dt] bf16, rows sign-folded: X~_i = (2 y_i - 1) X_i
+  double* colsum = nullptr;  // [Dp] column sums of X~ (linear part of the log density)
+  float* beta_ref = nullptr; // [Dp] reference point (zeros when none is set)
   // borrowed from the engine
   const uint16_t* bh = nullptr; const uint16_t* bm = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
   float* G = nullptr;        // [nsplit][rows][Dp]
@@ -41,6 +45,11 @@ int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xbf16_host /*[N][D]*/,
                           int32_t C, int32_t D, int32_t Dp, std::string& err);
 
 int32_t logistic_tc_maps(LogisticTC& tc, std::string& err);
+
+// write H~0 = X~·beta_ref (three bf16 terms) into the reserved columns (beta_ref == nullptr: clear them)
+void logistic_tc_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev);
+// staging rows: 1.0 in the reserved columns of the high term
+void logistic_tc_init_stage(LogisticTC& tc, cudaStream_t s, uint16_t* bh);
 
 template <class E>
 int32_t logistic_tc_setup(LogisticTC& tc, E& eng, const void* Xh, int32_t xd, const double* y, int64_t N, std::string& err) {
@@ -77,10 +86,72 @@ int32_t logistic_tc_setup(LogisticTC& tc, E& eng, const void* Xh, int32_t xd, co
     M.stage_ld = eng.x.template alloc<double>(size_t(tc.partial_rows));
     eng.x.zero(M.stage_ld, size_t(tc.partial_rows) * sizeof(double));
     tc.bh = M.stage_bh; tc.bm = M.stage_bm; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.Ld = M.stage_ld;
+    logistic_tc_init_stage(tc, eng.x.stream, M.stage_bh);
+    M.lin_w = tc.colsum;
+    M.beta_ref = tc.beta_ref;
     rc = logistic_tc_maps(tc, err);
     if (rc) return rc;
     eng.model.Npad = tc.Npad;
     return 0;
+  }
+}
+
+// ≙ no reference counterpart (numerical device of the tensor path, see bnuts.h).  Evaluates the
+// gradient at beta_ref with the exact three-term path first and refuses a point whose gradient
+// is larger than a typical posterior-bulk gradient sqrt(tr H) <= sqrt(N D)/2: the two-term
+// split of beta - beta_ref is accurate relative to H·(beta - beta_ref), which is the gradient
+// only if beta_ref sits at the mode to within the posterior width.
+template <class E>
+int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref, std::string& err) {
+  using T = typename std::remove_reference<decltype(*eng.M.zs)>::type;
+  if constexpr (!std::is_same<T, float>::value) {
+    err = "reference point needs the tensor gradient path (dtype F32)";
+    return BNUTS_ERR_UNSUPPORTED;
+  } else {
+    auto& M = eng.M;
+    auto& x = eng.x;
+    if (!tc.ready) { err = "reference point needs the tensor gradient path"; return BNUTS_ERR_UNSUPPORTED; }
+    // back to the exact path
+    tc.nterms = 3;
+    x.zero(tc.beta_ref, size_t(M.Dp) * sizeof(float));
+    logistic_tc_write_reference(tc, x.stream, nullptr);
+    if (!beta_ref) return x.check(err);
+    if (!tc.aug) { err = "no spare K columns for the reference term (D + 3 > 128)"; return BNUTS_ERR_UNSUPPORTED; }
+    std::vector<float> b(size_t(M.Dp), 0.f);
+    std::vector<uint16_t> h(size_t(tc.Dt), 0), m(size_t(tc.Dt), 0), l(size_t(tc.Dt), 0);
+    for (int d = 0; d < M.D; ++d) {
+      b[d] = float(beta_ref[d]);
+      if (!(b[d] == b[d]) || b[d] - b[d] != 0.f) { err = "reference point is not finite"; return BNUTS_ERR_INVALID_ARGUMENT; }
+      h[d] = bf16_bits(b[d]);
+      const float r1 = b[d] - bf16_val(h[d]);
+      m[d] = bf16_bits(r1);
+      l[d] = bf16_bits(r1 - bf16_val(m[d]));
+    }
+    for (int k = 0; k < 3; ++k) h[M.D + k] = 0x3F80;
+    x.h2d(M.stage_bh, h.data(), h.size() * 2); x.h2d(M.stage_bm, m.data(), m.size() * 2); x.h2d(M.stage_bl, l.data(), l.size() * 2);
+    tc.run(x.stream, 1);
+    const int ns = tc.last_nsplit;
+    std::vector<float> g(size_t(ns) * M.Dp);
+    x.d2h(g.data(), M.stage_g, g.size() * sizeof(float));
+    int32_t rc = x.check(err);
+    if (rc) return rc;
+    double n2 = 0.0;
+    for (int d = 0; d < M.D; ++d) {
+      double acc = 0.0;
+      for (int s = 0; s < ns; ++s) acc += double(g[size_t(s) * M.Dp + d]);
+      acc -= double(M.tau) * double(b[d]);
+      n2 += acc * acc;
+    }
+    const double bound = 0.5 * std::sqrt(double(tc.N) * double(M.D));
+    if (!(n2 <= bound * bound)) {
+      err = "reference point rejected: |grad| = " + std::to_string(std::sqrt(n2)) + " exceeds sqrt(N D)/2 = " +
+            std::to_string(bound) + " (not at the mode); exact three-term path kept";
+      return BNUTS_ERR_INVALID_ARGUMENT;
+    }
+    x.h2d(tc.beta_ref, b.data(), size_t(M.Dp) * sizeof(float));
+    logistic_tc_write_reference(tc, x.stream, tc.beta_ref);
+    tc.nterms = 2;
+    return x.check(err);
   }
 }
 

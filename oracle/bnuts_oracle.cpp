@@ -725,6 +725,8 @@ int32_t bnuts_model_gaussian(bnuts_engine* e, const double* P) { DISPATCH(e, mod
 int32_t bnuts_model_logistic(bnuts_engine* e, const void* X, int32_t xd, const double* y, int64_t N, double tau, int32_t rb) {
   DISPATCH(e, model_logistic(E, X, xd, y, N, tau, rb), model_logistic(E, X, xd, y, N, tau, rb));
 }
+// numerical device of the CUDA tensor path; the oracle computes in plain arithmetic: accepted, no effect
+int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double*) { return e ? 0 : BNUTS_ERR_INVALID_ARGUMENT; }
 int32_t bnuts_set_positions(bnuts_engine* e, const double* q) { DISPATCH(e, set_positions(E, q), set_positions(E, q)); }
 int32_t bnuts_get_state(bnuts_engine* e, double* q, double* g, double* l) { DISPATCH(e, get_state(E, q, g, l), get_state(E, q, g, l)); }
 int32_t bnuts_set_metric_diag(bnuts_engine* e, const double* m) { DISPATCH(e, set_metric(E, m), set_metric(E, m)); }

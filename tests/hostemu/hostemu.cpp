@@ -87,6 +87,10 @@ struct HostExec {
     err = "tensor path is CUDA-only";
     return BNUTS_ERR_UNSUPPORTED;
   }
+  template <class E> int32_t logistic_reference(E&, const double*, std::string& err) {
+    err = "tensor path is CUDA-only";
+    return BNUTS_ERR_UNSUPPORTED;
+  }
   template <class T> void metric_update(const EngineMem<T>& M, int N, double lambda) {
     for (int c = 0; c < M.C; ++c) metric_update_chain(M, c, N, lambda, SerialLanes{});
   }

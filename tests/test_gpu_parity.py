@@ -73,6 +73,47 @@ def test_tensor_gradient_within_tolerance(bn, oracle_lib, cuda_lib, N, D, C):
     assert l1[0] == pytest.approx(-N * np.log(2), rel=1e-6)
 
 
+def test_tensor_reference_point(bn, oracle_lib, cuda_lib):
+    """Two-term path around a reference point near the mode: same tolerance as the exact path;
+    a reference far from the mode is refused and the exact path stays in force."""
+    N, D, C = 20000, 100, 256
+    X, y, beta = make_logistic(N, D)
+    rng = np.random.default_rng(5)
+    ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0, row_blocks=1)
+    # a few Newton steps on the host give the mode
+    b = beta.copy()
+    for _ in range(8):
+        eta = X @ b; s = 1 / (1 + np.exp(-eta))
+        g = X.T @ (y - s) - b; H = (X * (s * (1 - s))[:, None]).T @ X + np.eye(D)
+        b = b + np.linalg.solve(H, g)
+    sd = 1.0 / np.sqrt(np.diag(H))
+    q = _f32(b[None, :] + rng.normal(size=(C, D)) * sd[None, :] * np.linspace(0.05, 3.0, C)[:, None])
+    ref.set_positions(q); _, g0, l0 = ref.get_state()
+    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0)
+    tc.set_positions(q); _, g3, l3 = tc.get_state()
+    with pytest.raises(bn.BnutsError):
+        tc.logistic_set_reference(b + 1.0)           # far from the mode: refused
+    tc.set_positions(q); _, g3b, _ = tc.get_state()
+    assert g3b.tobytes() == g3.tobytes()             # exact path still in force, untouched
+    tc.logistic_set_reference(b)
+    tc.set_positions(q); _, g2, l2 = tc.get_state()
+    # chains at 0.05..3 posterior sd from the mode: |grad| runs from ~0 to sqrt(tr H), so the error is bounded
+    # relative to |grad| or by the fp32 conditioning floor of a sum of N terms of size ~1/2, whichever is larger
+    bound = np.maximum(TOL32 * np.linalg.norm(g0, axis=1), 3 * N * 6e-8)
+    e3 = np.linalg.norm(g3 - g0, axis=1); e2 = np.linalg.norm(g2 - g0, axis=1)
+    assert np.all(e3 < bound) and np.all(e2 < bound), (np.max(e3 / bound), np.max(e2 / bound))
+    far = np.linalg.norm(g0, axis=1) > 0.5 * np.sqrt(N * D) / 2
+    assert far.sum() > C // 4 and np.max(_rel(g2[far], g0[far])) < TOL32
+    assert np.max(np.abs(l2 - l0) / np.abs(l0)) < 1e-6 and np.max(np.abs(l3 - l0) / np.abs(l0)) < 1e-6
+    # per-leapfrog parity with the reference point in force
+    p = _f32(rng.normal(size=(C, D)) * np.sqrt(N) * 0.3)
+    a = ref.leapfrog(p, 1e-3, 3); c = tc.leapfrog(p, 1e-3, 3)
+    assert np.max(_rel(c[0], a[0])) < TOL32 and np.max(_rel(c[2], a[2])) < 5 * TOL32
+    tc.logistic_set_reference(None)
+    tc.set_positions(q); _, g3c, _ = tc.get_state()
+    assert g3c.tobytes() == g3.tobytes()
+
+
 def test_tensor_per_leapfrog_parity(bn, oracle_lib, cuda_lib):
     N, D, C = 3000, 100, 256
     X, y, beta = make_logistic(N, D)
