@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--adapt", type=int, default=40, help="length of the first/last step-size-only warmup stage (untimed)")
     ap.add_argument("--transitions", type=int, default=16, help="NUTS transitions per chain per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference", action="store_true", help="keep the exact three-term position operand")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -182,6 +183,15 @@ def main():
                       (a.adapt, bn.METRIC_NONE)):
             e.warmup_stage(n, mk, keep=False)
     t_w = time.perf_counter() - t_w
+    # reference point of the tensor path (include/bnuts.h): the across-chain mean after warmup sits at the mode
+    # to within sd/sqrt(C); the engine checks it and keeps the exact three-term path if it is refused
+    terms = 3
+    if not a.no_reference:
+        try:
+            e.logistic_set_reference(e.get_state()[0].mean(axis=0))
+            terms = 2
+        except bn.BnutsError as ex:
+            print("reference point refused: %s" % ex, file=sys.stderr)
     T = a.transitions
     for _ in range(a.warmup):
         e.sample_device_only(T)
@@ -208,16 +218,25 @@ def main():
     qh[:] = e.get_state()[0]
     chain = torch.empty((C, T, D), dtype=torch.float64).pin_memory().numpy()
     stats = np.zeros((C, T), dtype=bn.TREE_STATS_DTYPE)
+    kept = np.empty((C, a.steps * T, D))          # the e2e draws form one continuous chain per chain id
     barrier()
     t0 = time.perf_counter(); leap_e2e = 0
-    for _ in range(a.steps):
+    for k in range(a.steps):
         e.set_positions(qh)                       # H2D of this step's input positions (+ their gradient)
         e.sample(T, out=(chain, stats))           # D2H of the draws and tree statistics
         leap_e2e += int(stats["steps"].sum())
         qh[:] = chain[:, T - 1]
+        kept[:, k * T:(k + 1) * T] = chain
     barrier()
     dt = allmax(time.perf_counter() - t0)
     e2e = allsum(leap_e2e) / dt
+    # min-ESS/s (second half of BASELINE.json's metric): multi-chain bulk ESS per coordinate of the e2e draws;
+    # chains on different GPUs are independent, so per-coordinate ESS adds across ranks
+    ess_d = np.array([bn.diagnostics.ess(kept[:, :, d]) for d in range(D)]) if kept.shape[1] >= 4 else np.zeros(D)
+    if dist is not None:
+        tt = torch.tensor(ess_d, dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        ess_d = tt.cpu().numpy()
+    min_ess = float(ess_d.min())
 
     if dist is not None:
         dist.barrier()
@@ -244,6 +263,7 @@ def main():
                    "l2": "inputs larger than L2 (X is %d MB bf16)" % (N * 128 * 2 // 2**20),
                    "init": "beta* + 2e-3 N(0,1); untimed warmup: step size search, stages %d|25,50,100 (diag metric)|%d, %.1f s" % (a.adapt, a.adapt, t_w),
                    "step": "%d NUTS transitions of every chain (async within the call)" % T,
+                   "position_operand_terms": terms,
                    "mean_tree_depth": float(stats["depth"].mean()), "mean_leapfrogs_per_transition": float(stats["steps"].mean()),
                    "lockstep_steps_timed": int(c1["lockstep_steps"] - c0["lockstep_steps"]),
                    "active_row_fraction": float(leap / max(1, (c1["lockstep_steps"] - c0["lockstep_steps"]) * C * world))},
@@ -255,6 +275,8 @@ def main():
                      "kernel_share_of_step": grad_ms / ms},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(qh.nbytes), "d2h_bytes_per_step": int(chain.nbytes + stats.nbytes)},
         "clocks": clk,
+        "min_ess": {"value": min_ess, "per_s": min_ess / dt, "unit": "min over coordinates of multi-chain bulk ESS (/s: e2e wall clock)",
+                    "draws_per_chain": int(kept.shape[1])},
     }
     if world == 1 and not a.no_cpu_baseline:
         v, cores, sample = cpu_leapfrog_rate(bits, y, D, budget_s=15.0)

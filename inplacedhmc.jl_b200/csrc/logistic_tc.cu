@@ -130,6 +130,46 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+
+// ---- batched MMA issue.  One asm block = one elect.sync + up to four tcgen05.mma, so the per-instruction
+// issue cost (predicate conversion, descriptor moves into uniform registers) is paid once per block;
+// measured: with one elect per MMA the issuing warp needed ~70 clk per instruction, more than the 56-64 clk
+// the tensor pipe needs to execute it, and was the bottleneck of the whole kernel.
+#define BN_MMA_SS(ACC) "mov.b64 ra, {al, %2};\n\tmov.b64 rb, {bl, %4};\n\t@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ra, rb, %5, " ACC ";\n\t"
+#define BN_MMA_TS(ACC) "mov.b64 rb, {bl, %3};\n\t@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], rb, %4, " ACC ";\n\t"
+#define BN_SS_HEAD "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 ra, rb;\n\t.reg .b32 al, bl;\n\t" \
+                   "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\tmov.b32 al, %1;\n\tmov.b32 bl, %3;\n\t"
+#define BN_SS_STEP "add.u32 al, al, 2;\n\tadd.u32 bl, bl, 2;\n\t"
+#define BN_SS_ARGS ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory"
+// GEMM1: N4 consecutive K steps inside one 64-column chunk.  Only the 14-bit start-address field of a
+// descriptor changes (+32 B = 2 units; shared-memory addresses stay below 2^18, so no carry leaves the
+// field): the descriptors travel as 32-bit halves and the high halves are loop constants.
+template <int N4>
+__device__ __forceinline__ void mma_ss_run(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t acc_first) {
+  static_assert(N4 >= 1 && N4 <= 4, "1..4 K steps per chunk");
+  if constexpr (N4 == 1)
+    asm volatile(BN_SS_HEAD BN_MMA_SS("pa") "}\n" BN_SS_ARGS);
+  else if constexpr (N4 == 2)
+    asm volatile(BN_SS_HEAD BN_MMA_SS("pa") BN_SS_STEP BN_MMA_SS("pt") "}\n" BN_SS_ARGS);
+  else if constexpr (N4 == 3)
+    asm volatile(BN_SS_HEAD BN_MMA_SS("pa") BN_SS_STEP BN_MMA_SS("pt") BN_SS_STEP BN_MMA_SS("pt") "}\n" BN_SS_ARGS);
+  else
+    asm volatile(BN_SS_HEAD BN_MMA_SS("pa") BN_SS_STEP BN_MMA_SS("pt") BN_SS_STEP BN_MMA_SS("pt") BN_SS_STEP BN_MMA_SS("pt") "}\n"
+                 BN_SS_ARGS);
+}
+// GEMM2: the four K steps (16 data rows each) of one 64-row half block for one residual term.  A advances
+// 8 TMEM columns, then 24 to the next 32-row chunk (its hi or lo half), B advances 2048 B = 128 units.
+__device__ __forceinline__ void mma_ts_run4(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t acc_first) {
+  asm volatile("{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 rb;\n\t.reg .b32 ta, bl;\n\t"
+               "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+               "mov.b32 ta, %1;\n\tmov.b32 bl, %2;\n\t" BN_MMA_TS("pa")
+               "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 128;\n\t" BN_MMA_TS("pt")
+               "add.u32 ta, ta, 24;\n\tadd.u32 bl, bl, 128;\n\t" BN_MMA_TS("pt")
+               "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 128;\n\t" BN_MMA_TS("pt") "}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -205,6 +245,35 @@ __device__ __forceinline__ float2 rcp2(float2 d, bool sw) {
 #define BNUTS_TC_RCPSW 0x00   // bit k set: pair k of every 8 pairs uses the FMA-pipe reciprocal
 #endif
 constexpr int RCPSW = BNUTS_TC_RCPSW;
+#ifndef BNUTS_TC_DEBUG
+#define BNUTS_TC_DEBUG 0      // timing experiments only (results are wrong): 1 skip elementwise, 2 skip GEMM1, 4 skip GEMM2
+#endif
+constexpr int TCDBG = BNUTS_TC_DEBUG;
+#ifndef BNUTS_TC_GROUPS
+#define BNUTS_TC_GROUPS 2     // elementwise warp groups: 1 = all 16 warps share every row block (one 32-column chunk
+#endif                        // each, lowest latency per block); 2 = two groups of 8 ping-pong over the blocks
+constexpr int NG = BNUTS_TC_GROUPS;
+#ifndef BNUTS_TC_ORDER
+#define BNUTS_TC_ORDER 1      // MMA issuer: 0 = all waits of an iteration first, then GEMM1(i+2) and GEMM2(i) back to back;
+#endif                        // 1 = GEMM1(i+2) is issued before waiting for the residual of block i
+constexpr int ORDER = BNUTS_TC_ORDER;
+// with several groups a warp waits for S of block i + NG before it publishes R of block i; GEMM1(i + 2) must
+// then not depend on that R (ORDER 0 would deadlock)
+static_assert(NG == 1 || ORDER == 1, "BNUTS_TC_GROUPS > 1 needs BNUTS_TC_ORDER = 1");
+constexpr int EW_PER_GROUP = 16 / NG;     // warps per group
+constexpr int CPW = NG;                   // 32-column chunks per warp and block
+// timing trace (debug builds only, -DBNUTS_TC_TRACE): CTA (0,0) records clock64() at fixed points of
+// the first 256 row blocks: trace[role][block][slot], role 0 = TMA producer, 1 = MMA issuer, 2 = elementwise warp 2
+#ifdef BNUTS_TC_TRACE
+__device__ long long g_tc_trace[3 * 256 * 16];
+#define TC_TRACE(role, blk, slot)                                                                   \
+  do {                                                                                              \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (blk) < 256 && (threadIdx.x & 31) == 0)               \
+      g_tc_trace[((role) * 256 + (blk)) * 16 + (slot)] = clock64();                                  \
+  } while (0)
+#else
+#define TC_TRACE(role, blk, slot) do {} while (0)
+#endif
 
 template <int DT> struct SmemPlan {
   static constexpr int KC = DT / 64;
@@ -257,9 +326,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (smem_u32(smem) & 1023u) asm volatile("trap;");
     mbar_init(bar_b, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 256); }
+    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 32 * EW_PER_GROUP); }
     mbar_init(g_full, 1);
-    mbar_init(g_empty, 256);
+    mbar_init(g_empty, 32 * EW_PER_GROUP);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -285,7 +354,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       for (int i = 0; i < nb; ++i) {
         const int st = i % NS;
         const uint32_t ph = (uint32_t)(i / NS) & 1u;
+        TC_TRACE(0, i, 0);
         mbar_wait(&x_empty[st], ph ^ 1u);
+        TC_TRACE(0, i, 1);
         mbar_expect_tx(&x_full[st], P::X_BYTES);
         for (int kc = 0; kc < KC; ++kc)
           tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK_BYTES, &x_full[st], kc * 64, (b0 + i) * ROWS);
@@ -299,69 +370,91 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
       constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
       const uint32_t aX = smem_u32(sX);
-      // descriptors of the three β tiles are loop invariant; per-k offsets are compile-time constants
-      uint64_t dB[3];
+      // descriptor halves: the high words are constants, the low words carry the start address
+      const uint64_t dKM = desc_kmajor(0, 0), dMN = desc_mnmajor(0, 0);
+      const uint32_t km_hi = (uint32_t)(dKM >> 32), km_lo0 = (uint32_t)dKM;
+      const uint32_t mn_hi = (uint32_t)(dMN >> 32), mn_lo0 = (uint32_t)dMN;
+      uint32_t bB[3];
 #pragma unroll
-      for (int term = 0; term < 3; ++term) dB[term] = desc_kmajor(smem_u32(sB) + (uint32_t)term * P::B_BYTES, 0);
+      for (int term = 0; term < 3; ++term) bB[term] = km_lo0 + ((smem_u32(sB) + (uint32_t)term * P::B_BYTES) >> 4);
       mbar_wait(bar_b, 0);
+      // GEMM1 of block i: S[buf] = sum over terms of B_term · X_iᵀ.  No wait for the S/R buffer: its previous
+      // user is GEMM2(i - 3), issued earlier by this same thread, and tcgen05.mma instructions of one thread
+      // execute in issue order; the elementwise warps' accesses to it were ordered before that GEMM2 by r_full.
       auto gemm1 = [&](int i) {
         const int st = i % NS, buf = i % NSB;
-        mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
-        // No wait for the S/R buffer: its previous user is GEMM2(i - 3), issued earlier by this same
-        // thread, and tcgen05.mma instructions of one thread execute in issue order; the elementwise
-        // warps' accesses to it were ordered before that GEMM2 by r_full.
-        tc_fence_after();
-        const uint64_t dX = desc_kmajor(aX + (uint32_t)st * P::X_BYTES, 0);
+        const uint32_t xlo = km_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
         const uint32_t d = tmem_S + (uint32_t)buf * 128u;
 #pragma unroll
         for (int term = 0; term < 3; ++term)
           if (term < nterms) {
 #pragma unroll
-            for (int kk = 0; kk < NK; ++kk) {
-              const uint64_t off = (uint64_t)(((kk >> 2) * CHUNK_BYTES + (kk & 3) * 32) >> 4);
-              if (elect_one()) mma_ss(d, dB[term] + off, dX + off, IDESC1, (term | kk) ? 1u : 0u);
+            for (int c = 0; c < (NK + 3) / 4; ++c) {
+              constexpr int LAST = NK - ((NK + 3) / 4 - 1) * 4;   // K steps in the last chunk
+              const uint32_t off = (uint32_t)(c * (CHUNK_BYTES >> 4));
+              const uint32_t acc = (term | c) ? 1u : 0u;
+              if (TCDBG & 2) continue;
+              if (c + 1 < (NK + 3) / 4) mma_ss_run<4>(d, bB[term] + off, km_hi, xlo + off, km_hi, IDESC1, acc);
+              else mma_ss_run<LAST>(d, bB[term] + off, km_hi, xlo + off, km_hi, IDESC1, acc);
             }
           }
+        TC_TRACE(1, i, 7);
         if (elect_one()) tc_commit(&s_full[buf]);
-        __syncwarp();
+        TC_TRACE(1, i, 2);
       };
+      auto wait_x = [&](int i) { mbar_wait(&x_full[i % NS], (uint32_t)(i / NS) & 1u); };
+      wait_x(0);
+      tc_fence_after();
       gemm1(0);
-      if (nb > 1) gemm1(1);
+      if (nb > 1) { wait_x(1); tc_fence_after(); gemm1(1); }
       int period = 0, in_period = 0;
       for (int i = 0; i < nb; ++i) {
-        if (i + 2 < nb) gemm1(i + 2);
+        // all waits of the iteration first, then GEMM1(i+2) and GEMM2(i) back to back, so the tensor
+        // pipe's queue stays fed while this thread does its bookkeeping
         const int st = i % NS, buf = i % NSB, u = i / NSB;
+        TC_TRACE(1, i, 0);
+        if (i + 2 < nb) wait_x(i + 2);
+        TC_TRACE(1, i, 1);
+        if (ORDER == 1 && i + 2 < nb) { tc_fence_after(); gemm1(i + 2); }
         mbar_wait(&r_full[buf], (uint32_t)u & 1u);
+        TC_TRACE(1, i, 4);
         if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
+        TC_TRACE(1, i, 5);
         tc_fence_after();
-        const uint64_t dXm = desc_mnmajor(aX + (uint32_t)st * P::X_BYTES, 0);
+        if (ORDER == 0 && i + 2 < nb) gemm1(i + 2);
+        const uint32_t xm = mn_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
         const uint32_t a = tmem_S + (uint32_t)buf * 128u;
         const uint32_t acc0 = in_period > 0 ? 1u : 0u;
 #pragma unroll
         for (int term = 0; term < 2; ++term)
 #pragma unroll
-          for (int kk = 0; kk < ROWS / 16; ++kk)
-            if (elect_one())
-              mma_ts(tmem_G, a + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8 + term * 16), dXm + (uint64_t)(kk * 2048 >> 4), IDESC2,
-                     (term | kk) ? 1u : acc0);
+          for (int hb = 0; hb < 2; ++hb) {   // 64-row halves of the block
+            if (TCDBG & 4) continue;
+            mma_ts_run4(tmem_G, a + (uint32_t)(hb * 64 + term * 16), xm + (uint32_t)(hb * 4 * 128), mn_hi, IDESC2,
+                        (term | hb) ? 1u : acc0);
+          }
+        TC_TRACE(1, i, 8);
         if (elect_one()) tc_commit(&x_empty[st]);
+        TC_TRACE(1, i, 6);
         ++in_period;
-        if (i + 1 == nb || (i % fe) == fe - 1) {
+        if (i + 1 == nb || in_period == fe) {
           if (elect_one()) tc_commit(g_full);
           ++period;
           in_period = 0;
         }
         __syncwarp();
+        TC_TRACE(1, i, 9);
       }
     }
   } else {
     // ===================================================== elementwise + epilogue (16 warps)
-    // Two groups of 8 warps ping-pong over the row blocks (group g takes blocks i = g mod 2), so
-    // on every scheduler one group computes while the other sits in its TMEM load/store/sync
-    // phase.  Inside a group: TMEM lane group q = warp % 4 (hardware rule), column half h.
+    // NG groups of 16/NG warps; group g takes blocks i = g mod NG.  Inside a group: TMEM lane group
+    // q = warp % 4 (hardware rule), column part h; a warp owns CPW = NG chunks of 32 columns per block.
+    // Measured: the latency of one block through this stage, not its throughput, limits the kernel (the
+    // S -> R -> GEMM2 chain has only three TMEM buffers of slack), so NG = 1 (shortest latency) is the default.
     const int ew = warp - 2;
-    const int grp = ew >> 3;
-    const int h = (ew >> 2) & 1;
+    const int grp = ew / EW_PER_GROUP;
+    const int h = (ew % EW_PER_GROUP) >> 2;
     const int q = warp & 3;
     const int row = tile * CHAINS + q * 32 + lane;   // staging row = chain slot
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
@@ -371,19 +464,34 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const float2 MONE2 = make_float2(-1.0f, -1.0f);
     const float LN2 = 0.6931471805599453f;
     float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
-    for (int i = grp; i < nb; i += 2) {
+    int fpos = grp, fper = 0;               // i % fe and i / fe, kept without divisions
+    while (fpos >= fe) { fpos -= fe; ++fper; }
+    // Work items of this warp: (block i, chunk cc), i = grp, grp + NG, ..., cc < CPW.  The TMEM load of
+    // the next item is issued before the stores / barrier traffic of the current one, so its latency
+    // (and the s_full wait of the next block, normally already complete) is off the critical path.
+    uint32_t v[32];
+    auto load_item = [&](int i, int cc) {
       const int buf = i % NSB, u = i / NSB;
-      mbar_wait(&s_full[buf], (uint32_t)u & 1u);
-      tc_fence_after();
-      float bsum = 0.f;   // sum over this thread's 64 elements of  log2(1 + 2^-|u|)
+      if (cc == 0) {
+        if (warp == 2) TC_TRACE(2, i, 0);
+        mbar_wait(&s_full[buf], (uint32_t)u & 1u);
+        if (warp == 2) TC_TRACE(2, i, 1);
+        tc_fence_after();
+      }
+      tmem_ld32(tmem_S + (uint32_t)buf * 128u + lane_sel + (uint32_t)(CPW * h + cc) * 32u, v);
+    };
+    if (grp < nb && !(TCDBG & 1)) load_item(grp, 0);
+    for (int i = grp; i < nb; i += NG) {
+      const int buf = i % NSB;
+      float bsum = 0.f;   // sum over this thread's elements of  log2(1 + 2^-|u|)
       float asum = 0.f;   // sum of |eta|
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int ch = 2 * h + cc;
+      for (int cc = 0; cc < ((TCDBG & 1) ? 0 : CPW); ++cc) {
+        const int ch = CPW * h + cc;
         const uint32_t tS = tmem_S + (uint32_t)buf * 128u + lane_sel + (uint32_t)ch * 32u;
-        uint32_t v[32];
-        tmem_ld32(tS, v);
+        if (warp == 2) TC_TRACE(2, i, 3);
         tmem_ld_wait();
+        if (warp == 2) TC_TRACE(2, i, 4);
         uint32_t hi[16], lo[16];
         float2 prod = ONE2;
         float as0 = 0.f, as1 = 0.f;
@@ -392,11 +500,11 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           // eta = H~ (natural units); t = exp(-|eta|) in (0,1]; d = 1 + t in (1,2]
           const float e0 = __uint_as_float(v[2 * j]), e1 = __uint_as_float(v[2 * j + 1]);
           const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
-          const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
+          const float2 d2 = (TCDBG & 16) ? __fadd2_rn(u2, ONE2) : __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
           prod = __fmul2_rn(prod, d2);                       // 32 factors in (1,2]: no overflow
           as0 += fabsf(e0); as1 += fabsf(e1);
           // rc = 1/d = sigma(|eta|) in [1/2,1);  sigma(-eta) = 1/2 - copysign(rc - 1/2, eta)
-          const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
+          const float2 hm = __fadd2_rn((TCDBG & 8) ? d2 : rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
           const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
                                         __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
           const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
@@ -408,33 +516,42 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
         bsum += lg2_approx(prod.x * prod.y);
         asum += as0 + as1;
+        if (warp == 2) TC_TRACE(2, i, 5);
+        // next item's S -> registers (v is dead now)
+        if (cc + 1 < CPW) load_item(i, cc + 1);
+        else if (i + NG < nb) load_item(i + NG, 0);
         tmem_st16(tS, hi);
         tmem_st16(tS + 16u, lo);
       }
+      if (warp == 2) TC_TRACE(2, i, 6);
       tmem_st_wait();
+      if (warp == 2) TC_TRACE(2, i, 7);
       tc_fence_before();
       mbar_arrive(&r_full[buf]);
+      if (warp == 2) TC_TRACE(2, i, 2);
       lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);      // sum log sigma(eta) minus the linear part (added by the consumer)
-      if (i + 1 == nb || (i % fe) == fe - 1) {
-        // this block closes flush period i / fe: drain the GEMM2 accumulator and add it outside
-        // the tensor core (the other group keeps working on block i + 1 meanwhile)
-        const int period = i / fe;
+      const bool closes = (i + 1 == nb) || (fpos == fe - 1);
+      const int period = fper;
+      fpos += NG;
+      while (fpos >= fe) { fpos -= fe; ++fper; }
+      if (closes) {
+        // this block closes flush period i / fe: drain the GEMM2 accumulator and add it outside the tensor core
         mbar_wait(g_full, (uint32_t)period & 1u);
         tc_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int ch = 2 * h + cc;
+        for (int cc = 0; cc < CPW; ++cc) {
+          const int ch = CPW * h + cc;
           if (ch * 32 < dk) {
-            uint32_t v[32];
-            tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, v);
+            uint32_t w[32];
+            tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, w);
             tmem_ld_wait();
             if (row < nrows) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const int d = ch * 32 + j;
                 if (d < dk && d < Dp) {   // dk can exceed the row stride Dp when the reference columns spill over
-                  float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                         __uint_as_float(v[j + 3]));
+                  float4 a = make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]), __uint_as_float(w[j + 2]),
+                                         __uint_as_float(w[j + 3]));
                   float4* gp = reinterpret_cast<float4*>(gout + d);
                   if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
                   *gp = a;
@@ -448,11 +565,11 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
     }
     // rows >= N of the last block are zero padding: eta = 0, y = 0 -> each contributed -log 2
-    if (h == 0 && grp == ((nb - 1) & 1) && nb > 0 && b1 == nblk_total)
+    if (h == 0 && nb > 0 && grp == ((nb - 1) % NG) && b1 == nblk_total)
       lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
     // combine the four partial sums of each chain (2 groups x 2 column halves) and publish
     double* lp = reinterpret_cast<double*>(sX);   // X stages are dead by now
-    const int part = grp * 2 + h;
+    const int part = grp * (4 / NG) + h;
     asm volatile("bar.sync 1, 512;" ::: "memory");
     if (part > 0) lp[(part - 1) * 128 + q * 32 + lane] = lsum;
     asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -547,6 +664,11 @@ void LogisticTC::run(cudaStream_t s, int nrows) {
     default: launch<128, 8>(*this, s, nrows, last_nsplit); break;
   }
 }
+#ifdef BNUTS_TC_TRACE
+extern "C" int bnuts_debug_tc_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 3 * 256 * 16);
+}
+#endif
 void LogisticTC::destroy() {
   if (Xb) cudaFree(Xb);
   if (colsum) cudaFree(colsum);
