@@ -160,6 +160,22 @@ int32_t bnuts_sample(bnuts_engine* e, int32_t N,
                      bnuts_tree_stats* stats_out, int64_t stats_stride_chain,
                      int32_t* selected_index);
 
+/* Row-sharded data (BASELINE config 5; the reference has no collective of any kind,
+ * src/mcmc.jl:150-157).  Every engine of a group holds ALL chains (same seed, chain_offset, positions, step
+ * sizes) and one shard of the rows of X (pass the local rows to bnuts_model_logistic).  After one of the calls
+ * below, each leapfrog step sums the per-shard gradient / log-density partials over the group, so all
+ * replicas see bit-identical gradients and make identical tree decisions; the prior term is added once,
+ * after the sum.
+ *   bnuts_set_nccl        CUDA engines, one per GPU: ncclAllReduce over NVLink on the engine's stream.
+ *                         id: the 128 bytes of bnuts_nccl_unique_id() from rank 0, broadcast by the host.
+ *   bnuts_set_allreduce   host-provided collective (tests, other transports): fn sums `count` elements
+ *                         (dtype 0 = Float64, 1 = Float32) in place across the group and returns 0; buf is
+ *                         device memory for the CUDA engine (its stream is idle during the call). */
+typedef int32_t (*bnuts_allreduce_fn)(void* ctx, void* buf, int64_t count, int32_t dtype);
+int32_t bnuts_set_allreduce(bnuts_engine* e, bnuts_allreduce_fn fn, void* ctx);
+int32_t bnuts_nccl_unique_id(uint8_t* id /* [128] */);
+int32_t bnuts_set_nccl(bnuts_engine* e, const uint8_t* id /* [128] */, int32_t world, int32_t rank);
+
 int32_t bnuts_counters(bnuts_engine* e, bnuts_counter_block* out);
 /* Measurement hook (no reference counterpart): when enabled, every launch of the
  * batched gradient kernel inside the run loop is bracketed by CUDA events on the

@@ -56,10 +56,12 @@ EXPORTS = [
     "bnuts_model_gaussian", "bnuts_model_logistic", "bnuts_logistic_set_reference", "bnuts_set_positions", "bnuts_get_state",
     "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed",
     "bnuts_inject", "bnuts_leapfrog", "bnuts_find_initial_stepsize", "bnuts_warmup_stage", "bnuts_sample",
-    "bnuts_counters", "bnuts_profile", "bnuts_chain_status",
+    "bnuts_counters", "bnuts_profile", "bnuts_chain_status", "bnuts_set_allreduce", "bnuts_nccl_unique_id", "bnuts_set_nccl",
 ]
 
 _P = C.c_void_p
+# ≙ bnuts_allreduce_fn: int32 fn(void* ctx, void* buf, int64 count, int32 dtype)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32)
 
 
 class BnutsError(RuntimeError):
@@ -84,6 +86,9 @@ def load_library(path=None):
     lib.bnuts_model_gaussian.argtypes = [_P, _P]
     lib.bnuts_model_logistic.argtypes = [_P, _P, C.c_int32, _P, C.c_int64, C.c_double, C.c_int32]
     lib.bnuts_logistic_set_reference.argtypes = [_P, _P]
+    lib.bnuts_set_allreduce.argtypes = [_P, ALLREDUCE_FN, _P]
+    lib.bnuts_nccl_unique_id.argtypes = [_P]
+    lib.bnuts_set_nccl.argtypes = [_P, _P, C.c_int32, C.c_int32]
     lib.bnuts_set_positions.argtypes = [_P, _P]
     lib.bnuts_get_state.argtypes = [_P, _P, _P, _P]
     lib.bnuts_set_metric_diag.argtypes = [_P, _P]
@@ -104,6 +109,15 @@ def load_library(path=None):
         if n != "bnuts_last_error":
             getattr(lib, n).restype = C.c_int32
     return lib
+
+
+def nccl_unique_id(lib=None):
+    lib = lib or load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.bnuts_nccl_unique_id(buf)
+    if rc:
+        raise BnutsError(rc, "bnuts_nccl_unique_id failed (NCCL not found?)")
+    return bytes(buf)
 
 
 def _ptr(a):
@@ -176,6 +190,26 @@ class Engine:
         three).  β_ref must sit near the posterior mode (checked); None returns to the exact path."""
         b = _f64(beta_ref, (self.D,))
         self._chk(self.lib.bnuts_logistic_set_reference(self.h, _ptr(b)))
+
+    # ---- row-sharded data (every engine of the group holds all chains and one shard of the rows of X)
+    def set_allreduce(self, fn):
+        """fn(address, count, dtype) sums `count` elements (dtype 0 = Float64, 1 = Float32) at `address` in place
+        across the group.  The ctypes thunk is kept alive on the engine."""
+        def thunk(_ctx, buf, count, dtype):
+            try:
+                fn(buf, count, dtype)
+                return 0
+            except Exception:          # never let an exception cross the C ABI
+                import traceback
+                traceback.print_exc()
+                return -1
+        self._allreduce_thunk = ALLREDUCE_FN(thunk)
+        self._chk(self.lib.bnuts_set_allreduce(self.h, self._allreduce_thunk, None))
+
+    def set_nccl(self, unique_id, world, rank):
+        """unique_id: the 128 bytes of nccl_unique_id(lib) from rank 0 (broadcast them with the host's own plumbing)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._chk(self.lib.bnuts_set_nccl(self.h, buf, world, rank))
 
     # ---- state
     def set_positions(self, q=None, allow_nonfinite=False):

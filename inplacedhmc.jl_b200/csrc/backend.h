@@ -42,6 +42,10 @@ template <class T> struct EngineMem {
   int32_t* stage_row;            // [C] row of each chain in the current request
   unsigned long long* stage_count;  // rows handed out in the current lockstep step
   int32_t stage_rows;            // rows of the request being consumed (stride of the partials)
+  // row-sharded data: every engine of the group runs the same chains and must hand
+  // out the same rows, so requests are only flagged here (row = chain in "wide" staging) and a scan in chain
+  // order assigns the compact rows afterwards; null in the ordinary (atomic counter) mode
+  int32_t* stage_active;         // [C]
   int32_t Dt;            // padded K of the tensor path
   const T* beta_ref;     // [Dp] reference point of the tensor path (staged operand is q − beta_ref), or null
   const double* lin_w;   // [Dp] tensor path: the kernel's log-density partials omit ½ Σ_d lin_w[d] q[d]
@@ -163,6 +167,10 @@ template <class T, class LP> struct Backend {
   // take a staging row for this chain's gradient request (batched targets only)
   BN_HD int take_row() const {
     if (!M.stage_q) return -1;
+    if (M.stage_active) {
+      if (lp.lane0()) M.stage_active[c] = 1;
+      return c;
+    }
     const int row = lp.alloc_row(M.stage_count);
     if (lp.lane0()) M.stage_row[c] = row;
     return row;

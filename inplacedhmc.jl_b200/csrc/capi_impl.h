@@ -111,6 +111,19 @@ int32_t bnuts_sample(bnuts_engine* e, int32_t N, double* chain_out, int64_t sd, 
                      bnuts_tree_stats* stats_out, int64_t ssc, int32_t* sel) {
   BN_DISPATCH(e, transitions(N, nullptr, BNUTS_METRIC_NONE, 0.0, chain_out, sd, sc, stats_out, ssc, sel, nullptr));
 }
+int32_t bnuts_set_allreduce(bnuts_engine* e, bnuts_allreduce_fn fn, void* ctx) {
+  if (!fn) return BNUTS_ERR_INVALID_ARGUMENT;
+  BN_DISPATCH(e, enable_reduce(fn, ctx));
+}
+int32_t bnuts_nccl_unique_id(uint8_t* id) { return id ? BNUTS_EXEC::nccl_unique_id(id) : BNUTS_ERR_INVALID_ARGUMENT; }
+int32_t bnuts_set_nccl(bnuts_engine* e, const uint8_t* id, int32_t world, int32_t rank) {
+  if (!e || !id || world < 1 || rank < 0 || rank >= world) return BNUTS_ERR_INVALID_ARGUMENT;
+  AnyEngine* ae = reinterpret_cast<AnyEngine*>(e);
+  std::string& err = ae->dtype == BNUTS_F64 ? ae->e64->err : ae->e32->err;
+  int32_t rc = ae->dtype == BNUTS_F64 ? ae->e64->x.nccl_init(id, world, rank, err) : ae->e32->x.nccl_init(id, world, rank, err);
+  if (rc) return rc;
+  BN_DISPATCH(e, enable_reduce(nullptr, nullptr));
+}
 int32_t bnuts_counters(bnuts_engine* e, bnuts_counter_block* out) {
   if (!out) return BNUTS_ERR_INVALID_ARGUMENT;
   BN_DISPATCH(e, get_counters(out));

@@ -54,6 +54,13 @@ template <class T, class X> struct EngineCore {
   double* d_tmp_cd = nullptr;   // [C][D] scratch (positions / momenta in)
   double* d_tmp_c = nullptr;    // [C]
   std::vector<double> h_draws;  // staging when caller strides are not compact
+  // row-sharded data: per-leapfrog sum of the gradient partials over the group
+  bool reduce_on = false;
+  bnuts_allreduce_fn red_fn = nullptr; void* red_ctx = nullptr;
+  T* red_g = nullptr;           // [C][Dp] folded gradient partials, summed across the group in place
+  double* red_l = nullptr;      // [C]     folded log-density partials (Float64)
+  T* wide_q = nullptr; uint16_t* wide_bh = nullptr; uint16_t* wide_bm = nullptr; uint16_t* wide_bl = nullptr;
+  int32_t* d_active = nullptr;  // [C] request flags (deterministic row assignment)
 
   int32_t fail(int32_t code, const std::string& m) { err = m; return code; }
 
@@ -89,6 +96,7 @@ template <class T, class X> struct EngineCore {
   }
   void destroy() {
     x.sync();
+    free_reduce();
     void* ptrs[] = {M.zs, M.zlq, M.st_rho, M.st_psf, M.m_rho, M.m_psm, M.m_psp, M.ps_cur, M.Minv, M.W, M.cs,
                     M.stage_q, M.stage_g, M.stage_l, M.stage_ld, M.stage_bh, M.stage_bm, M.stage_bl, M.stage_row, M.draws, d_stats, d_sel, d_eps_hist,
                     d_inj_dirs, d_inj_p, d_tmp_cd, d_tmp_c, model.P, model.X, model.y, model.Xb, model.yf};
@@ -97,7 +105,44 @@ template <class T, class X> struct EngineCore {
   }
 
   // ---------------------------------------------------------------- models
+  void free_reduce() {
+    void** ps[] = {(void**)&red_g, (void**)&red_l, (void**)&wide_q, (void**)&wide_bh, (void**)&wide_bm, (void**)&wide_bl,
+                   (void**)&d_active};
+    for (void** p : ps) if (*p) { x.free(*p); *p = nullptr; }
+    reduce_on = false;
+  }
+  // ≙ no reference counterpart (the reference has no collective).  After this call the engine
+  // treats its design matrix as one shard of the rows: every lockstep step the folded partials
+  // [rows x Dp] gradient + [rows] log density are summed over the group before the chains consume them.
+  // All engines of the group must hold all chains (same seed, chain_offset, positions).
+  int32_t enable_reduce(bnuts_allreduce_fn fn, void* ctx) {
+    if (model.kind != MODEL_LOGISTIC) return fail(BNUTS_ERR_NO_MODEL, "row sharding needs the logistic model (set it first)");
+    free_reduce();
+    const size_t CD = size_t(M.C) * M.Dp;
+    red_g = x.template alloc<T>(CD); red_l = x.template alloc<double>(M.C);
+    wide_q = x.template alloc<T>(CD); d_active = x.template alloc<int32_t>(M.C);
+    x.zero(wide_q, CD * sizeof(T)); x.zero(d_active, size_t(M.C) * sizeof(int32_t));
+    if (M.stage_bh) {
+      const size_t nbt = size_t(M.C) * M.Dt;
+      wide_bh = x.template alloc<uint16_t>(nbt); wide_bm = x.template alloc<uint16_t>(nbt); wide_bl = x.template alloc<uint16_t>(nbt);
+      x.zero(wide_bh, nbt * 2); x.zero(wide_bm, nbt * 2); x.zero(wide_bl, nbt * 2);
+    }
+    red_fn = fn; red_ctx = ctx;
+    reduce_on = true;
+    return x.check(err);
+  }
+  // the view of the staging buffers the chains see in row-sharded mode: they write requests to the wide
+  // buffers (row = chain) and read the reduced result (one partial block)
+  EngineMem<T> reduce_view(int64_t rows) const {
+    EngineMem<T> V = M;
+    V.stage_q = wide_q; V.stage_bh = wide_bh; V.stage_bm = wide_bm; V.stage_bl = wide_bl;
+    V.stage_active = d_active;
+    V.stage_g = red_g; V.stage_ld = red_l; V.stage_nb = 1; V.stage_rows = (int32_t)rows; V.lin_w = nullptr;
+    return V;
+  }
+
   void free_model() {
+    free_reduce();
     void** ps[] = {(void**)&model.P, (void**)&model.X, (void**)&model.y, (void**)&model.Xb, (void**)&model.yf,
                    (void**)&M.stage_q, (void**)&M.stage_g, (void**)&M.stage_l, (void**)&M.stage_ld, (void**)&M.stage_bh,
                    (void**)&M.stage_bm, (void**)&M.stage_bl, (void**)&M.stage_row};
@@ -222,15 +267,28 @@ template <class T, class X> struct EngineCore {
   int32_t run(bool pending) {
     const bool batched = model.batched();
     const int iters = batched ? 1 : (1 << 30);
-    int64_t np = pending ? x.read_count() : 0;
+    int64_t np = 0;
+    if (pending) np = reduce_on ? x.assign_rows(reduce_view(0), M) : x.read_count();
     for (;;) {
       if (np > 0 && batched) {
         M.stage_nb = x.gradient(*this, (int)np);
         M.stage_rows = (int32_t)np;
         counters.kernel_launches += 1;
         counters.gradient_rows += np;
+        if (reduce_on) {   // fold the partials of this shard, sum them over the group (one exchange per leapfrog)
+          x.fold_partials(M, (int)np, red_g, red_l);
+          int32_t rc = x.allreduce(red_g, np * M.Dp, sizeof(T) == 4, red_l, np, red_fn, red_ctx, err);
+          if (rc) return rc;
+          counters.kernel_launches += 1;
+        }
       }
-      np = x.advance(M, rp, iters);
+      if (reduce_on) {
+        const EngineMem<T> V = reduce_view(np);
+        x.advance(V, rp, iters);
+        np = x.assign_rows(V, M);
+      } else {
+        np = x.advance(M, rp, iters);
+      }
       counters.kernel_launches += 1;
       counters.lockstep_steps += 1;
       if (np <= 0) break;
@@ -306,7 +364,7 @@ template <class T, class X> struct EngineCore {
     if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
     if (q) { x.h2d(d_tmp_cd, q, size_t(M.C) * M.D * sizeof(double)); M.pos_in = d_tmp_cd; } else M.pos_in = nullptr;
     PrepareArgs a{}; a.mode = MODE_EVAL;
-    x.prepare(M, rp, a);
+    if (reduce_on) x.prepare(reduce_view(0), rp, a); else x.prepare(M, rp, a);
     int32_t rc = run(true);
     if (rc) return rc;
     if (x.any_status(M, ST_NONFINITE_START)) return fail(BNUTS_ERR_NONFINITE_START, "starting point has non-finite density");

@@ -10,7 +10,9 @@
 //   logistic_tc.cu   tcgen05/TMA fused two-GEMM logistic gradient (fp32 variant)
 //   k_metric, k_finish_da, small gathers
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -78,6 +80,99 @@ template <class T> __global__ void k_gather_state(EngineMem<T> M, double* o) {
   }
   if (lane == 0) o[2 * n + c] = (double)M.zlq[(int64_t)c * M.S + s];
 }
+
+// ------------------------------------------------------------------ row-sharded mode
+// Deterministic row assignment: exclusive scan of the request flags in chain order (one CTA; C is a few
+// thousand), so every engine of the group gives chain c the same staging row.
+__global__ void __launch_bounds__(1024) k_scan_rows(const int32_t* __restrict__ active, int32_t* stage_row, int C,
+                                                    unsigned long long* count) {
+  __shared__ int wsum[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < C; c0 += 1024) {
+    const int c = c0 + threadIdx.x;
+    const int f = (c < C && active[c]) ? 1 : 0;
+    int incl = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int v = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+      wsum[lane] = v;   // inclusive over warps
+    }
+    __syncthreads();
+    const int base = base_s;
+    const int excl = base + (w ? wsum[w - 1] : 0) + incl - f;
+    if (f) stage_row[c] = excl;
+    __syncthreads();
+    if (threadIdx.x == 0) base_s = base + wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = (unsigned long long)base_s;
+}
+// move the flagged chains' requests from the wide staging (row = chain) to their compact rows
+template <class T>
+__global__ void __launch_bounds__(ADV_THREADS) k_gather_rows(EngineMem<T> V, EngineMem<T> Mc) {
+  const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (c >= V.C) return;
+  const int lane = (int)(threadIdx.x & 31);
+  if (!V.stage_active[c]) return;
+  const int64_t r = Mc.stage_row[c];
+  for (int d = lane; d < V.Dp; d += 32) Mc.stage_q[r * V.Dp + d] = V.stage_q[(int64_t)c * V.Dp + d];
+  if (Mc.stage_bh)
+    for (int d = lane; d < V.Dt; d += 32) {
+      Mc.stage_bh[r * V.Dt + d] = V.stage_bh[(int64_t)c * V.Dt + d];
+      Mc.stage_bm[r * V.Dt + d] = V.stage_bm[(int64_t)c * V.Dt + d];
+      Mc.stage_bl[r * V.Dt + d] = V.stage_bl[(int64_t)c * V.Dt + d];
+    }
+  __syncwarp();
+  if (lane == 0) V.stage_active[c] = 0;
+}
+// fold this shard's partial blocks (row blocks of the deterministic path / splits of the tensor path) in a
+// fixed order: one gradient row + one Float64 log-density per staged row, ready for the sum over the group
+template <class T>
+__global__ void __launch_bounds__(ADV_THREADS) k_fold_partials(EngineMem<T> M, int rows, T* red_g, double* red_l) {
+  const int row = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (row >= rows) return;
+  const int lane = (int)(threadIdx.x & 31);
+  const int64_t bs = (int64_t)rows * M.Dp;
+  const T* sg = M.stage_g + (int64_t)row * M.Dp;
+  double lin = 0.0;
+  for (int d = lane; d < M.Dp; d += 32) {
+    T acc = T(0);
+    if (d < M.D) {
+      for (int b = 0; b < M.stage_nb; ++b) acc = acc + sg[b * bs + d];
+      if (M.lin_w) lin = fma(M.lin_w[d], (double)M.stage_q[(int64_t)row * M.Dp + d], lin);
+    }
+    red_g[(int64_t)row * M.Dp + d] = acc;
+  }
+  for (int off = 16; off >= 1; off >>= 1) lin += __shfl_xor_sync(0xffffffffu, lin, off);
+  if (lane == 0) {
+    double l = 0.0;
+    for (int b = 0; b < M.stage_nb; ++b)
+      l += M.stage_ld ? M.stage_ld[(int64_t)b * rows + row] : (double)M.stage_l[(int64_t)b * rows + row];
+    red_l[row] = fma(0.5, lin, l);
+  }
+}
+
+// NCCL is bound at run time (dlopen) so the library loads on hosts without it; only bnuts_set_nccl needs it
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  void* lib = nullptr;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err);
+};
 
 // ------------------------------------------------------------------ deterministic gradients
 // G[c][d] = -sum_k P[d][k] Q[c][k], k strictly sequential per output so the result
@@ -180,6 +275,7 @@ struct CudaExec {
   int32_t* d_status = nullptr;
   int device = 0;
   LogisticTC tc;
+  void* nccl_comm = nullptr;
   // measurement hook: CUDA-event pairs around the batched gradient launches
   bool profiling = false;
   std::vector<cudaEvent_t> ev;   // pairs
@@ -226,6 +322,8 @@ struct CudaExec {
     return check(err);
   }
   void shutdown() {
+    if (nccl_comm && nccl().CommDestroy) nccl().CommDestroy(nccl_comm);
+    nccl_comm = nullptr;
     tc.destroy();
     if (d_scal) cudaFree(d_scal);
     if (h_scal) cudaFreeHost(h_scal);
@@ -303,6 +401,51 @@ struct CudaExec {
   template <class E> int32_t logistic_tensor_setup(E& eng, const void* Xh, int32_t xd, const double* y, int64_t N, std::string& err) {
     return logistic_tc_setup(tc, eng, Xh, xd, y, N, err);
   }
+  // ---- row-sharded mode
+  static NcclApi& nccl() { static NcclApi api; return api; }
+  static int32_t nccl_unique_id(uint8_t* id) {
+    std::string err;
+    if (!nccl().load(err)) return BNUTS_ERR_UNSUPPORTED;
+    NcclApi::UniqueId u;
+    if (nccl().GetUniqueId(&u) != 0) return BNUTS_ERR_CUDA;
+    std::memcpy(id, u.internal, 128);
+    return 0;
+  }
+  int32_t nccl_init(const uint8_t* id, int world, int rank, std::string& err) {
+    if (!nccl().load(err)) return BNUTS_ERR_UNSUPPORTED;
+    note(cudaSetDevice(device), "cudaSetDevice");
+    if (nccl_comm) { nccl().CommDestroy(nccl_comm); nccl_comm = nullptr; }
+    NcclApi::UniqueId u;
+    std::memcpy(u.internal, id, 128);
+    const int r = nccl().CommInitRank(&nccl_comm, world, u, rank);
+    if (r != 0) { err = std::string("ncclCommInitRank: ") + nccl().GetErrorString(r); nccl_comm = nullptr; return BNUTS_ERR_CUDA; }
+    return 0;
+  }
+  template <class T> int64_t assign_rows(const EngineMem<T>& V, const EngineMem<T>& Mc) {
+    k_scan_rows<<<1, 1024, 0, stream>>>(V.stage_active, Mc.stage_row, V.C, d_scal);
+    k_gather_rows<T><<<warp_grid(V.C), ADV_THREADS, 0, stream>>>(V, Mc);
+    note(cudaGetLastError(), "row assignment");
+    return read_count();
+  }
+  template <class T> void fold_partials(const EngineMem<T>& M, int rows, T* red_g, double* red_l) {
+    k_fold_partials<T><<<warp_grid(rows), ADV_THREADS, 0, stream>>>(M, rows, red_g, red_l);
+    note(cudaGetLastError(), "fold partials");
+  }
+  int32_t allreduce(void* g, int64_t ng, bool g_is_f32, double* l, int64_t nl, bnuts_allreduce_fn fn, void* ctx, std::string& err) {
+    if (nccl_comm && !fn) {
+      // one fused exchange per leapfrog step: [rows x Dp] gradient + [rows] log density, summed in place
+      nccl().GroupStart();
+      int r1 = nccl().AllReduce(g, g, (size_t)ng, g_is_f32 ? 7 : 8, 0, nccl_comm, stream);   // ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0
+      int r2 = nccl().AllReduce(l, l, (size_t)nl, 8, 0, nccl_comm, stream);
+      int r3 = nccl().GroupEnd();
+      if (r1 || r2 || r3) { err = std::string("ncclAllReduce: ") + nccl().GetErrorString(r1 ? r1 : (r2 ? r2 : r3)); return BNUTS_ERR_CUDA; }
+      return 0;
+    }
+    if (!fn) { err = "row-sharded mode without a collective"; return BNUTS_ERR_INTERNAL; }
+    note(cudaStreamSynchronize(stream), "allreduce sync");
+    if (fn(ctx, g, ng, g_is_f32 ? 1 : 0) != 0 || fn(ctx, l, nl, 0) != 0) { err = "host allreduce callback failed"; return BNUTS_ERR_INTERNAL; }
+    return 0;
+  }
   template <class E> int32_t logistic_reference(E& eng, const double* beta_ref, std::string& err) {
     return logistic_tc_set_reference(tc, eng, beta_ref, err);
   }
@@ -333,6 +476,24 @@ struct CudaExec {
     for (int i = 0; i < 3; ++i) tot[i] = (int64_t)h_scal[i];
   }
 };
+
+bool NcclApi::load(std::string& err) {
+  if (lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+  if (!lib) { err = "NCCL not found (dlopen libnccl.so.2): " + std::string(dlerror() ? dlerror() : ""); return false; }
+  GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+  CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+  AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+  GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+  GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+  GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+  if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GroupStart || !GroupEnd || !GetErrorString) {
+    err = "NCCL symbols missing"; lib = nullptr; return false;
+  }
+  return true;
+}
 
 }  // namespace bn
 

@@ -87,6 +87,39 @@ struct HostExec {
     err = "tensor path is CUDA-only";
     return BNUTS_ERR_UNSUPPORTED;
   }
+  // ---- row-sharded mode (same semantics as the CUDA policy, serial loops)
+  static int32_t nccl_unique_id(uint8_t*) { return BNUTS_ERR_UNSUPPORTED; }
+  int32_t nccl_init(const uint8_t*, int, int, std::string& err) { err = "NCCL is CUDA-only"; return BNUTS_ERR_UNSUPPORTED; }
+  template <class T> int64_t assign_rows(const EngineMem<T>& V, const EngineMem<T>& Mc) {
+    int64_t n = 0;
+    for (int c = 0; c < V.C; ++c) {
+      if (!V.stage_active[c]) continue;
+      const int64_t r = n++;
+      Mc.stage_row[c] = (int32_t)r;
+      for (int d = 0; d < V.Dp; ++d) Mc.stage_q[r * V.Dp + d] = V.stage_q[size_t(c) * V.Dp + d];
+      V.stage_active[c] = 0;
+    }
+    count = 0;
+    return n;
+  }
+  template <class T> void fold_partials(const EngineMem<T>& M, int rows, T* red_g, double* red_l) {
+    const int64_t bs = int64_t(rows) * M.Dp;
+    for (int row = 0; row < rows; ++row) {
+      for (int d = 0; d < M.Dp; ++d) {
+        T acc = T(0);
+        if (d < M.D) for (int b = 0; b < M.stage_nb; ++b) acc = acc + M.stage_g[b * bs + int64_t(row) * M.Dp + d];
+        red_g[int64_t(row) * M.Dp + d] = acc;
+      }
+      double l = 0.0;
+      for (int b = 0; b < M.stage_nb; ++b) l += double(M.stage_l[int64_t(b) * rows + row]);
+      red_l[row] = l;
+    }
+  }
+  int32_t allreduce(void* g, int64_t ng, bool g_is_f32, double* l, int64_t nl, bnuts_allreduce_fn fn, void* ctx, std::string& err) {
+    if (!fn) { err = "row-sharded mode without a collective"; return BNUTS_ERR_INTERNAL; }
+    if (fn(ctx, g, ng, g_is_f32 ? 1 : 0) != 0 || fn(ctx, l, nl, 0) != 0) { err = "host allreduce callback failed"; return BNUTS_ERR_INTERNAL; }
+    return 0;
+  }
   template <class E> int32_t logistic_reference(E&, const double*, std::string& err) {
     err = "tensor path is CUDA-only";
     return BNUTS_ERR_UNSUPPORTED;

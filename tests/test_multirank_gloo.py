@@ -42,3 +42,64 @@ def test_two_ranks_equal_one_engine(tmp_path, bn):
     assert got.tobytes() == ch.tobytes()
     tot = np.load(tmp_path / "tot0.npy")
     assert tot[0] == st["steps"].sum() and tot[1] == 2.0
+
+
+# ---------------------------------------------------------------- row-sharded data
+def _gloo_allreduce(addr, count, dtype):
+    import ctypes
+    ct = ctypes.c_double if dtype == 0 else ctypes.c_float
+    a = np.ctypeslib.as_array((ct * count).from_address(addr))
+    t = torch.from_numpy(a)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)       # in place: t shares memory with the engine's buffer
+
+
+def _row_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import inplacedhmc_jl_b200 as bn
+    from conftest import make_logistic
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, D, C = 400, 9, 7
+    X, y, beta = make_logistic(N, D, seed=21)
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    e = bn.Engine(C, D, max_depth=6, lib=HOSTEMU_SO, seed=5)          # all chains on every rank, same seed
+    e.model_logistic(X[lo:hi], y[lo:hi], 1.0, row_blocks=2)            # one shard of the rows
+    e.set_allreduce(_gloo_allreduce)
+    rng = np.random.default_rng(4)
+    e.set_positions(beta[None, :] + rng.normal(size=(C, D)) * 0.3)
+    q, g, l = e.get_state()
+    e.find_initial_stepsize()
+    ch0, st0, _ = e.warmup_stage(30, 1)
+    ch, st, sel = e.sample(25, want_index=True)
+    np.savez(os.path.join(out, f"rows{rank}.npz"), g=g, l=l, ch=ch, st=st, sel=sel, eps=e.get_stepsize(), lockstep=e.counters()["lockstep_steps"])
+    dist.destroy_process_group()
+
+
+def test_row_sharded_replicas_agree_and_match_one_engine(tmp_path, bn):
+    """Two ranks hold half the rows each and all chains; gradients are summed per leapfrog (gloo).  The replicas
+    must be bit-identical to each other (same tree decisions on every rank) and equal to a single engine that
+    holds all rows up to summation order."""
+    from conftest import make_logistic
+    build_hostemu()
+    world = 2
+    mp.spawn(_row_worker, args=(world, 29519, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "rows0.npz"), np.load(tmp_path / "rows1.npz")
+    for k in ("g", "l", "ch", "st", "sel", "eps"):
+        assert r0[k].tobytes() == r1[k].tobytes(), k                   # replica determinism, bit for bit
+    N, D, C = 400, 9, 7
+    X, y, beta = make_logistic(N, D, seed=21)
+    e = bn.Engine(C, D, max_depth=6, lib=HOSTEMU_SO, seed=5)
+    e.model_logistic(X, y, 1.0, row_blocks=2)
+    rng = np.random.default_rng(4)
+    e.set_positions(beta[None, :] + rng.normal(size=(C, D)) * 0.3)
+    q, g, l = e.get_state()
+    np.testing.assert_allclose(r0["g"], g, rtol=1e-12, atol=1e-12)     # same sum, different association
+    np.testing.assert_allclose(r0["l"], l, rtol=1e-13)
+    e.find_initial_stepsize()
+    e.warmup_stage(30, 1)
+    ch, st, sel = e.sample(25, want_index=True)
+    # free-running chains: rounding differences of 1e-16 can flip a decision eventually; the bulk must coincide
+    same = (st["depth"] == r0["st"]["depth"]) & (st["steps"] == r0["st"]["steps"]) & (sel == r0["sel"])
+    assert same[:, :3].all() and same.mean() > 0.8, same.mean()
+    ok = same.all(axis=1)
+    np.testing.assert_allclose(r0["ch"][ok], ch[ok], rtol=1e-8, atol=1e-8)
