@@ -40,7 +40,9 @@ typedef enum {
 enum { BNUTS_F64 = 0, BNUTS_F32 = 1 };                 /* engine arithmetic type */
 enum { BNUTS_X_F64 = 0, BNUTS_X_F32 = 1, BNUTS_X_BF16 = 2 }; /* design-matrix storage */
 enum { BNUTS_GRAD_AUTO = 0, BNUTS_GRAD_DETERMINISTIC = 1, BNUTS_GRAD_TENSOR = 2 };
-enum { BNUTS_METRIC_NONE = 0, BNUTS_METRIC_DIAG = 1 }; /* ≙ TuningNUTS{Nothing|Diagonal}, src/warmup.jl:217-234 */
+enum { BNUTS_METRIC_NONE = 0, BNUTS_METRIC_DIAG = 1 }; /* ≙ TuningNUTS{Nothing|Diagonal}, src/warmup.jl:217-234
+                                                         (TuningNUTS{Symmetric} also adapts a diagonal in the reference:
+                                                         src/warmup.jl:309 -> src/hamiltonian.jl:117) */
 
 /* ≙ NUTS(max_depth, min_Δ) src/NUTS.jl:204-220 + run geometry */
 typedef struct {
@@ -118,6 +120,14 @@ int32_t bnuts_get_state(bnuts_engine* e, double* q, double* grad, double* logden
  * minv == NULL resets to the identity (src/warmup.jl:102). Per-chain metric. */
 int32_t bnuts_set_metric_diag(bnuts_engine* e, const double* minv /* [C][D] */);
 int32_t bnuts_get_metric_diag(bnuts_engine* e, double* minv /* [C][D] */);
+
+/* ≙ GaussianKineticEnergy(M⁻¹::AbstractMatrix) — the dense constructor the reference keeps only as a comment
+ * (src/hamiltonian.jl:44, W = cholesky(inv(M⁻¹)).L); its field types force Diagonal (:35-37).  One dense
+ * symmetric positive definite M⁻¹ [D][D] shared by all chains; kinetic energy ½pᵀM⁻¹p, p♯ = M⁻¹p, drift
+ * q + εM⁻¹p, momenta p = L⁻ᵀz with M⁻¹ = LLᵀ.  Implemented by whitening (see engine_core.h); Gaussian and iid
+ * normal targets.  minv == NULL returns to the per-chain diagonal metric.  Existing positions are kept. */
+int32_t bnuts_set_metric_dense(bnuts_engine* e, const double* minv /* [D][D] */);
+int32_t bnuts_get_metric_dense(bnuts_engine* e, double* minv /* [D][D] */);
 
 int32_t bnuts_set_stepsize(bnuts_engine* e, const double* eps /* [C] */);
 int32_t bnuts_get_stepsize(bnuts_engine* e, double* eps /* [C] */);

@@ -54,7 +54,7 @@ assert TREE_STATS_DTYPE.itemsize == 32
 EXPORTS = [
     "bnuts_create", "bnuts_destroy", "bnuts_last_error", "bnuts_model_iid_normal", "bnuts_model_funnel",
     "bnuts_model_gaussian", "bnuts_model_logistic", "bnuts_logistic_set_reference", "bnuts_set_positions", "bnuts_get_state",
-    "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed",
+    "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_set_metric_dense", "bnuts_get_metric_dense", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed",
     "bnuts_inject", "bnuts_leapfrog", "bnuts_find_initial_stepsize", "bnuts_warmup_stage", "bnuts_sample",
     "bnuts_counters", "bnuts_profile", "bnuts_chain_status", "bnuts_set_allreduce", "bnuts_nccl_unique_id", "bnuts_set_nccl",
 ]
@@ -93,6 +93,8 @@ def load_library(path=None):
     lib.bnuts_get_state.argtypes = [_P, _P, _P, _P]
     lib.bnuts_set_metric_diag.argtypes = [_P, _P]
     lib.bnuts_get_metric_diag.argtypes = [_P, _P]
+    lib.bnuts_set_metric_dense.argtypes = [_P, _P]
+    lib.bnuts_get_metric_dense.argtypes = [_P, _P]
     lib.bnuts_set_stepsize.argtypes = [_P, _P]
     lib.bnuts_get_stepsize.argtypes = [_P, _P]
     lib.bnuts_seed.argtypes = [_P, C.c_uint64, C.c_uint32]
@@ -228,6 +230,16 @@ class Engine:
     def get_metric_diag(self):
         m = np.empty((self.C, self.D))
         self._chk(self.lib.bnuts_get_metric_diag(self.h, _ptr(m)))
+        return m
+
+    def set_metric_dense(self, minv=None):
+        """One dense SPD M⁻¹ [D, D] shared by all chains (None: back to the per-chain diagonal metric)."""
+        m = _f64(minv, (self.D, self.D))
+        self._chk(self.lib.bnuts_set_metric_dense(self.h, _ptr(m)))
+
+    def get_metric_dense(self):
+        m = np.empty((self.D, self.D))
+        self._chk(self.lib.bnuts_get_metric_dense(self.h, _ptr(m)))
         return m
 
     def set_stepsize(self, eps):

@@ -77,6 +77,11 @@ int32_t bnuts_get_metric_diag(bnuts_engine* e, double* m) {
   if (!m) return BNUTS_ERR_INVALID_ARGUMENT;
   BN_DISPATCH(e, get_metric(m));
 }
+int32_t bnuts_set_metric_dense(bnuts_engine* e, const double* m) { BN_DISPATCH(e, set_metric_dense(m)); }
+int32_t bnuts_get_metric_dense(bnuts_engine* e, double* m) {
+  if (!m) return BNUTS_ERR_INVALID_ARGUMENT;
+  BN_DISPATCH(e, get_metric_dense(m));
+}
 int32_t bnuts_set_stepsize(bnuts_engine* e, const double* eps) {
   if (!eps) return BNUTS_ERR_INVALID_ARGUMENT;
   BN_DISPATCH(e, set_stepsize(eps));

@@ -13,6 +13,8 @@
 // warmup!(TuningNUTS) (src/warmup.jl:269-314), bnuts_sample ≙ mcmc!
 // (src/warmup.jl:316-332), bnuts_find_initial_stepsize ≙ src/warmup.jl:188-200.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 #include <cstring>
@@ -38,6 +40,19 @@ template <class T> struct ModelCtx {
   bool batched() const { return kind == MODEL_GAUSSIAN || kind == MODEL_LOGISTIC; }
 };
 
+// Shared dense metric M⁻¹ = L·Lᵀ (≙ GaussianKineticEnergy(M⁻¹::AbstractMatrix), the upstream constructor the
+// reference keeps only as a comment, src/hamiltonian.jl:44).  HMC with a dense metric is, step for step, HMC
+// with the unit metric on the whitened variable q̃ = L⁻¹q: p̃ = Lᵀp ~ N(0, I), ½p̃ᵀp̃ = ½pᵀM⁻¹p,
+// q̃′ = q̃ + ε p̃ₘ ⇔ q′ = q + ε M⁻¹pₘ, ∇ℓ̃ = Lᵀ∇ℓ, and the turn test ρ̃·p̃ = ρᵀM⁻¹p.  So the per-chain state
+// machine runs unchanged in whitened coordinates, the metric lives in the model (for the Gaussian target
+// P̃ = LᵀPL: one GEMM operand instead of three metric applications per leapfrog) and positions, momenta and
+// gradients are mapped at the C-ABI boundary by batched matrix products on the device.
+struct DenseMetric {
+  bool on = false;
+  std::vector<double> Minv, L, Linv;                 // host, [D][D] row-major
+  double* dL = nullptr; double* dLt = nullptr; double* dLinv = nullptr; double* dLinvt = nullptr;   // device
+};
+
 template <class T, class X> struct EngineCore {
   bnuts_config cfg{};
   X x;
@@ -54,6 +69,10 @@ template <class T, class X> struct EngineCore {
   double* d_tmp_cd = nullptr;   // [C][D] scratch (positions / momenta in)
   double* d_tmp_c = nullptr;    // [C]
   std::vector<double> h_draws;  // staging when caller strides are not compact
+  DenseMetric dm;
+  std::vector<double> h_P;      // Gaussian target precision as given by the caller (user coordinates)
+  int32_t user_model_kind = MODEL_NONE;
+  double* d_xf_in = nullptr; double* d_xf_out = nullptr; size_t cap_xf = 0;   // transform scratch
   // row-sharded data: per-leapfrog sum of the gradient partials over the group
   bool reduce_on = false;
   bnuts_allreduce_fn red_fn = nullptr; void* red_ctx = nullptr;
@@ -97,6 +116,8 @@ template <class T, class X> struct EngineCore {
   void destroy() {
     x.sync();
     free_reduce();
+    free_dense();
+    if (d_xf_in) { x.free(d_xf_in); x.free(d_xf_out); d_xf_in = d_xf_out = nullptr; }
     void* ptrs[] = {M.zs, M.zlq, M.st_rho, M.st_psf, M.m_rho, M.m_psm, M.m_psp, M.ps_cur, M.Minv, M.W, M.cs,
                     M.stage_q, M.stage_g, M.stage_l, M.stage_ld, M.stage_bh, M.stage_bm, M.stage_bl, M.stage_row, M.draws, d_stats, d_sel, d_eps_hist,
                     d_inj_dirs, d_inj_p, d_tmp_cd, d_tmp_c, model.P, model.X, model.y, model.Xb, model.yf};
@@ -148,13 +169,61 @@ template <class T, class X> struct EngineCore {
                    (void**)&M.stage_bm, (void**)&M.stage_bl, (void**)&M.stage_row};
     for (void** p : ps) if (*p) { x.free(*p); *p = nullptr; }
     model = ModelCtx<T>();
+    user_model_kind = MODEL_NONE; h_P.clear();
     M.stage_nb = 0;
     M.beta_ref = nullptr; M.lin_w = nullptr;
   }
   int32_t model_simple(int kind) {
     free_model();
     model.kind = kind; M.model_kind = kind;
+    user_model_kind = kind; h_P.clear();
+    if (dm.on) return apply_dense_to_model();
     return 0;
+  }
+  int32_t upload_gaussian(const std::vector<double>& Pd) {
+    const size_t n = size_t(M.D) * M.D;
+    std::vector<T> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = T(Pd[i]);
+    if (!model.P) model.P = x.template alloc<T>(n);
+    x.h2d(model.P, h.data(), n * sizeof(T));
+    if (!M.stage_q) alloc_stage(1);
+    model.kind = MODEL_GAUSSIAN; M.model_kind = MODEL_GAUSSIAN;
+    return x.check(err);
+  }
+  // whitened model: P̃ = Lᵀ P L (P = I for the iid normal target)
+  int32_t apply_dense_to_model() {
+    const int D = M.D;
+    if (user_model_kind == MODEL_NONE) return 0;
+    if (user_model_kind != MODEL_GAUSSIAN && user_model_kind != MODEL_IID_NORMAL)
+      return fail(BNUTS_ERR_UNSUPPORTED, "dense metric is implemented for the Gaussian and iid normal targets");
+    std::vector<double> T1(size_t(D) * D, 0.0), Pt(size_t(D) * D, 0.0);
+    const double* L = dm.L.data();
+    if (user_model_kind == MODEL_GAUSSIAN) {   // T1 = P L
+      for (int i = 0; i < D; ++i)
+        for (int k = 0; k < D; ++k) {
+          const double pik = h_P[size_t(i) * D + k];
+          for (int j = 0; j <= k; ++j) T1[size_t(i) * D + j] += pik * L[size_t(k) * D + j];
+        }
+    } else {
+      T1 = dm.L;
+    }
+    for (int k = 0; k < D; ++k)               // P̃ = Lᵀ T1
+      for (int i = 0; i <= k; ++i) {
+        const double lki = L[size_t(k) * D + i];
+        for (int j = 0; j < D; ++j) Pt[size_t(i) * D + j] += lki * T1[size_t(k) * D + j];
+      }
+    for (int i = 0; i < D; ++i)               // symmetrise away rounding asymmetry
+      for (int j = 0; j < i; ++j) {
+        const double s = 0.5 * (Pt[size_t(i) * D + j] + Pt[size_t(j) * D + i]);
+        Pt[size_t(i) * D + j] = s; Pt[size_t(j) * D + i] = s;
+      }
+    if (model.kind != MODEL_GAUSSIAN) free_model_keep_user();
+    return upload_gaussian(Pt);
+  }
+  void free_model_keep_user() {
+    const int32_t k = user_model_kind; std::vector<double> p = h_P;
+    free_model();
+    user_model_kind = k; h_P = p;
   }
   // partial_rows = rows of the partial-output buffers (>= nb * C)
   void alloc_stage(int nb, size_t partial_rows = 0) {
@@ -176,16 +245,14 @@ template <class T, class X> struct EngineCore {
     if (!P) return fail(BNUTS_ERR_INVALID_ARGUMENT, "precision is NULL");
     free_model();
     const size_t n = size_t(M.D) * M.D;
-    std::vector<T> h(n);
-    for (size_t i = 0; i < n; ++i) h[i] = T(P[i]);
-    model.P = x.template alloc<T>(n);
-    x.h2d(model.P, h.data(), n * sizeof(T));
-    alloc_stage(1);
-    model.kind = MODEL_GAUSSIAN; M.model_kind = MODEL_GAUSSIAN;
-    return x.check(err);
+    h_P.assign(P, P + n);
+    user_model_kind = MODEL_GAUSSIAN;
+    if (dm.on) return apply_dense_to_model();
+    return upload_gaussian(h_P);
   }
   int32_t model_logistic(const void* Xh, int32_t xd, const double* y, int64_t N, double tau, int32_t rb) {
     if (!Xh || !y || N <= 0 || rb <= 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad logistic arguments");
+    if (dm.on) return fail(BNUTS_ERR_UNSUPPORTED, "dense metric is implemented for the Gaussian and iid normal targets");
     if (xd != BNUTS_X_F64 && xd != BNUTS_X_F32 && xd != BNUTS_X_BF16) return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad x_dtype");
     free_model();
     const bool want_tensor = cfg.gradient_path == BNUTS_GRAD_TENSOR ||
@@ -217,6 +284,7 @@ template <class T, class X> struct EngineCore {
     }
     model.N = N;
     M.tau = T(tau);
+    user_model_kind = MODEL_LOGISTIC;
     model.kind = MODEL_LOGISTIC; M.model_kind = MODEL_LOGISTIC;
     return x.check(err);
   }
@@ -241,6 +309,94 @@ template <class T, class X> struct EngineCore {
     x.h2d(M.W, hw.data(), hw.size() * sizeof(T));
     return x.check(err);
   }
+  // ---------------------------------------------------------------- dense metric (see DenseMetric above)
+  void free_dense() {
+    void** ps[] = {(void**)&dm.dL, (void**)&dm.dLt, (void**)&dm.dLinv, (void**)&dm.dLinvt};
+    for (void** p : ps) if (*p) { x.free(*p); *p = nullptr; }
+    dm.on = false; dm.Minv.clear(); dm.L.clear(); dm.Linv.clear();
+  }
+  void xf_reserve(size_t n) {
+    if (n <= cap_xf) return;
+    if (d_xf_in) { x.free(d_xf_in); x.free(d_xf_out); }
+    d_xf_in = x.template alloc<double>(n); d_xf_out = x.template alloc<double>(n);
+    cap_xf = n;
+  }
+  // rows [R][D] (device, Float64) times a D x D matrix, in place through the scratch buffer
+  void xf_device(double* rows, int64_t R, const double* mat) {
+    xf_reserve(size_t(R) * M.D);
+    x.rows_times_matrix(rows, d_xf_out, R, M.D, mat);
+    x.d2d(rows, d_xf_out, size_t(R) * M.D * sizeof(double));
+  }
+  // host rows -> device scratch, transformed; returns the device pointer of the result
+  double* xf_host(const double* rows, int64_t R, const double* mat) {
+    xf_reserve(size_t(R) * M.D);
+    x.h2d(d_xf_in, rows, size_t(R) * M.D * sizeof(double));
+    x.rows_times_matrix(d_xf_in, d_xf_out, R, M.D, mat);
+    return d_xf_out;
+  }
+  int32_t set_metric_dense(const double* minv) {
+    const int D = M.D;
+    // current positions in user coordinates, to be re-expressed under the new metric
+    std::vector<double> q_user;
+    const bool have_pos = model.kind != MODEL_NONE && !x.any_status(M, ST_NONFINITE_START);
+    if (have_pos) { q_user.resize(size_t(M.C) * D); int32_t rc = get_state(q_user.data(), nullptr, nullptr); if (rc) return rc; }
+    if (!minv) {
+      free_dense();
+      if (user_model_kind == MODEL_GAUSSIAN) { int32_t rc = upload_gaussian(h_P); if (rc) return rc; }
+      else if (user_model_kind == MODEL_IID_NORMAL) { const int32_t k = user_model_kind; free_model(); model.kind = k; M.model_kind = k; user_model_kind = k; }
+    } else {
+      if (user_model_kind != MODEL_NONE && user_model_kind != MODEL_GAUSSIAN && user_model_kind != MODEL_IID_NORMAL)
+        return fail(BNUTS_ERR_UNSUPPORTED, "dense metric is implemented for the Gaussian and iid normal targets");
+      const size_t n = size_t(D) * D;
+      std::vector<double> A(minv, minv + n), L(n, 0.0), Li(n, 0.0);
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < i; ++j)
+          if (std::fabs(A[size_t(i) * D + j] - A[size_t(j) * D + i]) > 1e-10 * (std::fabs(A[size_t(i) * D + i]) + std::fabs(A[size_t(j) * D + j])))
+            return fail(BNUTS_ERR_INVALID_ARGUMENT, "dense metric must be symmetric");
+      for (int j = 0; j < D; ++j) {            // Cholesky M⁻¹ = L Lᵀ
+        double s = A[size_t(j) * D + j];
+        for (int k = 0; k < j; ++k) s -= L[size_t(j) * D + k] * L[size_t(j) * D + k];
+        if (!(s > 0.0)) return fail(BNUTS_ERR_INVALID_ARGUMENT, "dense metric must be positive definite");
+        const double ljj = std::sqrt(s);
+        L[size_t(j) * D + j] = ljj;
+        for (int i = j + 1; i < D; ++i) {
+          double t = A[size_t(i) * D + j];
+          for (int k = 0; k < j; ++k) t -= L[size_t(i) * D + k] * L[size_t(j) * D + k];
+          L[size_t(i) * D + j] = t / ljj;
+        }
+      }
+      for (int c = 0; c < D; ++c) {            // L⁻¹ by forward substitution, column by column
+        Li[size_t(c) * D + c] = 1.0 / L[size_t(c) * D + c];
+        for (int i = c + 1; i < D; ++i) {
+          double t = 0.0;
+          for (int k = c; k < i; ++k) t -= L[size_t(i) * D + k] * Li[size_t(k) * D + c];
+          Li[size_t(i) * D + c] = t / L[size_t(i) * D + i];
+        }
+      }
+      free_dense();
+      dm.Minv = A; dm.L = L; dm.Linv = Li;
+      std::vector<double> Lt(n), Lit(n);
+      for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) { Lt[size_t(j) * D + i] = L[size_t(i) * D + j]; Lit[size_t(j) * D + i] = Li[size_t(i) * D + j]; }
+      dm.dL = x.template alloc<double>(n); dm.dLt = x.template alloc<double>(n);
+      dm.dLinv = x.template alloc<double>(n); dm.dLinvt = x.template alloc<double>(n);
+      x.h2d(dm.dL, L.data(), n * 8); x.h2d(dm.dLt, Lt.data(), n * 8); x.h2d(dm.dLinv, Li.data(), n * 8); x.h2d(dm.dLinvt, Lit.data(), n * 8);
+      dm.on = true;
+      int32_t rc = apply_dense_to_model();
+      if (rc) return rc;
+    }
+    int32_t rc = set_metric(nullptr);          // the per-chain diagonal lives in the (new) sampling coordinates
+    if (rc) return rc;
+    if (have_pos && model.kind != MODEL_NONE) return set_positions(q_user.data());
+    return x.check(err);
+  }
+  int32_t get_metric_dense(double* out) {
+    const size_t n = size_t(M.D) * M.D;
+    if (dm.on) { std::memcpy(out, dm.Minv.data(), n * 8); return 0; }
+    std::fill(out, out + n, 0.0);
+    for (int d = 0; d < M.D; ++d) out[size_t(d) * M.D + d] = 1.0;
+    return 0;
+  }
+
   int32_t get_metric(double* out) {
     std::vector<T> hm(size_t(M.C) * M.Dp);
     x.d2h(hm.data(), M.Minv, hm.size() * sizeof(T));
@@ -337,6 +493,8 @@ template <class T, class X> struct EngineCore {
     if (N <= 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "N must be positive");
     if (metric_kind != BNUTS_METRIC_NONE && metric_kind != BNUTS_METRIC_DIAG)
       return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad metric_kind");
+    if (metric_kind == BNUTS_METRIC_DIAG && dm.on)
+      return fail(BNUTS_ERR_UNSUPPORTED, "diagonal adaptation on top of a dense metric is not supported");
     const bool want_draws = chain_out != nullptr || metric_kind == BNUTS_METRIC_DIAG;
     ensure_out(N, want_draws);
     double* keep_draws = M.draws;
@@ -351,6 +509,7 @@ template <class T, class X> struct EngineCore {
     if (metric_kind == BNUTS_METRIC_DIAG) x.metric_update(M, N, lambda < 0 ? 5.0 / N : lambda);  // ≙ src/warmup.jl:308-309
     if (da) x.finish_da(M);                                                                     // ≙ final_ϵ, :313
     next_t += uint32_t(N);
+    if (dm.on && chain_out) xf_device(M.draws, int64_t(M.C) * N, dm.dLt);   // draws back to user coordinates: q = L q̃
     copy_out(N, chain_out, sd, sc, stats_out, ssc, sel, eps_out);
     M.draws = keep_draws;
     rc = x.check(err);
@@ -362,7 +521,11 @@ template <class T, class X> struct EngineCore {
 
   int32_t set_positions(const double* q) {
     if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
-    if (q) { x.h2d(d_tmp_cd, q, size_t(M.C) * M.D * sizeof(double)); M.pos_in = d_tmp_cd; } else M.pos_in = nullptr;
+    if (q && dm.on) {                       // q̃ = L⁻¹ q
+      double* qt = xf_host(q, M.C, dm.dLinvt);
+      x.d2d(d_tmp_cd, qt, size_t(M.C) * M.D * sizeof(double));
+      M.pos_in = d_tmp_cd;
+    } else if (q) { x.h2d(d_tmp_cd, q, size_t(M.C) * M.D * sizeof(double)); M.pos_in = d_tmp_cd; } else M.pos_in = nullptr;
     PrepareArgs a{}; a.mode = MODE_EVAL;
     if (reduce_on) x.prepare(reduce_view(0), rp, a); else x.prepare(M, rp, a);
     int32_t rc = run(true);
@@ -374,6 +537,7 @@ template <class T, class X> struct EngineCore {
     double* o = d_tmp_cd;
     x.gather_state(M, o);
     const size_t n = size_t(M.C) * M.D;
+    if (dm.on) { xf_device(o, M.C, dm.dLt); xf_device(o + n, M.C, dm.dLinv); }   // q = L q̃,  ∇ℓ = L⁻ᵀ ∇ℓ̃
     if (q) x.d2h(q, o, n * sizeof(double));
     if (g) x.d2h(g, o + n, n * sizeof(double));
     if (l) x.d2h(l, o + 2 * n, size_t(M.C) * sizeof(double));
@@ -389,7 +553,8 @@ template <class T, class X> struct EngineCore {
     }
     if (p && Tn > 0) {
       d_inj_p = x.template alloc<double>(size_t(Tn) * M.C * M.D);
-      x.h2d(d_inj_p, p, size_t(Tn) * M.C * M.D * sizeof(double));
+      if (dm.on) x.d2d(d_inj_p, xf_host(p, int64_t(Tn) * M.C, dm.dL), size_t(Tn) * M.C * M.D * sizeof(double));   // p̃ = Lᵀ p
+      else x.h2d(d_inj_p, p, size_t(Tn) * M.C * M.D * sizeof(double));
     }
     rp.inj_T = Tn; rp.inj_start = next_t; rp.inj_dirs = d_inj_dirs; rp.inj_p = d_inj_p;
     return x.check(err);
@@ -401,12 +566,14 @@ template <class T, class X> struct EngineCore {
     const size_t n = size_t(M.C) * M.D;
     double* d_p = x.template alloc<double>(n);
     double* d_out = x.template alloc<double>(3 * n + M.C);
-    x.h2d(d_p, p_in, n * sizeof(double));
+    if (dm.on) x.d2d(d_p, xf_host(p_in, M.C, dm.dL), n * sizeof(double));   // p̃ = Lᵀ p
+    else x.h2d(d_p, p_in, n * sizeof(double));
     x.h2d(d_tmp_c, eps, size_t(M.C) * sizeof(double));
     M.bare_p_in = d_p; M.bare_out = d_out;
     PrepareArgs a{}; a.mode = MODE_BARE; a.N = nsteps; a.bare_eps = d_tmp_c;
     x.prepare(M, rp, a);
     int32_t rc = run(false);
+    if (!rc && dm.on) { xf_device(d_out, M.C, dm.dLt); xf_device(d_out + n, M.C, dm.dLinv); xf_device(d_out + 2 * n, M.C, dm.dLinv); }
     if (!rc) {
       if (q_out) x.d2h(q_out, d_out, n * sizeof(double));
       if (p_out) x.d2h(p_out, d_out + n, n * sizeof(double));

@@ -219,6 +219,51 @@ __global__ void __launch_bounds__(256) k_grad_gaussian(const T* __restrict__ P, 
     }
 }
 
+// out[r][j] = sum_k in[r][k] mat[k][j] in Float64, k strictly sequential: the coordinate maps of the dense
+// metric at the C-ABI boundary (positions, momenta, gradients, draws).  64x64 output tile, 4x4 per thread.
+__global__ void __launch_bounds__(256) k_rows_times_matrix(const double* __restrict__ in, double* out, long long R, int D,
+                                                           const double* __restrict__ mat) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ double As[TK][TM + 1];
+  __shared__ double Bs[TK][TN + 1];
+  const long long r0 = (long long)blockIdx.y * TM;
+  const int j0 = blockIdx.x * TN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < D; k0 += TK) {
+    for (int idx = threadIdx.x; idx < TM * TK; idx += 256) {
+      const int r = idx / TK, k = idx % TK;
+      As[k][r] = (r0 + r < R && k0 + k < D) ? in[(r0 + r) * D + k0 + k] : 0.0;
+      const int kb = idx / TN, jb = idx % TN;
+      Bs[kb][jb] = (k0 + kb < D && j0 + jb < D) ? mat[(long long)(k0 + kb) * D + j0 + jb] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long r = r0 + ty * 4 + i;
+      const int jj = j0 + tx * 4 + j;
+      if (r < R && jj < D) out[r * D + jj] = acc[i][j];
+    }
+}
+
 // One warp = 32 chains, one CTA per (chain group, row block).  Rows of the block are
 // walked sequentially; eta and the gradient partials accumulate in index order.
 template <class T>
@@ -339,6 +384,12 @@ struct CudaExec {
   void free(void* p) { cudaFree(p); }
   void h2d(void* d, const void* s, size_t n) { note(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream), "h2d"); note(cudaStreamSynchronize(stream), "h2d sync"); }
   void d2h(void* d, const void* s, size_t n) { note(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream), "d2h"); note(cudaStreamSynchronize(stream), "d2h sync"); }
+  void d2d(void* d, const void* s, size_t n) { note(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream), "d2d"); }
+  void rows_times_matrix(const double* in, double* out, int64_t R, int D, const double* mat) {
+    dim3 grid((D + 63) / 64, (unsigned)((R + 63) / 64));
+    k_rows_times_matrix<<<grid, 256, 0, stream>>>(in, out, (long long)R, D, mat);
+    note(cudaGetLastError(), "rows_times_matrix");
+  }
   void zero(void* d, size_t n) { note(cudaMemsetAsync(d, 0, n, stream), "memset"); }
   void sync() { note(cudaStreamSynchronize(stream), "sync"); }
   int32_t check(std::string& err) {

@@ -17,6 +17,7 @@
 // Structure deliberately mirrors the reference (recursive adjacent_tree), unlike
 // the CUDA engine (iterative per-chain state machine).
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -163,6 +164,13 @@ template <class T> struct Engine {
   Model<T> model;
   std::vector<T> q, g, lq;       // [C][D], [C][D], [C]
   std::vector<T> Minv, W;        // [C][D]   (GaussianKineticEnergy, src/hamiltonian.jl:33-38)
+  // shared dense metric (≙ the dense GaussianKineticEnergy constructor kept as a comment at
+  // src/hamiltonian.jl:44): M⁻¹ [D][D] and the momentum factor W = L⁻ᵀ with M⁻¹ = L Lᵀ, so W Wᵀ = M.
+  // Applied DIRECTLY here (mat-vecs in the kinetic energy, p♯, the drift and the momentum draw); the device
+  // engine whitens instead, so agreement of the two is a check of that equivalence.
+  bool dense = false;
+  std::vector<T> MinvD, WD;      // [D][D] row-major
+  std::vector<double> MinvD64;
   std::vector<double> eps;       // [C]
   std::vector<int32_t> status;   // [C]
   uint64_t seed = 0;
@@ -189,11 +197,44 @@ template <class T> struct Ham {
   int c;  // local chain
   const T* Minv() const { return &E->Minv[size_t(c) * E->D]; }
   const T* W() const { return &E->W[size_t(c) * E->D]; }
+  bool dense() const { return E->dense; }
+  // out = M⁻¹ v, k sequential
+  void apply_minv(const T* v, T* out) const {
+    const int D = E->D;
+    for (int i = 0; i < D; ++i) {
+      T acc = T(0);
+      const T* row = &E->MinvD[size_t(i) * D];
+      for (int k = 0; k < D; ++k) acc = fma_(row[k], v[k], acc);
+      out[i] = acc;
+    }
+  }
+  // p = W z  (≙ rand_p!, src/kinetic_energy.jl:63, with a dense W)
+  void draw_momentum(T* p, uint64_t seed, uint32_t gchain, uint32_t t) const {
+    const int D = E->D;
+    if (!E->dense) {
+      const T* Wd = W();
+      for (int d = 0; d < D; ++d) p[d] = Wd[d] * bn::std_normal(seed, gchain, t, uint32_t(d), T(0));
+      return;
+    }
+    std::vector<T> z(D);
+    for (int d = 0; d < D; ++d) z[d] = bn::std_normal(seed, gchain, t, uint32_t(d), T(0));
+    for (int i = 0; i < D; ++i) {
+      T acc = T(0);
+      const T* row = &E->WD[size_t(i) * D];
+      for (int k = 0; k < D; ++k) acc = fma_(row[k], z[k], acc);
+      p[i] = acc;
+    }
+  }
 };
 
 // ≙ kinetic_energy, src/kinetic_energy.jl:14-24:  ke += p*M⁻¹*p ; 0.5*ke
 template <class T> T kinetic_energy(const Ham<T>& H, const T* p) {
   const int D = H.E->D;
+  if (H.dense()) {
+    std::vector<T> ps(D);
+    H.apply_minv(p, ps.data());
+    return T(0.5) * dot_warp(ps.data(), p, D);
+  }
   const T* Mi = H.Minv();
   T part[32];
   for (int l = 0; l < 32; ++l) part[l] = T(0);
@@ -211,6 +252,7 @@ template <class T> T* calculate_psharp(Arena<T>& A, const Ham<T>& H, const T* p)
   const int D = H.E->D;
   const T* Mi = H.Minv();
   T* ps = A.alloc(D);
+  if (H.dense()) { H.apply_minv(p, ps); return ps; }
   for (int d = 0; d < D; ++d) ps[d] = Mi[d] * p[d];
   return ps;
 }
@@ -230,6 +272,11 @@ template <class T> PhasePoint<T> leapfrog(ChainCtx<T>& X, const Ham<T>& H, const
   n.q = X.arena.alloc(D);
   n.g = X.arena.alloc(D);
   const T eh = T(0.5) * eps;
+  if (H.dense()) {
+    for (int d = 0; d < D; ++d) n.p[d] = fma_(eh, z.g[d], z.p[d]);
+    H.apply_minv(n.p, n.g);                       // n.g as scratch: M⁻¹ pₘ
+    for (int d = 0; d < D; ++d) n.q[d] = fma_(eps, n.g[d], z.q[d]);
+  } else
   for (int d = 0; d < D; ++d) {
     const T pm = fma_(eh, z.g[d], z.p[d]);
     n.p[d] = pm;
@@ -390,8 +437,7 @@ bnuts_tree_stats sample_tree(Engine<T>& E, ChainCtx<T>& X, int c, double eps, ui
   if (injected && E.has_inj_p) {
     for (int d = 0; d < D; ++d) z.p[d] = T(E.inj_p[(it * E.C + c) * D + d]);
   } else {  // ≙ rand_p!, src/kinetic_energy.jl:63: p = W .* randn
-    const T* W = H.W();
-    for (int d = 0; d < D; ++d) z.p[d] = W[d] * bn::std_normal(E.seed, gchain, t, uint32_t(d), T(0));
+    H.draw_momentum(z.p, E.seed, gchain, t);
   }
   Trajectory<T> tr{logdensity(H, z), T(eps), T(E.cfg.min_delta), E.seed, gchain, t};
   Proposal<T> zeta;
@@ -525,6 +571,8 @@ int32_t run_transitions(Engine<T>& E, int N, const bnuts_dual_averaging* da, int
                         int32_t* sel, double* eps_out) {
   if (E.model.kind == bn::MODEL_NONE) return fail(E, BNUTS_ERR_NO_MODEL, "no model set");
   if (N <= 0) return fail(E, BNUTS_ERR_INVALID_ARGUMENT, "N must be positive");
+  if (metric_kind == BNUTS_METRIC_DIAG && E.dense)
+    return fail(E, BNUTS_ERR_UNSUPPORTED, "diagonal adaptation on top of a dense metric is not supported");
   ensure_ctx(E);
   const int C = E.C, D = E.D;
   const uint32_t t0 = E.next_t;
@@ -578,9 +626,8 @@ template <class T> int32_t initial_stepsize(Engine<T>& E, const bnuts_stepsize_s
     ChainCtx<T>& X = E.ctx[omp_get_thread_num()];
     Ham<T> H{&E, c};
     std::vector<T> p(D);
-    const T* W = H.W();
     const uint32_t gchain = uint32_t(E.cfg.chain_offset + c);
-    for (int d = 0; d < D; ++d) p[d] = W[d] * bn::std_normal(E.seed, gchain, t, uint32_t(d), T(0));  // ≙ src/warmup.jl:195
+    H.draw_momentum(p.data(), E.seed, gchain, t);  // ≙ src/warmup.jl:195
     PhasePoint<T> z{&E.q[size_t(c) * D], p.data(), &E.g[size_t(c) * D], E.lq[c]};
     const T target = logdensity(H, z);
     if (!isfinite_(target)) { E.status[c] = BNUTS_ERR_NONFINITE_START; bad += 1; continue; }
@@ -667,6 +714,40 @@ int32_t model_logistic(Engine<T>& E, const void* X, int32_t xd, const double* y,
   for (int64_t i = 0; i < N; ++i) E.model.y[size_t(i)] = T(y[i]);
   return 0;
 }
+template <class T> int32_t set_metric_dense(Engine<T>& E, const double* minv) {
+  const int D = E.D;
+  const size_t n = size_t(D) * D;
+  if (!minv) { E.dense = false; E.MinvD.clear(); E.WD.clear(); E.MinvD64.clear(); return 0; }
+  std::vector<double> L(n, 0.0), Li(n, 0.0);
+  for (int j = 0; j < D; ++j) {
+    double s = minv[size_t(j) * D + j];
+    for (int k = 0; k < j; ++k) s -= L[size_t(j) * D + k] * L[size_t(j) * D + k];
+    if (!(s > 0.0)) return fail(E, BNUTS_ERR_INVALID_ARGUMENT, "dense metric must be positive definite");
+    const double ljj = std::sqrt(s);
+    L[size_t(j) * D + j] = ljj;
+    for (int i = j + 1; i < D; ++i) {
+      double t = minv[size_t(i) * D + j];
+      for (int k = 0; k < j; ++k) t -= L[size_t(i) * D + k] * L[size_t(j) * D + k];
+      L[size_t(i) * D + j] = t / ljj;
+    }
+  }
+  for (int c = 0; c < D; ++c) {
+    Li[size_t(c) * D + c] = 1.0 / L[size_t(c) * D + c];
+    for (int i = c + 1; i < D; ++i) {
+      double t = 0.0;
+      for (int k = c; k < i; ++k) t -= L[size_t(i) * D + k] * Li[size_t(k) * D + c];
+      Li[size_t(i) * D + c] = t / L[size_t(i) * D + i];
+    }
+  }
+  E.MinvD.resize(n); E.WD.resize(n); E.MinvD64.assign(minv, minv + n);
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      E.MinvD[size_t(i) * D + j] = T(minv[size_t(i) * D + j]);
+      E.WD[size_t(i) * D + j] = T(Li[size_t(j) * D + i]);   // W = L⁻ᵀ
+    }
+  E.dense = true;
+  return 0;
+}
 template <class T> int32_t set_metric(Engine<T>& E, const double* minv) {
   const size_t n = size_t(E.C) * E.D;
   for (size_t i = 0; i < n; ++i) {
@@ -734,6 +815,16 @@ int32_t bnuts_set_nccl(bnuts_engine*, const uint8_t*, int32_t, int32_t) { return
 int32_t bnuts_set_positions(bnuts_engine* e, const double* q) { DISPATCH(e, set_positions(E, q), set_positions(E, q)); }
 int32_t bnuts_get_state(bnuts_engine* e, double* q, double* g, double* l) { DISPATCH(e, get_state(E, q, g, l), get_state(E, q, g, l)); }
 int32_t bnuts_set_metric_diag(bnuts_engine* e, const double* m) { DISPATCH(e, set_metric(E, m), set_metric(E, m)); }
+int32_t bnuts_set_metric_dense(bnuts_engine* e, const double* m) { DISPATCH(e, set_metric_dense(E, m), set_metric_dense(E, m)); }
+int32_t bnuts_get_metric_dense(bnuts_engine* e, double* m) {
+  if (!m) return BNUTS_ERR_INVALID_ARGUMENT;
+  auto get = [&](auto& E) {
+    const size_t D = size_t(E.D);
+    for (size_t i = 0; i < D * D; ++i) m[i] = E.dense ? E.MinvD64[i] : ((i / D == i % D) ? 1.0 : 0.0);
+    return 0;
+  };
+  DISPATCH(e, get(E), get(E));
+}
 int32_t bnuts_get_metric_diag(bnuts_engine* e, double* m) {
   if (!m) return BNUTS_ERR_INVALID_ARGUMENT;
   DISPATCH(e, ([&] { for (size_t i = 0; i < E.Minv.size(); ++i) m[i] = double(E.Minv[i]); return 0; })(),

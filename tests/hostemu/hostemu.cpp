@@ -5,6 +5,7 @@
 // control code and vector-loop code of the CUDA engine against the oracle without
 // a GPU.  It is never shipped or loaded by the product; libbnuts.so contains only
 // the CUDA execution policy.
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -22,6 +23,15 @@ struct HostExec {
   void free(void* p) { std::free(p); }
   void h2d(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
   void d2h(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
+  void d2d(void* d, const void* s, size_t n) { std::memmove(d, s, n); }
+  void rows_times_matrix(const double* in, double* out, int64_t R, int D, const double* mat) {
+    for (int64_t r = 0; r < R; ++r)
+      for (int j = 0; j < D; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k < D; ++k) acc = std::fma(in[r * D + k], mat[size_t(k) * D + j], acc);
+        out[r * D + j] = acc;
+      }
+  }
   void zero(void* d, size_t n) { std::memset(d, 0, n); }
   void sync() {}
   int32_t check(std::string&) { return 0; }
