@@ -176,47 +176,77 @@ struct NcclApi {
 
 // ------------------------------------------------------------------ deterministic gradients
 // G[c][d] = -sum_k P[d][k] Q[c][k], k strictly sequential per output so the result
-// is bit-identical to the oracle's scalar loop.  64x64 output tile, 4x4 per thread.
-template <class T>
-__global__ void __launch_bounds__(256) k_grad_gaussian(const T* __restrict__ P, const T* Q, T* G, int C, int D, int Dp) {
-  constexpr int TM = 64, TN = 64, TK = 16;
-  __shared__ T Ps[TK][TM + 1];
-  __shared__ T Qs[TK][TN + 1];
+// is bit-identical to the oracle's scalar loop (no split-K, explicit fma).  Register-tiled SIMT GEMM:
+// TM x TN output tile per CTA (d x chains), RM x RN outputs per thread, operands staged through shared
+// memory K-slab by K-slab with 16-byte loads along k.
+template <class T, int TM, int TN, int RM, int RN>
+__global__ void __launch_bounds__((TM / RM) * (TN / RN)) k_grad_gaussian(const T* __restrict__ P, const T* Q, T* G, int C, int D, int Dp) {
+  constexpr int TK = 16;
+  constexpr int NT = (TM / RM) * (TN / RN);
+  constexpr int VEC = 16 / sizeof(T);                 // elements per 16-byte load
+  __shared__ __align__(16) T Ps[TK][TM + 4];
+  __shared__ __align__(16) T Qs[TK][TN + 4];
   const int d0 = blockIdx.x * TM, c0 = blockIdx.y * TN;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  T acc[4][4];
+  const int tx = threadIdx.x % (TN / RN), ty = threadIdx.x / (TN / RN);
+  T acc[RM][RN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    for (int j = 0; j < RN; ++j) acc[i][j] = T(0);
+  const bool vec_ok = (D % VEC) == 0;                  // rows of P stay 16-byte aligned
   for (int k0 = 0; k0 < D; k0 += TK) {
-    for (int idx = threadIdx.x; idx < TM * TK; idx += 256) {
-      const int r = idx / TK, k = idx % TK;
-      const int d = d0 + r, kk = k0 + k;
-      Ps[k][r] = (d < D && kk < D) ? P[(int64_t)d * D + kk] : T(0);
+    // stage P[d0.., k0..] and Q[c0.., k0..] transposed ([k][row]); VEC consecutive k per load
+    for (int idx = threadIdx.x; idx < TM * (TK / VEC); idx += NT) {
+      const int r = idx / (TK / VEC), kv = (idx % (TK / VEC)) * VEC;
+      const int d = d0 + r;
+      T v[VEC];
+      if (vec_ok && d < D && k0 + kv + VEC <= D) {
+        *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(P + (int64_t)d * D + k0 + kv);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[e] = (d < D && k0 + kv + e < D) ? P[(int64_t)d * D + k0 + kv + e] : T(0);
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) Ps[kv + e][r] = v[e];
+    }
+    for (int idx = threadIdx.x; idx < TN * (TK / VEC); idx += NT) {
+      const int r = idx / (TK / VEC), kv = (idx % (TK / VEC)) * VEC;
       const int c = c0 + r;
-      Qs[k][r] = (c < C && kk < D) ? Q[(int64_t)c * Dp + kk] : T(0);
+      T v[VEC];
+      if (c < C && k0 + kv + VEC <= D) {               // Dp is a multiple of 32: rows of Q are aligned
+        *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(Q + (int64_t)c * Dp + k0 + kv);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[e] = (c < C && k0 + kv + e < D) ? Q[(int64_t)c * Dp + k0 + kv + e] : T(0);
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) Qs[kv + e][r] = v[e];
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
-      T a[4], b[4];
+      T a[RM], b[RN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = Ps[k][ty * 4 + i]; b[i] = Qs[k][tx * 4 + i]; }
+      for (int i = 0; i < RM; ++i) a[i] = Ps[k][ty * RM + i];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < RN; ++j) b[j] = Qs[k][tx * RN + j];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma_(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = fma_(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int j = 0; j < RN; ++j) {
+    const int c = c0 + tx * RN + j;
+    if (c >= C) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int d = d0 + ty * 4 + i, c = c0 + tx * 4 + j;
-      if (d < D && c < C) G[(int64_t)c * Dp + d] = -acc[i][j];
+    for (int i = 0; i < RM; ++i) {
+      const int d = d0 + ty * RM + i;
+      if (d < D) G[(int64_t)c * Dp + d] = -acc[i][j];
     }
+  }
 }
 
 // out[r][j] = sum_k in[r][k] mat[k][j] in Float64, k strictly sequential: the coordinate maps of the dense
@@ -432,8 +462,18 @@ struct CudaExec {
     using T = typename std::remove_reference<decltype(*M.zs)>::type;
     int nb = 1;
     if (eng.model.kind == MODEL_GAUSSIAN) {
-      dim3 grid((M.D + 63) / 64, (rows + 63) / 64);
-      k_grad_gaussian<T><<<grid, 256, 0, stream>>>(eng.model.P, M.stage_q, M.stage_g, rows, M.D, M.Dp);
+      // tile size by the number of active rows, so straggler steps (a few chains deep in their trees)
+      // still spread over many SMs; every variant keeps k sequential per output (bit-identical results)
+      if (sizeof(T) == 4 && rows > 1024) {
+        dim3 grid((M.D + 127) / 128, (rows + 127) / 128);
+        k_grad_gaussian<T, 128, 128, 8, 8><<<grid, 256, 0, stream>>>(eng.model.P, M.stage_q, M.stage_g, rows, M.D, M.Dp);
+      } else if (rows > 128) {
+        dim3 grid((M.D + 63) / 64, (rows + 63) / 64);
+        k_grad_gaussian<T, 64, 64, 4, 4><<<grid, 256, 0, stream>>>(eng.model.P, M.stage_q, M.stage_g, rows, M.D, M.Dp);
+      } else {
+        dim3 grid((M.D + 31) / 32, (rows + 15) / 16);
+        k_grad_gaussian<T, 32, 16, 2, 2><<<grid, 128, 0, stream>>>(eng.model.P, M.stage_q, M.stage_g, rows, M.D, M.Dp);
+      }
     } else if (eng.model.kind == MODEL_LOGISTIC) {
       if (eng.model.tensor) { tc.run(stream, rows); nb = tc.last_nsplit; }
       else {

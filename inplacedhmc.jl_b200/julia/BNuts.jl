@@ -107,7 +107,14 @@ function threaded_mcmc(ℓ, N; δ::Float64 = 0.8, initialization = (),
     try
         attach!(e, ℓ)
         init = NamedTuple(initialization)
-        haskey(init, :κ) && check(e, ccall((:bnuts_set_metric_diag, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, init.κ.M⁻¹))
+        if haskey(init, :κ)   # ≙ GaussianKineticEnergy: a D × nchains matrix of diagonals, or one dense D × D M⁻¹ (src/hamiltonian.jl:44)
+            Mi = init.κ.M⁻¹
+            if size(Mi) == (D, D) && nchains != D
+                check(e, ccall((:bnuts_set_metric_dense, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, Matrix{Float64}(Mi)))
+            else
+                check(e, ccall((:bnuts_set_metric_diag, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, Mi))
+            end
+        end
         q = haskey(init, :q) ? init.q : nothing                      # D × nchains
         check(e, ccall((:bnuts_set_positions, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, q === nothing ? C_NULL : q))
         foreach(s -> warmup!(e, s), warmup_stages)
@@ -123,6 +130,15 @@ function threaded_mcmc(ℓ, N; δ::Float64 = 0.8, initialization = (),
         ccall((:bnuts_destroy, libbnuts), Int32, (Ptr{Cvoid},), e)
     end
 end
+
+"""Row-sharded data (BASELINE config 5): call on every process after `attach!` with the 128-byte id that rank 0
+got from `nccl_unique_id()` and the host broadcast.  No reference counterpart (`src/mcmc.jl:150-157` has threads only)."""
+nccl_unique_id() = (id = zeros(UInt8, 128); ccall((:bnuts_nccl_unique_id, libbnuts), Int32, (Ptr{UInt8},), id) == 0 || error("NCCL not available"); id)
+join_row_shards!(e, id::Vector{UInt8}, world::Integer, rank::Integer) =
+    check(e, ccall((:bnuts_set_nccl, libbnuts), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), e, id, world, rank))
+"Reference point of the tensor-core logistic path (β₀ near the mode, e.g. the result of FindLocalOptimum)."
+set_reference!(e, β₀::Vector{Float64}) =
+    check(e, ccall((:bnuts_logistic_set_reference, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, β₀))
 
 "≙ mcmc_with_warmup(ℓ, N; ...), src/mcmc.jl:109-128 (one chain)."
 function mcmc_with_warmup(ℓ, N; kw...)

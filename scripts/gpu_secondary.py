@@ -9,7 +9,7 @@ import inplacedhmc_jl_b200 as bn
 from conftest import make_gaussian
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
-def run(name, C, D, dtype, setup, n_draws, stages=((75, 0), (25, 1), (50, 1), (100, 1), (50, 0)), delta=0.8, eps=None):
+def run(name, C, D, dtype, setup, n_draws, stages=((75, 0), (25, 1), (50, 1), (100, 1), (50, 0)), delta=0.8, eps=None, flops_per_leapfrog=0):
     e = bn.Engine(C, D, dtype=dtype, seed=11, gradient_path=bn.GRAD_DETERMINISTIC)
     setup(e); e.set_positions(None)
     t = time.perf_counter()
@@ -32,6 +32,8 @@ def run(name, C, D, dtype, setup, n_draws, stages=((75, 0), (25, 1), (50, 1), (1
            "divergences": c1["divergences"] - c0["divergences"], "lockstep_steps": c1["lockstep_steps"] - c0["lockstep_steps"],
            "hbm_alg_GBs": leap * 13 * D * sz / (ms * 1e-3) / 1e9, "hbm_peak_GBs": PEAK}
     rec["hbm_frac"] = rec["hbm_alg_GBs"] / PEAK
+    if flops_per_leapfrog:
+        rec["alg_TFLOPs"] = leap * flops_per_leapfrog / (ms * 1e-3) / 1e12
     print(json.dumps(rec), flush=True)
     e.close()
 
@@ -46,4 +48,9 @@ if __name__ == "__main__":
     if "gauss" in which:
         P, S = make_gaussian(1000)
         run("c2 dense Gaussian D=1000, diag metric, CUDA-core deterministic gradient", 4096, 1000, bn.F32, lambda e: e.model_gaussian(P), 5,
-            stages=((20, 0),))
+            stages=((20, 0),), flops_per_leapfrog=2 * 1000 * 1000)
+
+        def dense(e):
+            e.model_gaussian(P); e.set_metric_dense(S)     # c2: dense-metric GaussianKE, M⁻¹ = Σ injected
+        run("c2 dense Gaussian D=1000, shared dense metric M^-1 = Sigma (whitened: one GEMM per leapfrog)", 4096, 1000, bn.F32, dense, 20,
+            stages=((75, 0), (100, 0)), flops_per_leapfrog=2 * 1000 * 1000)
