@@ -170,21 +170,12 @@ def main():
     bits, y, beta = synth(N, D)
     e = bn.Engine(C, D, dtype=bn.F32, seed=20261018, chain_offset=rank * C, device=local, gradient_path=bn.GRAD_TENSOR)
     e.model_logistic(bits, y, 1.0)
-    # FindLocalOptimum (src/warmup.jl:152-186) is out of scope: start at the data-generating beta
-    rng = np.random.default_rng(100 + rank)
-    q0 = beta[None, :] + rng.normal(size=(C, D)) * 2e-3
-    e.set_positions(q0)
-    e.find_initial_stepsize()
-    # ≙ default_warmup_stages (src/warmup.jl:361-372) with shorter windows: step size only, then
-    # step size + per-chain diagonal metric in doubling windows, then step size only
+    # ≙ default_warmup_stages (src/warmup.jl:361-372): q0 ~ U[-2,2]^D (:73), FindLocalOptimum, InitialStepsizeSearch, ...
     t_w = time.perf_counter()
-    if a.adapt > 0:
-        for n, mk in ((a.adapt, bn.METRIC_NONE), (25, bn.METRIC_DIAG), (50, bn.METRIC_DIAG), (100, bn.METRIC_DIAG),
-                      (a.adapt, bn.METRIC_NONE)):
-            e.warmup_stage(n, mk, keep=False)
-    t_w = time.perf_counter() - t_w
-    # reference point of the tensor path (include/bnuts.h): the across-chain mean after warmup sits at the mode
-    # to within sd/sqrt(C); the engine checks it and keeps the exact three-term path if it is refused
+    e.set_positions(None)
+    e.find_local_optimum(1e-4, 50)
+    # reference point of the tensor path (include/bnuts.h) = the optimum just found (across-chain mean); the engine
+    # checks it and keeps the exact three-term path if it is refused
     terms = 3
     if not a.no_reference:
         try:
@@ -192,6 +183,14 @@ def main():
             terms = 2
         except bn.BnutsError as ex:
             print("reference point refused: %s" % ex, file=sys.stderr)
+    e.find_initial_stepsize()
+    # ≙ default_warmup_stages (src/warmup.jl:361-372) with shorter windows: step size only, then
+    # step size + per-chain diagonal metric in doubling windows, then step size only
+    if a.adapt > 0:
+        for n, mk in ((a.adapt, bn.METRIC_NONE), (25, bn.METRIC_DIAG), (50, bn.METRIC_DIAG), (100, bn.METRIC_DIAG),
+                      (a.adapt, bn.METRIC_NONE)):
+            e.warmup_stage(n, mk, keep=False)
+    t_w = time.perf_counter() - t_w
     T = a.transitions
     for _ in range(a.warmup):
         e.sample_device_only(T)
@@ -263,7 +262,7 @@ def main():
         "config": {"workload": "c3: Bayesian logistic regression N=%d D=%d, %d chains total, max_depth 10" % (N, D, C * world),
                    "chains_per_gpu": C, "parallelism": "chains sharded, no collective",
                    "l2": "inputs larger than L2 (X is %d MB bf16)" % (N * 128 * 2 // 2**20),
-                   "init": "beta* + 2e-3 N(0,1); untimed warmup: step size search, stages %d|25,50,100 (diag metric)|%d, %.1f s" % (a.adapt, a.adapt, t_w),
+                   "init": "q0 ~ U[-2,2]^D; untimed warmup: FindLocalOptimum(1e-4, 50), step size search, stages %d|25,50,100 (diag metric)|%d, %.1f s" % (a.adapt, a.adapt, t_w),
                    "step": "%d NUTS transitions of every chain (async within the call)" % T,
                    "position_operand_terms": terms,
                    "mean_tree_depth": float(stats["depth"].mean()), "mean_leapfrogs_per_transition": float(stats["steps"].mean()),

@@ -34,7 +34,8 @@ typedef enum {
   BNUTS_ERR_STEPSIZE_SEARCH = -5,  /* ≙ error(), src/stepsize.jl:71,101 */
   BNUTS_ERR_STEPSIZE_COLLAPSE = -6,/* ≙ AssertionError eps < 1e-10, src/warmup.jl:291-296 */
   BNUTS_ERR_UNSUPPORTED = -7,
-  BNUTS_ERR_INTERNAL = -8
+  BNUTS_ERR_INTERNAL = -8,
+  BNUTS_ERR_OPTIMUM = -9           /* ≙ ThrowOptimizationError, src/warmup.jl:151,172 */
 } bnuts_status;
 
 enum { BNUTS_F64 = 0, BNUTS_F32 = 1 };                 /* engine arithmetic type */
@@ -145,6 +146,14 @@ int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const dou
  * is not modified.  Outputs [C][D] / [C], any may be NULL. */
 int32_t bnuts_leapfrog(bnuts_engine* e, const double* p_in, const double* eps, int32_t nsteps,
                        double* q_out, double* p_out, double* grad_out, double* logdensity_out);
+
+/* ≙ warmup!(FindLocalOptimum(magnitude_penalty, iterations)) src/warmup.jl:137-186: every chain climbs
+ * ℓ(q) − ½·magnitude_penalty·‖q‖² from its current position for at most `iterations` accepted steps and keeps
+ * (q, ∇ℓ, ℓ) of the best point; a chain whose start (or result) is non-finite is re-randomised with a doubled
+ * penalty, up to 100 times, then reported through bnuts_chain_status / BNUTS_ERR_OPTIMUM.  The reference's
+ * inner solver is the un-vendored QuasiNewtonMethods.proptimize!; here: gradient ascent with a
+ * Barzilai-Borwein step and Armijo backtracking, batched over chains.  Defaults 1e-4, 50 (src/warmup.jl:143,148). */
+int32_t bnuts_find_local_optimum(bnuts_engine* e, double magnitude_penalty, int32_t iterations);
 
 /* ≙ warmup!(InitialStepsizeSearch) src/warmup.jl:188-200 + src/stepsize.jl:51-126,150-164 */
 int32_t bnuts_find_initial_stepsize(bnuts_engine* e, const bnuts_stepsize_search* params);

@@ -20,6 +20,7 @@ METRIC_NONE, METRIC_DIAG = 0, 1
 ERRORS = {
     -1: "invalid argument", -2: "no model", -3: "CUDA error", -4: "non-finite start",
     -5: "step size search failed", -6: "step size collapsed", -7: "unsupported", -8: "internal error",
+    -9: "local optimum search failed",
 }
 
 
@@ -55,7 +56,7 @@ EXPORTS = [
     "bnuts_create", "bnuts_destroy", "bnuts_last_error", "bnuts_model_iid_normal", "bnuts_model_funnel",
     "bnuts_model_gaussian", "bnuts_model_logistic", "bnuts_logistic_set_reference", "bnuts_set_positions", "bnuts_get_state",
     "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_set_metric_dense", "bnuts_get_metric_dense", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed",
-    "bnuts_inject", "bnuts_leapfrog", "bnuts_find_initial_stepsize", "bnuts_warmup_stage", "bnuts_sample",
+    "bnuts_inject", "bnuts_leapfrog", "bnuts_find_local_optimum", "bnuts_find_initial_stepsize", "bnuts_warmup_stage", "bnuts_sample",
     "bnuts_counters", "bnuts_profile", "bnuts_chain_status", "bnuts_set_allreduce", "bnuts_nccl_unique_id", "bnuts_set_nccl",
 ]
 
@@ -100,6 +101,7 @@ def load_library(path=None):
     lib.bnuts_seed.argtypes = [_P, C.c_uint64, C.c_uint32]
     lib.bnuts_inject.argtypes = [_P, C.c_int32, _P, _P]
     lib.bnuts_leapfrog.argtypes = [_P, _P, _P, C.c_int32, _P, _P, _P, _P]
+    lib.bnuts_find_local_optimum.argtypes = [_P, C.c_double, C.c_int32]
     lib.bnuts_find_initial_stepsize.argtypes = [_P, C.POINTER(StepsizeSearchParams)]
     lib.bnuts_warmup_stage.argtypes = [_P, C.c_int32, C.c_int32, C.POINTER(DualAveragingParams), C.c_double,
                                        _P, C.c_int64, C.c_int64, _P, C.c_int64, _P]
@@ -268,6 +270,10 @@ class Engine:
         l = np.empty(self.C)
         self._chk(self.lib.bnuts_leapfrog(self.h, _ptr(p), _ptr(eps), nsteps, _ptr(q), _ptr(po), _ptr(g), _ptr(l)))
         return q, po, g, l
+
+    def find_local_optimum(self, magnitude_penalty=1e-4, iterations=50):
+        """≙ warmup!(FindLocalOptimum), src/warmup.jl:152-186 (defaults :143,148)."""
+        self._chk(self.lib.bnuts_find_local_optimum(self.h, magnitude_penalty, iterations))
 
     def find_initial_stepsize(self, a_min=0.25, a_max=0.75, eps0=1.0, C_=2.0, maxiter_crossing=400,
                               maxiter_bisect=400, allow_fail=False):

@@ -94,8 +94,8 @@ class InitialStepsizeSearch:
 
 @dataclass
 class FindLocalOptimum:
-    """≙ src/warmup.jl:137-150.  The optimiser lives in QuasiNewtonMethods.proptimize!
-    (un-vendored); this stage is out of scope of the hot path and is a no-op here."""
+    """≙ src/warmup.jl:137-150 -> bnuts_find_local_optimum.  The reference's inner solver is the un-vendored
+    QuasiNewtonMethods.proptimize!; the engine climbs with a Barzilai-Borwein step (see include/bnuts.h)."""
     magnitude_penalty: float = 1e-4
     iterations: int = 50
 
@@ -146,9 +146,11 @@ def default_warmup_stages(local_optimization=FindLocalOptimum(), stepsize_search
 
 def _run_warmup(e, stages):
     for st in stages:
-        if st is None or isinstance(st, FindLocalOptimum):
+        if st is None:
             continue
-        if isinstance(st, InitialStepsizeSearch):
+        if isinstance(st, FindLocalOptimum):
+            e.find_local_optimum(st.magnitude_penalty, st.iterations)
+        elif isinstance(st, InitialStepsizeSearch):
             e.find_initial_stepsize(st.a_min, st.a_max, st.ϵ0, st.C, st.maxiter_crossing, st.maxiter_bisect)
         elif isinstance(st, TuningNUTS):
             da = st.stepsize_adaptation

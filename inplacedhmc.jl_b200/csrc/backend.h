@@ -350,6 +350,58 @@ template <class T, class LP> struct Backend {
     return l;
   }
 
+  // ---- local optimum search (≙ warmup!(FindLocalOptimum), src/warmup.jl:152-186; see nuts_machine.h)
+  BN_HD void opt_trial(int src, int dst, T alpha, T lambda) const {
+    const T* q = zq(src); const T* g = zg(src);
+    T* qn = zq(dst);
+    const int row = take_row();
+    for (int d = lp.first(); d < M.D; d += lp.stride()) {
+      const T dv = fma_(-lambda, q[d], g[d]);
+      const T qd = fma_(alpha, dv, q[d]);
+      qn[d] = qd;
+      if (row >= 0) stage_put(row, d, qd);
+    }
+    lp.sync();
+  }
+  BN_HD void opt_norms(int slot, T lambda, T* dd, T* qq) const {
+    const T* q = zq(slot); const T* g = zg(slot);
+    T a[LP::NACC], c2[LP::NACC];
+    for (int i = 0; i < LP::NACC; ++i) a[i] = c2[i] = T(0);
+    for (int d = lp.first(); d < M.D; d += lp.stride()) {
+      const T dv = fma_(-lambda, q[d], g[d]);
+      T& x = a[lp.acc(d)]; x = fma_(dv, dv, x);
+      T& y = c2[lp.acc(d)]; y = fma_(q[d], q[d], y);
+    }
+    *dd = lp.reduce(a);
+    *qq = lp.reduce(c2);
+  }
+  BN_HD void opt_dots(int src, int dst, T lambda, T* dd_new, T* qq_new, T* dod) const {
+    const T* q0 = zq(src); const T* g0 = zg(src);
+    const T* q1 = zq(dst); const T* g1 = zg(dst);
+    T a[LP::NACC], c2[LP::NACC], e[LP::NACC];
+    for (int i = 0; i < LP::NACC; ++i) a[i] = c2[i] = e[i] = T(0);
+    for (int d = lp.first(); d < M.D; d += lp.stride()) {
+      const T d0 = fma_(-lambda, q0[d], g0[d]);
+      const T d1 = fma_(-lambda, q1[d], g1[d]);
+      T& x = a[lp.acc(d)]; x = fma_(d1, d1, x);
+      T& y = c2[lp.acc(d)]; y = fma_(q1[d], q1[d], y);
+      T& z = e[lp.acc(d)]; z = fma_(d0, d1, z);
+    }
+    *dd_new = lp.reduce(a);
+    *qq_new = lp.reduce(c2);
+    *dod = lp.reduce(e);
+  }
+  BN_HD void opt_restart_position(int slot, uint64_t seed, uint32_t gchain, uint32_t attempt) const {
+    T* q = zq(slot);
+    const int row = take_row();
+    for (int d = lp.first(); d < M.D; d += lp.stride()) {
+      const T qd = T(restart_position(seed, gchain, attempt, (uint32_t)d));
+      q[d] = qd;
+      if (row >= 0) stage_put(row, d, qd);
+    }
+    lp.sync();
+  }
+
   // ≙ copyto!(chain[:, n], z.Q.q), src/warmup.jl:299,326
   BN_HD void emit_draw(int slot, int n) const {
     if (!M.draws) return;
@@ -386,7 +438,7 @@ template <class T, class LP> struct Backend {
 };
 
 // ------------------------------------------------------------------ per-chain entry points
-enum RunMode : int32_t { MODE_SAMPLE = 0, MODE_SEARCH = 1, MODE_BARE = 2, MODE_EVAL = 3 };
+enum RunMode : int32_t { MODE_SAMPLE = 0, MODE_SEARCH = 1, MODE_BARE = 2, MODE_EVAL = 3, MODE_OPT = 4 };
 
 struct PrepareArgs {
   int32_t mode;
@@ -419,6 +471,8 @@ BN_HD void prepare_chain(const EngineMem<T>& M, const RunParams<T>& rp, const Pr
     if (rp.da_on) da_init(s);
   } else if (a.mode == MODE_SEARCH) {
     s.phase = (s.status == 0) ? PH_SEARCH_START : PH_IDLE;
+  } else if (a.mode == MODE_OPT) {
+    s.phase = (s.status == 0 || s.status == ST_NONFINITE_START) ? PH_OPT_START : PH_IDLE;
   } else if (a.mode == MODE_BARE) {
     s.remaining = a.N;
     s.ss_try = a.bare_eps[c];

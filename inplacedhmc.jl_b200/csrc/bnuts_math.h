@@ -343,6 +343,11 @@ BN_HD uint32_t draw_directions(uint64_t seed, uint32_t chain, uint32_t t) {
   return draw4(seed, chain, t, PURPOSE_DIRS, 0).x;
 }
 // initial position coordinate ~ U[-2,2]  (src/warmup.jl:73)
+// ≙ random_position! on a restart of FindLocalOptimum (src/warmup.jl:169): attempt >= 1
+BN_HD double restart_position(uint64_t seed, uint32_t chain, uint32_t attempt, uint32_t d) {
+  const u32x4 w = draw4(seed, chain, 0xffffffffu - attempt, PURPOSE_INIT, d);
+  return fma_(u01_half(w.x, w.y, 0.0), 4.0, -2.0);
+}
 BN_HD double init_position(uint64_t seed, uint32_t chain, uint32_t d) {
   const u32x4 w = draw4(seed, chain, 0xffffffffu, PURPOSE_INIT, d);
   return fma_(u01_half(w.x, w.y, 0.0), 4.0, -2.0);

@@ -102,6 +102,9 @@ int32_t bnuts_leapfrog(bnuts_engine* e, const double* p_in, const double* eps, i
                        double* p_out, double* g_out, double* l_out) {
   BN_DISPATCH(e, leapfrog(p_in, eps, nsteps, q_out, p_out, g_out, l_out));
 }
+int32_t bnuts_find_local_optimum(bnuts_engine* e, double magnitude_penalty, int32_t iterations) {
+  BN_DISPATCH(e, find_local_optimum(magnitude_penalty, iterations));
+}
 int32_t bnuts_find_initial_stepsize(bnuts_engine* e, const bnuts_stepsize_search* P) {
   if (!P) return BNUTS_ERR_INVALID_ARGUMENT;
   BN_DISPATCH(e, find_initial_stepsize(*P));

@@ -599,6 +599,20 @@ template <class T, class X> struct EngineCore {
       return fail(BNUTS_ERR_STEPSIZE_SEARCH, "initial step size search failed for some chains");
     return 0;
   }
+  // ≙ warmup!(FindLocalOptimum), src/warmup.jl:152-186
+  int32_t find_local_optimum(double magnitude_penalty, int32_t iterations) {
+    if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
+    if (!(magnitude_penalty >= 0.0) || iterations < 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad FindLocalOptimum parameters");
+    rp.opt.penalty = magnitude_penalty; rp.opt.iterations = iterations;
+    rp.da_on = 0;
+    PrepareArgs a{}; a.mode = MODE_OPT;
+    x.prepare(M, rp, a);
+    int32_t rc = run(false);
+    if (rc) return rc;
+    if (x.any_status(M, ST_OPTIMUM_FAILED))
+      return fail(BNUTS_ERR_OPTIMUM, "optimization failed to converge for some chains (100 restarts)");
+    return 0;
+  }
   int32_t get_counters(bnuts_counter_block* out) {
     int64_t tot[3];
     x.totals(M, tot);

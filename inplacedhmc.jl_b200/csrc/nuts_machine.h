@@ -39,11 +39,14 @@ enum Phase : int32_t {
   PH_SEARCH_LEAF = 5,
   PH_BARE_START = 6,    // bare integrator (bnuts_leapfrog)
   PH_BARE_LEAF = 7,
-  PH_EVAL_LEAF = 8      // set_positions: gradient of slot_cur pending
+  PH_EVAL_LEAF = 8,     // set_positions: gradient of slot_cur pending
+  PH_OPT_START = 9,     // FindLocalOptimum: begin the ascent from slot_cur
+  PH_OPT_LEAF = 10,     // gradient of the trial point pending
+  PH_OPT_REEVAL = 11    // gradient of a re-randomised start pending
 };
 
 // error codes mirrored from include/bnuts.h (kept numerically identical)
-constexpr int32_t ST_NONFINITE_START = -4, ST_STEPSIZE_SEARCH = -5, ST_STEPSIZE_COLLAPSE = -6;
+constexpr int32_t ST_NONFINITE_START = -4, ST_STEPSIZE_SEARCH = -5, ST_STEPSIZE_COLLAPSE = -6, ST_OPTIMUM_FAILED = -9;
 
 struct TreeStats {  // ≙ TreeStatisticsNUTS, src/NUTS.jl:229-242 (32 bytes)
   double pi, acceptance_rate;
@@ -77,6 +80,9 @@ template <class T> struct ChainState {
   T ss_target;
   int32_t ss_stage, ss_iter;
   int32_t bare_src;  // slot to restore after the bare integrator
+  // ---- local optimum search (≙ warmup!(FindLocalOptimum), src/warmup.jl:152-186)
+  double opt_alpha, opt_f, opt_dd, opt_lambda;
+  int32_t opt_iter, opt_bt, opt_tries, opt_pad;
   // ---- subtree stack (one entry per pending left sibling)
   T st_omega[MAX_LEVELS], st_pi[MAX_LEVELS], st_vlsa[MAX_LEVELS];
   int32_t st_first_i[MAX_LEVELS], st_slot[MAX_LEVELS], st_izeta[MAX_LEVELS];
@@ -84,6 +90,7 @@ template <class T> struct ChainState {
 
 struct DualAveragingP { double delta, gamma, kappa; int32_t t0; };
 struct SearchP { double a_min, a_max, eps0, C; int32_t maxiter_crossing, maxiter_bisect; };
+struct OptP { double penalty; int32_t iterations; int32_t pad; };   // ≙ FindLocalOptimum, src/warmup.jl:137-150
 
 template <class T> struct RunParams {
   int32_t max_depth;
@@ -95,6 +102,7 @@ template <class T> struct RunParams {
   int32_t da_on;
   DualAveragingP da;
   SearchP search;
+  OptP opt;
   // injection (≙ p = / directions = of sample_tree, src/NUTS.jl:251-258)
   int32_t inj_T;
   uint32_t inj_start;
@@ -137,6 +145,10 @@ template <class T> BN_HD void da_adapt(ChainState<T>& s, const DualAveragingP& P
 //   T    model_grad(slot)            // elementwise models: evaluate now; GEMM models: finalize staged result
 //   void emit_draw(slot, n_done)     // copy q out as Float64
 //   void bare_load_p(slot); void bare_emit(slot);
+//   void opt_trial(src, dst, T alpha, T lambda)   q_dst = q + alpha (∇ℓ − λ q), staged for its gradient
+//   void opt_norms(slot, T lambda, T* dd, T* qq)   |∇ℓ − λq|², |q|²
+//   void opt_dots(src, dst, T lambda, T* dd_new, T* qq_new, T* dod)   also d_old·d_new
+//   void opt_restart_position(slot, seed, gchain, attempt)
 template <class T, class B> struct Machine {
   B& b;
   ChainState<T>& s;        // register/working copy of the scalars
@@ -401,6 +413,76 @@ template <class T, class B> struct Machine {
     search_pre();
   }
 
+  // ---------------------------------------------------------------- local optimum
+  // ≙ warmup!(FindLocalOptimum), src/warmup.jl:152-186: maximise ℓ(q) − ½λ‖q‖² for at most `iterations`
+  // steps ("we don't need to find the mode, just be in a reasonable region", :146-147); a non-finite result
+  // re-randomises q and doubles λ, up to 100 times (:162-172).  The reference delegates the inner solver to
+  // QuasiNewtonMethods.proptimize! (un-vendored, unpinned); here it is gradient ascent with a
+  // Barzilai-Borwein step and Armijo backtracking, one gradient request per trial point, so thousands of
+  // chains search in lockstep through the same batched gradient kernels as the sampler.
+  BN_HD void opt_start() {
+    s.opt_lambda = rp.opt.penalty; s.opt_iter = 0; s.opt_tries = 0;
+    s.status = 0;
+    opt_begin();
+  }
+  BN_HD void opt_begin() {
+    s.slot_minus = s.slot_plus = s.slot_zeta = s.slot_cur; s.sp = 0;
+    const T lq = b.get_lq(s.slot_cur);
+    if (!isfinite_(lq)) { opt_restart(); return; }
+    T dd, qq;
+    b.opt_norms(s.slot_cur, T(s.opt_lambda), &dd, &qq);
+    s.opt_f = (double)lq - 0.5 * s.opt_lambda * (double)qq;
+    s.opt_dd = (double)dd;
+    s.opt_alpha = 1.0 / (1.0 + sqrt_(s.opt_dd));       // first step no longer than 1
+    s.opt_bt = 0;
+    if (s.opt_iter >= rp.opt.iterations || !(s.opt_dd > 0.0)) { opt_done(); return; }
+    opt_pre();
+  }
+  BN_HD void opt_restart() {   // ≙ src/warmup.jl:168-170
+    s.opt_tries += 1;
+    if (s.opt_tries > 100) { s.status = ST_OPTIMUM_FAILED; s.phase = PH_IDLE; return; }
+    s.opt_lambda += s.opt_lambda;
+    b.opt_restart_position(s.slot_cur, rp.seed, gchain(), (uint32_t)s.opt_tries);
+    s.phase = PH_OPT_REEVAL;
+  }
+  BN_HD void opt_reeval_post() {
+    T lq = b.model_grad(s.slot_cur);
+    if (!isfinite_(lq)) lq = -lim<T>::inf();
+    b.set_lq(s.slot_cur, lq);
+    s.opt_iter = 0;
+    opt_begin();
+  }
+  BN_HD void opt_pre() {
+    s.slot_new = alloc_slot();
+    b.opt_trial(s.slot_cur, s.slot_new, T(s.opt_alpha), T(s.opt_lambda));
+    s.phase = PH_OPT_LEAF;
+  }
+  BN_HD void opt_done() {
+    s.slot_minus = s.slot_plus = s.slot_zeta = s.slot_cur; s.sp = 0;
+    s.phase = PH_IDLE;
+  }
+  BN_HD void opt_post() {
+    T lq = b.model_grad(s.slot_new);
+    if (!isfinite_(lq)) lq = -lim<T>::inf();
+    b.set_lq(s.slot_new, lq);
+    T ddn, qqn, dod;
+    b.opt_dots(s.slot_cur, s.slot_new, T(s.opt_lambda), &ddn, &qqn, &dod);
+    const double fn = isfinite_(lq) ? (double)lq - 0.5 * s.opt_lambda * (double)qqn : -lim<double>::inf();
+    const bool accept = fn >= s.opt_f + 1e-4 * s.opt_alpha * s.opt_dd;   // Armijo; false for -Inf / NaN
+    if (accept) {
+      const double curv = s.opt_dd - (double)dod;      // -(s·y)/alpha with s = alpha d, y = d' - d
+      double an = curv > 0.0 ? s.opt_alpha * s.opt_dd / curv : 2.0 * s.opt_alpha;   // Barzilai-Borwein
+      an = an < 1e-12 ? 1e-12 : (an > 1e12 ? 1e12 : an);
+      s.slot_cur = s.slot_new; s.opt_f = fn; s.opt_dd = (double)ddn; s.opt_alpha = an;
+      s.opt_iter += 1; s.opt_bt = 0;
+      if (s.opt_iter >= rp.opt.iterations || !((double)ddn > 1e-20 * (1.0 + fn * fn))) { opt_done(); return; }
+    } else {
+      s.opt_alpha *= 0.25; s.opt_bt += 1;
+      if (s.opt_bt > 40) { opt_done(); return; }
+    }
+    opt_pre();
+  }
+
   // ---------------------------------------------------------------- bare integrator
   // ≙ stack leapfrog, src/kinetic_energy.jl:164-195 (engine state is restored)
   BN_HD void bare_start() {
@@ -451,13 +533,17 @@ template <class T, class B> struct Machine {
       case PH_SEARCH_LEAF: search_post(); break;
       case PH_BARE_LEAF: bare_post(); break;
       case PH_EVAL_LEAF: eval_post(); break;
+      case PH_OPT_LEAF: opt_post(); break;
+      case PH_OPT_REEVAL: opt_reeval_post(); break;
       default: break;
     }
     if (s.phase == PH_START) start_transition();
     else if (s.phase == PH_SEARCH_START) search_start();
     else if (s.phase == PH_BARE_START) bare_start();
+    else if (s.phase == PH_OPT_START) opt_start();
     if (s.phase == PH_NEXT) pre();
-    return s.phase == PH_LEAF || s.phase == PH_SEARCH_LEAF || s.phase == PH_BARE_LEAF || s.phase == PH_EVAL_LEAF;
+    return s.phase == PH_LEAF || s.phase == PH_SEARCH_LEAF || s.phase == PH_BARE_LEAF || s.phase == PH_EVAL_LEAF ||
+           s.phase == PH_OPT_LEAF || s.phase == PH_OPT_REEVAL;
   }
 };
 

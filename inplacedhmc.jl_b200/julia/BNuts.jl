@@ -43,7 +43,7 @@ Base.@kwdef struct InitialStepsizeSearch                                        
     a_min::Float64 = 0.25; a_max::Float64 = 0.75; ϵ₀::Float64 = 1.0; C::Float64 = 2.0
     maxiter_crossing::Int = 400; maxiter_bisect::Int = 400
 end
-Base.@kwdef struct FindLocalOptimum; magnitude_penalty::Float64 = 1e-4; iterations::Int = 50; end # out of scope: no-op
+Base.@kwdef struct FindLocalOptimum; magnitude_penalty::Float64 = 1e-4; iterations::Int = 50; end # src/warmup.jl:137-150
 struct TuningNUTS{M}                                                                               # src/warmup.jl:217-234
     N::Int; stepsize_adaptation::DualAveraging; λ::Float64
 end
@@ -78,7 +78,9 @@ attach!(e, ℓ::GaussianTarget) = check(e, ccall((:bnuts_model_gaussian, libbnut
 attach!(e, ℓ::LogisticTarget) = check(e, ccall((:bnuts_model_logistic, libbnuts), Int32,
     (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Float64, Int32), e, ℓ.X, 1, ℓ.y, length(ℓ.y), ℓ.prior_precision, 1))
 
-warmup!(e, ::Union{Nothing,FindLocalOptimum}) = nothing
+warmup!(e, ::Nothing) = nothing
+warmup!(e, s::FindLocalOptimum) =                                                                 # ≙ src/warmup.jl:152-186
+    check(e, ccall((:bnuts_find_local_optimum, libbnuts), Int32, (Ptr{Cvoid}, Float64, Int32), e, s.magnitude_penalty, s.iterations))
 function warmup!(e, s::InitialStepsizeSearch)                                                     # ≙ src/warmup.jl:188-200
     p = Ref(bnuts_stepsize_search(s.a_min, s.a_max, s.ϵ₀, s.C, s.maxiter_crossing, s.maxiter_bisect))
     check(e, ccall((:bnuts_find_initial_stepsize, libbnuts), Int32, (Ptr{Cvoid}, Ref{bnuts_stepsize_search}), e, p))

@@ -642,6 +642,75 @@ template <class T> int32_t initial_stepsize(Engine<T>& E, const bnuts_stepsize_s
   return 0;
 }
 
+// ≙ warmup!(FindLocalOptimum), src/warmup.jl:152-186.  The inner solver of the reference
+// (QuasiNewtonMethods.proptimize!) is un-vendored and unpinned; the ascent below (Barzilai-Borwein step,
+// Armijo backtracking, restart with a doubled penalty on a non-finite start) is this project's choice and is
+// restated independently of the device state machine (nuts_machine.h) so the two can be compared bit for bit.
+template <class T> int32_t find_local_optimum(Engine<T>& E, double penalty, int32_t iterations) {
+  if (E.model.kind == bn::MODEL_NONE) return fail(E, BNUTS_ERR_NO_MODEL, "no model set");
+  if (!(penalty >= 0.0) || iterations < 0) return fail(E, BNUTS_ERR_INVALID_ARGUMENT, "bad FindLocalOptimum parameters");
+  ensure_ctx(E);
+  const int C = E.C, D = E.D;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic) reduction(+ : bad)
+  for (int c = 0; c < C; ++c) {
+    ChainCtx<T>& X = E.ctx[omp_get_thread_num()];
+    Ham<T> H{&E, c};
+    const uint32_t gchain = uint32_t(E.cfg.chain_offset + c);
+    std::vector<T> q(&E.q[size_t(c) * D], &E.q[size_t(c) * D] + D), g(&E.g[size_t(c) * D], &E.g[size_t(c) * D] + D);
+    std::vector<T> qn(D), gn(D), dv(D), dn(D);
+    T lq = E.lq[c];
+    double lambda = penalty;
+    int tries = 0, iter = 0;
+    bool failed = false;
+    E.status[c] = 0;
+    for (;;) {   // (re)start
+      if (!isfinite_(lq)) {
+        tries += 1;
+        if (tries > 100) { failed = true; break; }
+        lambda += lambda;
+        for (int d = 0; d < D; ++d) q[d] = T(bn::restart_position(E.seed, gchain, uint32_t(tries), uint32_t(d)));
+        lq = evaluate_l(X, H, q.data(), g.data());
+        iter = 0;
+        continue;
+      }
+      const T lam = T(lambda);
+      for (int d = 0; d < D; ++d) dv[d] = fma_(-lam, q[d], g[d]);
+      double dd = double(dot_warp(dv.data(), dv.data(), D));
+      double f = double(lq) - 0.5 * lambda * double(dot_warp(q.data(), q.data(), D));
+      double alpha = 1.0 / (1.0 + bn::sqrt_(dd));
+      int bt = 0;
+      while (iter < iterations && dd > 0.0) {
+        const T al = T(alpha);
+        for (int d = 0; d < D; ++d) qn[d] = fma_(al, dv[d], q[d]);
+        T lqn = evaluate_l(X, H, qn.data(), gn.data());
+        for (int d = 0; d < D; ++d) dn[d] = fma_(-lam, qn[d], gn[d]);
+        const T ddn = dot_warp(dn.data(), dn.data(), D);
+        const T qqn = dot_warp(qn.data(), qn.data(), D);
+        const T dod = dot_warp(dv.data(), dn.data(), D);
+        const double fn = isfinite_(lqn) ? double(lqn) - 0.5 * lambda * double(qqn) : -bn::lim<double>::inf();
+        if (fn >= f + 1e-4 * alpha * dd) {
+          const double curv = dd - double(dod);
+          double an = curv > 0.0 ? alpha * dd / curv : 2.0 * alpha;
+          an = an < 1e-12 ? 1e-12 : (an > 1e12 ? 1e12 : an);
+          q.swap(qn); g.swap(gn); dv.swap(dn); lq = lqn;
+          f = fn; dd = double(ddn); alpha = an; iter += 1; bt = 0;
+          if (!(dd > 1e-20 * (1.0 + fn * fn))) break;
+        } else {
+          alpha *= 0.25; bt += 1;
+          if (bt > 40) break;
+        }
+      }
+      break;
+    }
+    if (failed) { E.status[c] = BNUTS_ERR_OPTIMUM; bad += 1; continue; }
+    for (int d = 0; d < D; ++d) { E.q[size_t(c) * D + d] = q[d]; E.g[size_t(c) * D + d] = g[d]; }
+    E.lq[c] = lq;
+  }
+  if (bad) return fail(E, BNUTS_ERR_OPTIMUM, "optimization failed to converge for some chains (100 restarts)");
+  return 0;
+}
+
 template <class T>
 int32_t bare_leapfrog(Engine<T>& E, const double* p_in, const double* eps, int nsteps, double* q_out, double* p_out,
                       double* g_out, double* l_out) {
@@ -847,6 +916,9 @@ int32_t bnuts_leapfrog(bnuts_engine* e, const double* p_in, const double* eps, i
                        double* p_out, double* g_out, double* l_out) {
   DISPATCH(e, bare_leapfrog(E, p_in, eps, nsteps, q_out, p_out, g_out, l_out),
            bare_leapfrog(E, p_in, eps, nsteps, q_out, p_out, g_out, l_out));
+}
+int32_t bnuts_find_local_optimum(bnuts_engine* e, double penalty, int32_t iterations) {
+  DISPATCH(e, find_local_optimum(E, penalty, iterations), find_local_optimum(E, penalty, iterations));
 }
 int32_t bnuts_find_initial_stepsize(bnuts_engine* e, const bnuts_stepsize_search* P) {
   if (!P) return BNUTS_ERR_INVALID_ARGUMENT;
