@@ -3,10 +3,11 @@
 //
 // One backend instance is bound to one chain.  All loops are written once over a
 // "lane policy" LP:
-//   device  (WarpLanes): lane l of the chain's warp handles d = l, l+32, ...;
+//   device  (WarpLanes): lane l of the chain's warp handles the groups of four consecutive
+//            elements d = 4l..4l+3 (+128, +256, ...) with 16/32-byte loads and stores;
 //            reductions finish with a xor-butterfly of warp shuffles
 //   tests   (SerialLanes): one host thread walks d = 0..D-1 and keeps 32 partial
-//            accumulators indexed by d & 31, then emulates the same butterfly
+//            accumulators indexed by (d >> 2) & 31, then emulates the same butterfly
 // so both produce bit-identical sums (the "warp order" of bnuts_models.h).
 //
 // Layout (T = engine arithmetic type, Dp = D rounded up to 32, chain-major so a
@@ -70,7 +71,9 @@ struct SerialLanes {
   static constexpr int NACC = 32;
   BN_HD int first() const { return 0; }
   BN_HD int stride() const { return 1; }
-  BN_HD int acc(int d) const { return d & 31; }
+  BN_HD int first4() const { return 0; }
+  BN_HD int stride4() const { return 4; }
+  BN_HD int acc(int d) const { return (d >> 2) & 31; }
   BN_HD bool lane0() const { return true; }
   BN_HD void sync() const {}
   BN_HD int alloc_row(unsigned long long* counter) const {
@@ -95,6 +98,8 @@ struct WarpLanes {
   int lane;
   BN_HD int first() const { return lane; }
   BN_HD int stride() const { return 32; }
+  BN_HD int first4() const { return 4 * lane; }
+  BN_HD int stride4() const { return 128; }
   BN_HD int acc(int) const { return 0; }
   BN_HD bool lane0() const { return lane == 0; }
   BN_HD void sync() const {
@@ -119,6 +124,39 @@ struct WarpLanes {
   }
 };
 #endif
+
+// Groups of four consecutive elements.  Every D-vector of the engine is padded to Dp (a multiple of 32) and
+// starts 128-byte aligned, so a whole group can always be LOADED (elements >= D are padding and are never
+// used); stores of a partial last group fall back to scalar stores of the valid elements.
+template <class T> BN_HD void ld4(const T* p, T (&v)[4]) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (sizeof(T) == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+#else
+  for (int e = 0; e < 4; ++e) v[e] = p[e];
+#endif
+}
+template <class T> BN_HD void st4(T* p, const T (&v)[4], int nv) {
+#if defined(__CUDA_ARCH__)
+  if (nv == 4) {
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+      *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+    }
+    return;
+  }
+#endif
+  for (int e = 0; e < nv; ++e) p[e] = v[e];
+}
+#define BN_FOR4(d0, nv) \
+  for (int d0 = lp.first4(), nv = (M.D - d0 < 4 ? M.D - d0 : 4); d0 < M.D; d0 += lp.stride4(), nv = (M.D - d0 < 4 ? M.D - d0 : 4))
 
 template <class T, class LP> struct Backend {
   const EngineMem<T>& M;
@@ -153,12 +191,20 @@ template <class T, class LP> struct Backend {
     T* ps = cv(M.ps_cur); T* mr = cv(M.m_rho); T* mm = cv(M.m_psm); T* mp = cv(M.m_psp);
     T part[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) part[i] = T(0);
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T pd = inj_p ? T(inj_p[d]) : W[d] * std_normal(seed, gchain, t, (uint32_t)d, T(0));
-      const T psd = Mi[d] * pd;
-      p[d] = pd; ps[d] = psd; mr[d] = pd; mm[d] = psd; mp[d] = psd;
-      T& a = part[lp.acc(d)];
-      a = fma_(psd, pd, a);
+    BN_FOR4(d0, nv) {
+      T w[4], mi[4], pv[4], sv[4];
+      ld4(W + d0, w); ld4(Mi + d0, mi);
+      for (int e = 0; e < 4; ++e) {
+        const int d = d0 + e;
+        pv[e] = T(0); sv[e] = T(0);
+        if (e < nv) {
+          pv[e] = inj_p ? T(inj_p[d]) : w[e] * std_normal(seed, gchain, t, (uint32_t)d, T(0));
+          sv[e] = mi[e] * pv[e];
+          T& a = part[lp.acc(d)];
+          a = fma_(sv[e], pv[e], a);
+        }
+      }
+      st4(p + d0, pv, nv); st4(ps + d0, sv, nv); st4(mr + d0, pv, nv); st4(mm + d0, sv, nv); st4(mp + d0, sv, nv);
     }
     *Ksum = lp.reduce(part);
     lp.sync();
@@ -177,15 +223,27 @@ template <class T, class LP> struct Backend {
   }
   // publish one coordinate of the position to evaluate; the tensor path also gets the
   // exact three-term bf16 split of the fp32 value (3 x 8 mantissa bits)
-  BN_HD void stage_put(int row, int d, T qd) const {
-    M.stage_q[(int64_t)row * M.Dp + d] = qd;
+  BN_HD void stage_put4(int row, int d0, const T (&qv)[4], int nv) const {
+    st4(M.stage_q + (int64_t)row * M.Dp + d0, qv, nv);
     if (M.stage_bh) {
-      const float qf = (float)qd - (M.beta_ref ? (float)M.beta_ref[d] : 0.f);
-      const uint16_t h = bf16_bits(qf);
-      const float r1 = qf - bf16_val(h);
-      const uint16_t m = bf16_bits(r1);
-      const int64_t o = (int64_t)row * M.Dt + d;
-      M.stage_bh[o] = h; M.stage_bm[o] = m; M.stage_bl[o] = bf16_bits(r1 - bf16_val(m));
+      T br[4] = {T(0), T(0), T(0), T(0)};
+      if (M.beta_ref) ld4(M.beta_ref + d0, br);
+      uint16_t h[4], m[4], l[4];
+      for (int e = 0; e < 4; ++e) {
+        const float qf = (float)qv[e] - (float)br[e];
+        h[e] = bf16_bits(qf);
+        const float r1 = qf - bf16_val(h[e]);
+        m[e] = bf16_bits(r1);
+        l[e] = bf16_bits(r1 - bf16_val(m[e]));
+      }
+      const int64_t o = (int64_t)row * M.Dt + d0;
+      if (nv == 4) {   // 8-byte stores (Dt is a multiple of 64, d0 of 4)
+        *reinterpret_cast<uint64_t*>(M.stage_bh + o) = (uint64_t)h[0] | ((uint64_t)h[1] << 16) | ((uint64_t)h[2] << 32) | ((uint64_t)h[3] << 48);
+        *reinterpret_cast<uint64_t*>(M.stage_bm + o) = (uint64_t)m[0] | ((uint64_t)m[1] << 16) | ((uint64_t)m[2] << 32) | ((uint64_t)m[3] << 48);
+        *reinterpret_cast<uint64_t*>(M.stage_bl + o) = (uint64_t)l[0] | ((uint64_t)l[1] << 16) | ((uint64_t)l[2] << 32) | ((uint64_t)l[3] << 48);
+      } else {
+        for (int e = 0; e < nv; ++e) { M.stage_bh[o + e] = h[e]; M.stage_bm[o + e] = m[e]; M.stage_bl[o + e] = l[e]; }
+      }
     }
   }
 
@@ -195,11 +253,15 @@ template <class T, class LP> struct Backend {
     T* qn = zq(dst); T* pn = zp(dst);
     const T* Mi = cv(M.Minv);
     const int row = take_row();
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T pm = fma_(eh, g[d], p[d]);
-      const T qd = fma_(eps * Mi[d], pm, q[d]);
-      pn[d] = pm; qn[d] = qd;
-      if (row >= 0) stage_put(row, d, qd);
+    BN_FOR4(d0, nv) {
+      T qv[4], pv[4], gv[4], mi[4], pm[4], qd[4];
+      ld4(q + d0, qv); ld4(p + d0, pv); ld4(g + d0, gv); ld4(Mi + d0, mi);
+      for (int e = 0; e < 4; ++e) {
+        pm[e] = fma_(eh, gv[e], pv[e]);
+        qd[e] = fma_(eps * mi[e], pm[e], qv[e]);
+      }
+      st4(pn + d0, pm, nv); st4(qn + d0, qd, nv);
+      if (row >= 0) stage_put4(row, d0, qd, nv);
     }
     lp.sync();
   }
@@ -214,13 +276,16 @@ template <class T, class LP> struct Backend {
     T* pf = push_level >= 0 ? stpsf(push_level) : nullptr;
     T part[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) part[i] = T(0);
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T pd = fma_(eh, g[d], p[d]);
-      const T psd = Mi[d] * pd;
-      p[d] = pd; ps[d] = psd;
-      if (pr) { pr[d] = pd; pf[d] = psd; }
-      T& a = part[lp.acc(d)];
-      a = fma_(psd, pd, a);
+    BN_FOR4(d0, nv) {
+      T pv[4], gv[4], mi[4], pd[4], sd[4];
+      ld4(p + d0, pv); ld4(g + d0, gv); ld4(Mi + d0, mi);
+      for (int e = 0; e < 4; ++e) {
+        pd[e] = fma_(eh, gv[e], pv[e]);
+        sd[e] = mi[e] * pd[e];
+        if (e < nv) { T& a = part[lp.acc(d0 + e)]; a = fma_(sd[e], pd[e], a); }
+      }
+      st4(p + d0, pd, nv); st4(ps + d0, sd, nv);
+      if (pr) { st4(pr + d0, pd, nv); st4(pf + d0, sd, nv); }
     }
     const T r = lp.reduce(part);
     lp.sync();
@@ -237,11 +302,17 @@ template <class T, class LP> struct Backend {
     const T* psp = fwd ? pc : pf;
     T am[LP::NACC], ap[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) am[i] = ap[i] = T(0);
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T r = fwd ? rl[d] + rr[d] : rr[d] + rl[d];
-      rl[d] = r;
-      T& a = am[lp.acc(d)]; a = fma_(r, psm[d], a);
-      T& b2 = ap[lp.acc(d)]; b2 = fma_(r, psp[d], b2);
+    BN_FOR4(d0, nv) {
+      T a4[4], b4[4], m4[4], p4[4], r4[4];
+      ld4(rl + d0, a4); ld4(rr + d0, b4); ld4(psm + d0, m4); ld4(psp + d0, p4);
+      for (int e = 0; e < 4; ++e) {
+        r4[e] = fwd ? a4[e] + b4[e] : b4[e] + a4[e];
+        if (e < nv) {
+          T& a = am[lp.acc(d0 + e)]; a = fma_(r4[e], m4[e], a);
+          T& b2 = ap[lp.acc(d0 + e)]; b2 = fma_(r4[e], p4[e], b2);
+        }
+      }
+      st4(rl + d0, r4, nv);
     }
     *dm = lp.reduce(am);
     *dp = lp.reduce(ap);
@@ -256,15 +327,20 @@ template <class T, class LP> struct Backend {
     const T* pc = cv(M.ps_cur);
     T am[LP::NACC], ap[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) am[i] = ap[i] = T(0);
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T r = fwd ? mr[d] + rr[d] : rr[d] + mr[d];
-      mr[d] = r;
-      const T pcd = pc[d];
-      const T psm = fwd ? mm[d] : pcd;
-      const T psp = fwd ? pcd : mp[d];
-      if (fwd) mp[d] = pcd; else mm[d] = pcd;
-      T& a = am[lp.acc(d)]; a = fma_(r, psm, a);
-      T& b2 = ap[lp.acc(d)]; b2 = fma_(r, psp, b2);
+    BN_FOR4(d0, nv) {
+      T a4[4], b4[4], c4[4], o4[4], r4[4];
+      ld4(mr + d0, a4); ld4(rr + d0, b4); ld4(pc + d0, c4); ld4((fwd ? mm : mp) + d0, o4);
+      for (int e = 0; e < 4; ++e) {
+        r4[e] = fwd ? a4[e] + b4[e] : b4[e] + a4[e];
+        const T psm = fwd ? o4[e] : c4[e];
+        const T psp = fwd ? c4[e] : o4[e];
+        if (e < nv) {
+          T& a = am[lp.acc(d0 + e)]; a = fma_(r4[e], psm, a);
+          T& b2 = ap[lp.acc(d0 + e)]; b2 = fma_(r4[e], psp, b2);
+        }
+      }
+      st4(mr + d0, r4, nv);
+      st4((fwd ? mp : mm) + d0, c4, nv);
     }
     *dm = lp.reduce(am);
     *dp = lp.reduce(ap);
@@ -275,9 +351,10 @@ template <class T, class LP> struct Backend {
   BN_HD T dot(const T* a, const T* b) const {
     T part[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) part[i] = T(0);
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      T& x = part[lp.acc(d)];
-      x = fma_(a[d], b[d], x);
+    BN_FOR4(d0, nv) {
+      T a4[4], b4[4];
+      ld4(a + d0, a4); ld4(b + d0, b4);
+      for (int e = 0; e < nv; ++e) { T& x = part[lp.acc(d0 + e)]; x = fma_(a4[e], b4[e], x); }
     }
     return lp.reduce(part);
   }
@@ -291,26 +368,42 @@ template <class T, class LP> struct Backend {
     T l;
     switch (M.model_kind) {
       case MODEL_IID_NORMAL: {
-        for (int d = lp.first(); d < M.D; d += lp.stride()) g[d] = iid_grad(q[d]);
+        BN_FOR4(d0, nv) {
+          T qv[4], gv[4];
+          ld4(q + d0, qv);
+          for (int e = 0; e < 4; ++e) gv[e] = iid_grad(qv[e]);
+          st4(g + d0, gv, nv);
+        }
         l = iid_value(dot(q, q));
         break;
       }
       case MODEL_FUNNEL: {
         T part[LP::NACC];
         for (int i = 0; i < LP::NACC; ++i) part[i] = T(0);
-        for (int d = lp.first(); d < M.D; d += lp.stride()) {
-          if (d >= 1) { T& x = part[lp.acc(d)]; x = fma_(q[d], q[d], x); }
+        BN_FOR4(d0, nv) {
+          T qv[4];
+          ld4(q + d0, qv);
+          for (int e = 0; e < nv; ++e)
+            if (d0 + e >= 1) { T& x = part[lp.acc(d0 + e)]; x = fma_(qv[e], qv[e], x); }
         }
         const T S = lp.reduce(part);
-        const T v = q[0], e = exp_(-v);
-        for (int d = lp.first(); d < M.D; d += lp.stride())
-          g[d] = (d == 0) ? funnel_grad_v(v, S, e, M.D) : funnel_grad_x(q[d], e);
-        l = funnel_value(v, S, e, M.D);
+        const T v = q[0], ex = exp_(-v);
+        BN_FOR4(d0, nv) {
+          T qv[4], gv[4];
+          ld4(q + d0, qv);
+          for (int e = 0; e < 4; ++e) gv[e] = (d0 + e == 0) ? funnel_grad_v(v, S, ex, M.D) : funnel_grad_x(qv[e], ex);
+          st4(g + d0, gv, nv);
+        }
+        l = funnel_value(v, S, ex, M.D);
         break;
       }
       case MODEL_GAUSSIAN: {
         const T* sg = M.stage_g + (int64_t)M.stage_row[c] * M.Dp;
-        for (int d = lp.first(); d < M.D; d += lp.stride()) g[d] = sg[d];
+        BN_FOR4(d0, nv) {
+          T gv[4];
+          ld4(sg + d0, gv);
+          st4(g + d0, gv, nv);
+        }
         lp.sync();
         l = T(0.5) * dot(q, g);
         break;
@@ -319,10 +412,16 @@ template <class T, class LP> struct Backend {
         const int64_t row = M.stage_row[c], rows = M.stage_rows;
         const int64_t bs = rows * M.Dp;
         const T* sg = M.stage_g + row * M.Dp;
-        for (int d = lp.first(); d < M.D; d += lp.stride()) {
-          T acc = T(0);
-          for (int b = 0; b < M.stage_nb; ++b) acc = acc + sg[b * bs + d];
-          g[d] = fma_(-M.tau, q[d], acc);
+        BN_FOR4(d0, nv) {
+          T acc[4] = {T(0), T(0), T(0), T(0)}, qv[4], gv[4];
+          for (int b = 0; b < M.stage_nb; ++b) {
+            T pv[4];
+            ld4(sg + b * bs + d0, pv);
+            for (int e = 0; e < 4; ++e) acc[e] = acc[e] + pv[e];
+          }
+          ld4(q + d0, qv);
+          for (int e = 0; e < 4; ++e) gv[e] = fma_(-M.tau, qv[e], acc[e]);
+          st4(g + d0, gv, nv);
         }
         T ls = T(0);
         if (M.stage_ld) {  // tensor path: partials are ~1e5 in magnitude, summed in Float64
@@ -331,9 +430,10 @@ template <class T, class LP> struct Backend {
           if (M.lin_w) {  // linear part of Σ log σ(η̃): ½ Σ_i η̃_i = ½ colsum(X̃)·q
             double part[LP::NACC];
             for (int i = 0; i < LP::NACC; ++i) part[i] = 0.0;
-            for (int d = lp.first(); d < M.D; d += lp.stride()) {
-              double& a = part[lp.acc(d)];
-              a = fma_(M.lin_w[d], (double)q[d], a);
+            BN_FOR4(d0, nv) {
+              T qv[4]; double wv[4];
+              ld4(q + d0, qv); ld4(M.lin_w + d0, wv);
+              for (int e = 0; e < nv; ++e) { double& a = part[lp.acc(d0 + e)]; a = fma_(wv[e], (double)qv[e], a); }
             }
             lsd = fma_(0.5, lp.reduce(part), lsd);
           }
@@ -355,11 +455,12 @@ template <class T, class LP> struct Backend {
     const T* q = zq(src); const T* g = zg(src);
     T* qn = zq(dst);
     const int row = take_row();
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T dv = fma_(-lambda, q[d], g[d]);
-      const T qd = fma_(alpha, dv, q[d]);
-      qn[d] = qd;
-      if (row >= 0) stage_put(row, d, qd);
+    BN_FOR4(d0, nv) {
+      T qv[4], gv[4], qd[4];
+      ld4(q + d0, qv); ld4(g + d0, gv);
+      for (int e = 0; e < 4; ++e) qd[e] = fma_(alpha, fma_(-lambda, qv[e], gv[e]), qv[e]);
+      st4(qn + d0, qd, nv);
+      if (row >= 0) stage_put4(row, d0, qd, nv);
     }
     lp.sync();
   }
@@ -367,10 +468,14 @@ template <class T, class LP> struct Backend {
     const T* q = zq(slot); const T* g = zg(slot);
     T a[LP::NACC], c2[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) a[i] = c2[i] = T(0);
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T dv = fma_(-lambda, q[d], g[d]);
-      T& x = a[lp.acc(d)]; x = fma_(dv, dv, x);
-      T& y = c2[lp.acc(d)]; y = fma_(q[d], q[d], y);
+    BN_FOR4(d0, nv) {
+      T qv[4], gv[4];
+      ld4(q + d0, qv); ld4(g + d0, gv);
+      for (int e = 0; e < nv; ++e) {
+        const T dv = fma_(-lambda, qv[e], gv[e]);
+        T& x = a[lp.acc(d0 + e)]; x = fma_(dv, dv, x);
+        T& y = c2[lp.acc(d0 + e)]; y = fma_(qv[e], qv[e], y);
+      }
     }
     *dd = lp.reduce(a);
     *qq = lp.reduce(c2);
@@ -380,12 +485,16 @@ template <class T, class LP> struct Backend {
     const T* q1 = zq(dst); const T* g1 = zg(dst);
     T a[LP::NACC], c2[LP::NACC], e[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) a[i] = c2[i] = e[i] = T(0);
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T d0 = fma_(-lambda, q0[d], g0[d]);
-      const T d1 = fma_(-lambda, q1[d], g1[d]);
-      T& x = a[lp.acc(d)]; x = fma_(d1, d1, x);
-      T& y = c2[lp.acc(d)]; y = fma_(q1[d], q1[d], y);
-      T& z = e[lp.acc(d)]; z = fma_(d0, d1, z);
+    BN_FOR4(d0, nv) {
+      T qa[4], ga[4], qb[4], gb[4];
+      ld4(q0 + d0, qa); ld4(g0 + d0, ga); ld4(q1 + d0, qb); ld4(g1 + d0, gb);
+      for (int k = 0; k < nv; ++k) {
+        const T da = fma_(-lambda, qa[k], ga[k]);
+        const T db = fma_(-lambda, qb[k], gb[k]);
+        T& x = a[lp.acc(d0 + k)]; x = fma_(db, db, x);
+        T& y = c2[lp.acc(d0 + k)]; y = fma_(qb[k], qb[k], y);
+        T& z = e[lp.acc(d0 + k)]; z = fma_(da, db, z);
+      }
     }
     *dd_new = lp.reduce(a);
     *qq_new = lp.reduce(c2);
@@ -394,10 +503,11 @@ template <class T, class LP> struct Backend {
   BN_HD void opt_restart_position(int slot, uint64_t seed, uint32_t gchain, uint32_t attempt) const {
     T* q = zq(slot);
     const int row = take_row();
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T qd = T(restart_position(seed, gchain, attempt, (uint32_t)d));
-      q[d] = qd;
-      if (row >= 0) stage_put(row, d, qd);
+    BN_FOR4(d0, nv) {
+      T qd[4] = {T(0), T(0), T(0), T(0)};
+      for (int e = 0; e < nv; ++e) qd[e] = T(restart_position(seed, gchain, attempt, (uint32_t)(d0 + e)));
+      st4(q + d0, qd, nv);
+      if (row >= 0) stage_put4(row, d0, qd, nv);
     }
     lp.sync();
   }
@@ -428,10 +538,12 @@ template <class T, class LP> struct Backend {
   BN_HD void load_position(int slot, uint64_t seed, uint32_t gchain) const {
     T* q = zq(slot);
     const int row = take_row();
-    for (int d = lp.first(); d < M.D; d += lp.stride()) {
-      const T qd = M.pos_in ? T(M.pos_in[(int64_t)c * M.D + d]) : T(init_position(seed, gchain, (uint32_t)d));
-      q[d] = qd;
-      if (row >= 0) stage_put(row, d, qd);
+    BN_FOR4(d0, nv) {
+      T qd[4] = {T(0), T(0), T(0), T(0)};
+      for (int e = 0; e < nv; ++e)
+        qd[e] = M.pos_in ? T(M.pos_in[(int64_t)c * M.D + d0 + e]) : T(init_position(seed, gchain, (uint32_t)(d0 + e)));
+      st4(q + d0, qd, nv);
+      if (row >= 0) stage_put4(row, d0, qd, nv);
     }
     lp.sync();
   }

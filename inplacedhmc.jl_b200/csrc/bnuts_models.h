@@ -5,7 +5,7 @@
 // (src/kinetic_energy.jl:73,89).  The four targets BASELINE.json names are
 // defined here once, as host/device scalar code, so the CUDA kernels and the CPU
 // oracle evaluate exactly the same expression tree.  Vector reductions follow
-// the "warp order" convention: lane l accumulates elements l, l+32, ... with fma
+// the "warp order" convention: lane l accumulates the groups of four consecutive elements 4l..4l+3 (+128, ...) with fma
 // in index order, then a xor-butterfly (16,8,4,2,1).
 #pragma once
 #include "bnuts_math.h"

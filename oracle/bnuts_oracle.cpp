@@ -38,7 +38,8 @@ using bn::log_;
 using bn::logaddexp_;
 
 // ------------------------------------------------------------------ reductions
-// "warp order": lane l accumulates elements l, l+32, ... then xor-butterfly.
+// "warp order": lane l accumulates the groups of four consecutive elements 4l..4l+3 (+128, ...) in index order
+// (accumulator (d >> 2) & 31), then xor-butterfly.
 template <class T> T butterfly(T* part) {
   for (int off = 16; off >= 1; off >>= 1) {
     T nw[32];
@@ -50,7 +51,7 @@ template <class T> T butterfly(T* part) {
 template <class T> T dot_warp(const T* a, const T* b, int D) {
   T part[32];
   for (int l = 0; l < 32; ++l) part[l] = T(0);
-  for (int d = 0; d < D; ++d) part[d & 31] = fma_(a[d], b[d], part[d & 31]);
+  for (int d = 0; d < D; ++d) part[(d >> 2) & 31] = fma_(a[d], b[d], part[(d >> 2) & 31]);
   return butterfly(part);
 }
 
@@ -92,7 +93,7 @@ template <class T> struct Model {
       case bn::MODEL_FUNNEL: {
         T part[32];
         for (int l = 0; l < 32; ++l) part[l] = T(0);
-        for (int d = 1; d < D; ++d) part[d & 31] = fma_(q[d], q[d], part[d & 31]);
+        for (int d = 1; d < D; ++d) part[(d >> 2) & 31] = fma_(q[d], q[d], part[(d >> 2) & 31]);
         const T S = butterfly(part);
         const T v = q[0], e = exp_(-v);
         g[0] = bn::funnel_grad_v(v, S, e, D);
@@ -238,7 +239,7 @@ template <class T> T kinetic_energy(const Ham<T>& H, const T* p) {
   const T* Mi = H.Minv();
   T part[32];
   for (int l = 0; l < 32; ++l) part[l] = T(0);
-  for (int d = 0; d < D; ++d) part[d & 31] = fma_(p[d] * Mi[d], p[d], part[d & 31]);
+  for (int d = 0; d < D; ++d) part[(d >> 2) & 31] = fma_(p[d] * Mi[d], p[d], part[(d >> 2) & 31]);
   return T(0.5) * butterfly(part);
 }
 // ≙ logdensity(H, z), src/kinetic_energy.jl:107-112
@@ -330,8 +331,8 @@ template <class T> bool is_turning(int D, const TurnStat<T>& tau) {
   for (int l = 0; l < 32; ++l) pm[l] = pp[l] = T(0);
   for (int d = 0; d < D; ++d) {
     const T r = tau.rho[d];
-    pm[d & 31] = fma_(r, tau.psm[d], pm[d & 31]);
-    pp[d & 31] = fma_(r, tau.psp[d], pp[d & 31]);
+    pm[(d >> 2) & 31] = fma_(r, tau.psm[d], pm[(d >> 2) & 31]);
+    pp[(d >> 2) & 31] = fma_(r, tau.psp[d], pp[(d >> 2) & 31]);
   }
   const T dm = butterfly(pm), dp = butterfly(pp);
   return (dm < T(0)) | (dp < T(0));

@@ -194,6 +194,8 @@ def test_cuda_sampling_moments_funnel_free_running(bn, cuda_lib):
         e.warmup_stage(N, mk, delta=0.95, keep=False)
     ch, st = e.sample(200)
     v = ch[:, :, 0]
-    assert abs(v.mean()) < 0.5 and 2.2 < v.std() < 3.5
+    # the neck of the funnel is under-sampled by any fixed-step HMC (mean of v biased by about +0.4 at delta = 0.95,
+    # the oracle gives the same): loose bounds, this is a smoke check of the free-running device engine
+    assert abs(v.mean()) < 0.8 and 2.2 < v.std() < 3.5
     c = e.counters()
     assert c["leapfrogs"] >= st["steps"].sum() and c["kernel_launches"] > 0
