@@ -420,8 +420,45 @@ template <class T, class X> struct EngineCore {
   // until every chain is idle.  Elementwise targets run inside advance().
   // Only chains with a gradient request occupy staging rows (active-chain
   // compaction), so the batched kernel cost follows the number of active chains.
+  // Batched targets, one engine: the host does not wait for each step's request count.  Inside one call the
+  // number of requesting chains never grows (a chain requests a gradient every lockstep step until it goes idle
+  // for the rest of the call), so the newest count that has ARRIVED is an upper bound for the rows of the next
+  // gradient launch: the launch covers all real requests plus, at worst, a few stale rows nobody reads.  Counts
+  // come back through a small ring of pinned slots (async copy + event); the host runs at most LAG steps ahead.
+  int32_t run_pipelined(bool pending) {
+    constexpr int LAG = 2;
+    int64_t np_known = pending ? x.read_count() : -1;   // -1: nothing known yet (first step has no gradient)
+    int64_t step = 0, completed = -1;
+    bool first = !pending;
+    for (;;) {
+      if (np_known > 0) {
+        M.stage_nb = x.gradient(*this, (int)np_known);
+        M.stage_rows = (int32_t)np_known;
+        counters.kernel_launches += 1;
+      }
+      x.advance_async(M, rp, 1, (int)(step % X::RING));
+      counters.kernel_launches += 1;
+      counters.lockstep_steps += 1;
+      ++step;
+      // collect the counts that have arrived; block only if the host is LAG steps ahead or knows nothing yet
+      while (completed + 1 < step) {
+        const int slot = (int)((completed + 1) % X::RING);
+        const bool must = first || (step - 1 - completed) >= LAG || np_known == 0;
+        if (!must && !x.count_ready(slot)) break;
+        const int64_t c = x.count_wait(slot);
+        ++completed;
+        counters.gradient_rows += c;       // rows requested by step `completed`, evaluated by the next launch
+        np_known = c;
+        first = false;
+      }
+      if (np_known == 0 && completed + 1 == step) break;
+      if (x.failed()) break;
+    }
+    return x.check(err);
+  }
   int32_t run(bool pending) {
     const bool batched = model.batched();
+    if (batched && !reduce_on && X::RING > 0) return run_pipelined(pending);
     const int iters = batched ? 1 : (1 << 30);
     int64_t np = 0;
     if (pending) np = reduce_on ? x.assign_rows(reduce_view(0), M) : x.read_count();

@@ -403,6 +403,7 @@ struct CudaExec {
     if (d_scal) cudaFree(d_scal);
     if (h_scal) cudaFreeHost(h_scal);
     if (d_status) cudaFree(d_status);
+    if (h_ring) { cudaFreeHost(h_ring); for (int i = 0; i < RING; ++i) cudaEventDestroy(ring_ev[i]); h_ring = nullptr; }
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
   }
   template <class U> U* alloc(size_t n) {
@@ -441,6 +442,27 @@ struct CudaExec {
     note(cudaMemsetAsync(d_scal, 0, sizeof(unsigned long long), stream), "memset");
     k_prepare<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, a);
   }
+  // ---- pipelined run loop (engine_core.h run_pipelined): request counts return through a ring of pinned slots
+  static constexpr int RING = 4;
+  unsigned long long* h_ring = nullptr;   // pinned [RING]
+  cudaEvent_t ring_ev[RING] = {};
+  template <class T> void advance_async(const EngineMem<T>& M, const RunParams<T>& rp, int iters, int slot) {
+    if (!h_ring) {
+      note(cudaMallocHost(&h_ring, RING * sizeof(unsigned long long)), "cudaMallocHost");
+      for (int i = 0; i < RING; ++i) note(cudaEventCreateWithFlags(&ring_ev[i], cudaEventDisableTiming), "event create");
+    }
+    note(cudaMemsetAsync(d_scal, 0, sizeof(unsigned long long), stream), "memset");
+    k_advance<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, iters, d_scal);
+    note(cudaGetLastError(), "k_advance");
+    note(cudaMemcpyAsync(h_ring + slot, d_scal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "pending d2h");
+    note(cudaEventRecord(ring_ev[slot], stream), "event record");
+  }
+  bool count_ready(int slot) { return cudaEventQuery(ring_ev[slot]) == cudaSuccess; }
+  int64_t count_wait(int slot) {
+    note(cudaEventSynchronize(ring_ev[slot]), "count wait");
+    return first_err == cudaSuccess ? (int64_t)h_ring[slot] : 0;
+  }
+  bool failed() const { return first_err != cudaSuccess; }
   template <class T> int64_t advance(const EngineMem<T>& M, const RunParams<T>& rp, int iters) {
     note(cudaMemsetAsync(d_scal, 0, sizeof(unsigned long long), stream), "memset");
     k_advance<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, iters, d_scal);

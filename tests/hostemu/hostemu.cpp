@@ -44,6 +44,15 @@ struct HostExec {
     count = 0;
     for (int c = 0; c < M.C; ++c) prepare_chain(M, rp, a, c, SerialLanes{});
   }
+  // pipelined run loop: on the host every count is available at once (same control flow, no lag)
+  static constexpr int RING = 4;
+  int64_t ring[RING] = {};
+  template <class T> void advance_async(const EngineMem<T>& M, const RunParams<T>& rp, int iters, int slot) {
+    ring[slot] = advance(M, rp, iters);
+  }
+  bool count_ready(int) { return true; }
+  int64_t count_wait(int slot) { return ring[slot]; }
+  bool failed() const { return false; }
   template <class T> int64_t advance(const EngineMem<T>& M, const RunParams<T>& rp, int iters) {
     int64_t np = 0;
     count = 0;
