@@ -188,6 +188,17 @@ template <class T, class X> struct EngineCore {
     x.h2d(model.P, h.data(), n * sizeof(T));
     if (!M.stage_q) alloc_stage(1);
     model.kind = MODEL_GAUSSIAN; M.model_kind = MODEL_GAUSSIAN;
+    // tensor-core gradient (fp32 engine): on request, or by default for large D where the GEMM dominates
+    const bool want_tensor = cfg.gradient_path == BNUTS_GRAD_TENSOR ||
+                             (cfg.gradient_path == BNUTS_GRAD_AUTO && sizeof(T) == 4 && X::has_tensor_path && M.D >= 512);
+    model.tensor = false;
+    if (want_tensor) {
+      if (sizeof(T) != 4 || !X::has_tensor_path)
+        return fail(BNUTS_ERR_UNSUPPORTED, "tensor gradient path needs dtype F32 on the CUDA engine");
+      int32_t rc = x.gauss_tensor_setup(*this, Pd, err);
+      if (rc) return rc;
+      model.tensor = true;
+    }
     return x.check(err);
   }
   // whitened model: P̃ = Lᵀ P L (P = I for the iid normal target)

@@ -18,6 +18,7 @@
 
 #include "engine_core.h"
 #include "logistic_tc.h"
+#include "gauss_tc.h"
 
 namespace bn {
 
@@ -350,6 +351,7 @@ struct CudaExec {
   int32_t* d_status = nullptr;
   int device = 0;
   LogisticTC tc;
+  GaussTC gt;
   void* nccl_comm = nullptr;
   // measurement hook: CUDA-event pairs around the batched gradient launches
   bool profiling = false;
@@ -400,6 +402,7 @@ struct CudaExec {
     if (nccl_comm && nccl().CommDestroy) nccl().CommDestroy(nccl_comm);
     nccl_comm = nullptr;
     tc.destroy();
+    gt.destroy();
     if (d_scal) cudaFree(d_scal);
     if (h_scal) cudaFreeHost(h_scal);
     if (d_status) cudaFree(d_status);
@@ -483,7 +486,9 @@ struct CudaExec {
     auto& M = eng.M;
     using T = typename std::remove_reference<decltype(*M.zs)>::type;
     int nb = 1;
-    if (eng.model.kind == MODEL_GAUSSIAN) {
+    if (eng.model.kind == MODEL_GAUSSIAN && eng.model.tensor) {
+      gt.run(stream, rows);
+    } else if (eng.model.kind == MODEL_GAUSSIAN) {
       // tile size by the number of active rows, so straggler steps (a few chains deep in their trees)
       // still spread over many SMs; every variant keeps k sequential per output (bit-identical results)
       if (sizeof(T) == 4 && rows > 1024) {
@@ -510,6 +515,28 @@ struct CudaExec {
     }
     note(cudaGetLastError(), "gradient kernel");
     return nb;
+  }
+  // Gaussian target on the tensor cores: staging of the three-term bf16 split of q (written by the chains,
+  // backend.h stage_put4) + the split of -P
+  template <class E> int32_t gauss_tensor_setup(E& eng, const std::vector<double>& P, std::string& err) {
+    using T = typename std::remove_reference<decltype(*eng.M.zs)>::type;
+    if constexpr (!std::is_same<T, float>::value) {
+      err = "tensor gradient path needs dtype F32";
+      return BNUTS_ERR_UNSUPPORTED;
+    } else {
+      auto& M = eng.M;
+      int32_t rc = gauss_tc_build(gt, P, M.C, M.D, M.Dp, err);
+      if (rc) return rc;
+      if (M.stage_bh && M.Dt != gt.Kp) { free(M.stage_bh); free(M.stage_bm); free(M.stage_bl); M.stage_bh = M.stage_bm = M.stage_bl = nullptr; }
+      M.Dt = gt.Kp;
+      const size_t nbt = size_t(M.C) * gt.Kp;
+      if (!M.stage_bh) {
+        M.stage_bh = alloc<uint16_t>(nbt); M.stage_bm = alloc<uint16_t>(nbt); M.stage_bl = alloc<uint16_t>(nbt);
+        zero(M.stage_bh, nbt * 2); zero(M.stage_bm, nbt * 2); zero(M.stage_bl, nbt * 2);
+      }
+      gt.qh = M.stage_bh; gt.qm = M.stage_bm; gt.ql = M.stage_bl; gt.G = M.stage_g;
+      return gauss_tc_maps(gt, err);
+    }
   }
   template <class E> int32_t logistic_tensor_setup(E& eng, const void* Xh, int32_t xd, const double* y, int64_t N, std::string& err) {
     return logistic_tc_setup(tc, eng, Xh, xd, y, N, err);

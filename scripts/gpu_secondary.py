@@ -9,8 +9,8 @@ import inplacedhmc_jl_b200 as bn
 from conftest import make_gaussian
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
-def run(name, C, D, dtype, setup, n_draws, stages=((75, 0), (25, 1), (50, 1), (100, 1), (50, 0)), delta=0.8, eps=None, flops_per_leapfrog=0):
-    e = bn.Engine(C, D, dtype=dtype, seed=11, gradient_path=bn.GRAD_DETERMINISTIC)
+def run(name, C, D, dtype, setup, n_draws, stages=((75, 0), (25, 1), (50, 1), (100, 1), (50, 0)), delta=0.8, eps=None, flops_per_leapfrog=0, path=bn.GRAD_DETERMINISTIC):
+    e = bn.Engine(C, D, dtype=dtype, seed=11, gradient_path=path)
     setup(e); e.set_positions(None)
     t = time.perf_counter()
     if eps is None:
@@ -52,5 +52,9 @@ if __name__ == "__main__":
 
         def dense(e):
             e.model_gaussian(P); e.set_metric_dense(S)     # c2: dense-metric GaussianKE, M⁻¹ = Σ injected
-        run("c2 dense Gaussian D=1000, shared dense metric M^-1 = Sigma (whitened: one GEMM per leapfrog)", 4096, 1000, bn.F32, dense, 20,
+        run("c2 dense Gaussian D=1000, shared dense metric M^-1 = Sigma (whitened: one GEMM per leapfrog), CUDA-core gradient", 4096, 1000, bn.F32, dense, 20,
             stages=((75, 0), (100, 0)), flops_per_leapfrog=2 * 1000 * 1000)
+        run("c2 dense Gaussian D=1000, shared dense metric M^-1 = Sigma, tcgen05 gradient (3x3-term bf16 split)", 4096, 1000, bn.F32, dense, 20,
+            stages=((75, 0), (100, 0)), flops_per_leapfrog=2 * 1000 * 1000, path=bn.GRAD_TENSOR)
+        run("c2 dense Gaussian D=1000, diag metric, tcgen05 gradient", 4096, 1000, bn.F32, lambda e: e.model_gaussian(P), 5,
+            stages=((20, 0),), flops_per_leapfrog=2 * 1000 * 1000, path=bn.GRAD_TENSOR)

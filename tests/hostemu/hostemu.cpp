@@ -102,6 +102,10 @@ struct HostExec {
     }
     return nbr;
   }
+  template <class E> int32_t gauss_tensor_setup(E&, const std::vector<double>&, std::string& err) {
+    err = "tensor path is CUDA-only";
+    return BNUTS_ERR_UNSUPPORTED;
+  }
   template <class E> int32_t logistic_tensor_setup(E&, const void*, int32_t, const double*, int64_t, std::string& err) {
     err = "tensor path is CUDA-only";
     return BNUTS_ERR_UNSUPPORTED;

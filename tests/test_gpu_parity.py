@@ -73,6 +73,43 @@ def test_tensor_gradient_within_tolerance(bn, oracle_lib, cuda_lib, N, D, C):
     assert l1[0] == pytest.approx(-N * np.log(2), rel=1e-6)
 
 
+@pytest.mark.parametrize("D,C", [(1000, 300), (70, 5), (128, 128), (257, 130)])
+def test_gauss_tensor_gradient_and_leapfrog_within_tolerance(bn, oracle_lib, cuda_lib, D, C):
+    """tcgen05 path of the Gaussian target (three-term bf16 splits of both operands) against the fp64 oracle on
+    identical fp32 inputs: gradient, log density, positions after leapfrogs; and against the CUDA-core path."""
+    from conftest import make_gaussian
+    P, S = make_gaussian(D, seed=5)
+    P = _f32(P)
+    rng = np.random.default_rng(6)
+    q = _f32(rng.normal(size=(C, D)))
+    ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_gaussian(P); ref.set_positions(q)
+    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_gaussian(P); tc.set_positions(q)
+    det = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=DET); det.model_gaussian(P); det.set_positions(q)
+    _, g0, l0 = ref.get_state(); _, g1, l1 = tc.get_state(); _, g2, l2 = det.get_state()
+    assert np.max(_rel(g1, g0)) < TOL32 and np.max(np.abs(l1 - l0) / np.abs(l0)) < TOL32
+    assert np.max(_rel(g1, g2)) < TOL32
+    p = _f32(rng.normal(size=(C, D)))
+    a = ref.leapfrog(p, 0.05, 3); b = tc.leapfrog(p, 0.05, 3)
+    assert np.max(_rel(b[0], a[0])) < TOL32 and np.max(_rel(b[2], a[2])) < 5 * TOL32
+    tc.set_stepsize(0.05); ch, st = tc.sample(3)
+    assert np.isfinite(ch).all() and (st["steps"] > 0).all()
+
+
+def test_gauss_tensor_with_dense_metric(bn, oracle_lib, cuda_lib):
+    from conftest import make_gaussian
+    D, C = 200, 64
+    P, S = make_gaussian(D, seed=7)
+    rng = np.random.default_rng(8)
+    q = rng.normal(size=(C, D))
+    ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_gaussian(P); ref.set_metric_dense(S); ref.set_positions(q)
+    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_gaussian(P); tc.set_metric_dense(S); tc.set_positions(q)
+    for x, y in zip(ref.get_state(), tc.get_state()):
+        assert np.max(np.abs(y - x)) / np.max(np.abs(x)) < 5e-5
+    p = rng.normal(size=(C, D))
+    a = ref.leapfrog(p, 0.3, 2); b = tc.leapfrog(p, 0.3, 2)
+    assert np.max(_rel(b[0], a[0])) < 5e-5
+
+
 def test_tensor_reference_point(bn, oracle_lib, cuda_lib):
     """Two-term path around a reference point near the mode: same tolerance as the exact path;
     a reference far from the mode is refused and the exact path stays in force."""
