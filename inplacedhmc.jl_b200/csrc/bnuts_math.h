@@ -20,8 +20,16 @@
 
 #if defined(__CUDACC__)
 #define BN_HD __host__ __device__ __forceinline__
+// large scalar routines (transcendentals, Philox) are real functions on the device: inlined at every call site they
+// made k_advance 460 KB of code and the kernel instruction-fetch bound (ncu: 45 % of warp samples "no instruction")
+#ifdef BNUTS_INLINE_MATH
+#define BN_HDN __host__ __device__ __forceinline__
+#else
+#define BN_HDN __host__ __device__ inline __noinline__
+#endif
 #else
 #define BN_HD inline
+#define BN_HDN inline
 #endif
 
 namespace bn {
@@ -78,7 +86,7 @@ template <> struct lim<float> {
 // ---------------------------------------------------------------- exp
 // k = round(x/ln2), r = x - k ln2 (two-term Cody-Waite), Taylor polynomial of
 // e^r on |r| <= ln2/2, scaled by 2^k through the exponent field.
-BN_HD double exp_(double x) {
+BN_HDN double exp_(double x) {
   if (x != x) return x;
   if (x > 709.0) return lim<double>::inf();
   if (x < -708.0) return 0.0;
@@ -103,7 +111,7 @@ BN_HD double exp_(double x) {
   const int64_t k = (int64_t)kf;  // |k| <= 1023 here
   return p * u2d((uint64_t)(k + 1023) << 52);
 }
-BN_HD float exp_(float x) {
+BN_HDN float exp_(float x) {
   if (x != x) return x;
   if (x > 88.0f) return lim<float>::inf();
   if (x < -87.0f) return 0.0f;
@@ -125,7 +133,7 @@ BN_HD float exp_(float x) {
 // ---------------------------------------------------------------- log
 // x = 2^e * m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = (m-1)/(m+1),
 // odd series in s with the exact rational coefficients 1/(2j+1).
-BN_HD double log_(double x) {
+BN_HDN double log_(double x) {
   if (x != x) return x;
   if (x < 0.0) return lim<double>::nan();
   if (x == 0.0) return -lim<double>::inf();
@@ -158,7 +166,7 @@ BN_HD double log_(double x) {
   const double ef = (double)e;
   return fma_(ef, 6.93147180369123816490e-01, fma_(ef, 1.90821492927058770002e-10, lm));
 }
-BN_HD float log_(float x) {
+BN_HDN float log_(float x) {
   if (x != x) return x;
   if (x < 0.0f) return lim<float>::nan();
   if (x == 0.0f) return -lim<float>::inf();
@@ -203,7 +211,7 @@ template <class T> BN_HD T logaddexp_(T x, T y) {
 // ---------------------------------------------------------------- sin/cos(2 pi u)
 // u in [0,1).  j = nearest quarter turn, f = u - j/4 in [-1/8,1/8] (exact),
 // Taylor series of sin/cos on |phi| <= pi/4, then a quadrant rotation.
-BN_HD void sincos2pi_(double u, double* s_out, double* c_out) {
+BN_HDN void sincos2pi_(double u, double* s_out, double* c_out) {
   const double jf = ::floor(fma_(u, 4.0, 0.5));
   const double f = u - jf * 0.25;
   const double x = f * 6.283185307179586476925;
@@ -233,7 +241,7 @@ BN_HD void sincos2pi_(double u, double* s_out, double* c_out) {
   *s_out = (j == 0) ? s : (j == 1) ? c : (j == 2) ? -s : -c;
   *c_out = (j == 0) ? c : (j == 1) ? -s : (j == 2) ? -c : s;
 }
-BN_HD void sincos2pi_(float u, float* s_out, float* c_out) {
+BN_HDN void sincos2pi_(float u, float* s_out, float* c_out) {
   const float jf = ::floorf(fma_(u, 4.0f, 0.5f));
   const float f = u - jf * 0.25f;
   const float x = f * 6.28318530717958648f;
@@ -261,7 +269,7 @@ BN_HD void mulhilo32(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
   *hi = (uint32_t)(p >> 32);
   *lo = (uint32_t)p;
 }
-BN_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
+BN_HDN u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
   for (int r = 0; r < 10; ++r) {
     uint32_t hi0, lo0, hi1, lo1;
     mulhilo32(0xD2511F53u, c.x, &hi0, &lo0);

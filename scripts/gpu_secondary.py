@@ -10,7 +10,7 @@ from conftest import make_gaussian
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
 def run(name, C, D, dtype, setup, n_draws, stages=((75, 0), (25, 1), (50, 1), (100, 1), (50, 0)), delta=0.8, eps=None, flops_per_leapfrog=0, path=bn.GRAD_DETERMINISTIC):
-    e = bn.Engine(C, D, dtype=dtype, seed=11, gradient_path=path)
+    e = bn.Engine(C, D, dtype=dtype, seed=11, gradient_path=path, lib=bn.load_library(os.environ['BNUTS_LIB']) if os.environ.get('BNUTS_LIB') else None)
     setup(e); e.set_positions(None)
     t = time.perf_counter()
     if eps is None:

@@ -56,7 +56,11 @@ def _f32(x):
     return np.asarray(x, dtype=np.float32).astype(np.float64)
 
 
-@pytest.mark.parametrize("N,D,C", [(2000, 100, 200), (128, 64, 128), (1000, 17, 3), (5000, 128, 257)])
+# shapes: headline D, tile-exact, tiny, D = 128 (no spare K columns: three-term mode only), the boundaries of the
+# reserved reference columns (D = 125 fits, 126 does not, 61 -> K 64, 62 spills into a second 64-column chunk),
+# one chain, one coordinate, N not a multiple of the 128-row block
+@pytest.mark.parametrize("N,D,C", [(2000, 100, 200), (128, 64, 128), (1000, 17, 3), (5000, 128, 257), (300, 125, 5),
+                                   (300, 126, 5), (129, 1, 1), (77, 61, 130), (500, 62, 9)])
 def test_tensor_gradient_within_tolerance(bn, oracle_lib, cuda_lib, N, D, C):
     X, y, beta = make_logistic(N, D)
     rng = np.random.default_rng(1)
@@ -71,6 +75,12 @@ def test_tensor_gradient_within_tolerance(bn, oracle_lib, cuda_lib, N, D, C):
     # known answer at beta = 0: grad = X'(y - 1/2), l = -N log 2
     np.testing.assert_allclose(g1[0], (y - 0.5) @ X, rtol=1e-5, atol=1e-4)
     assert l1[0] == pytest.approx(-N * np.log(2), rel=1e-6)
+    # extreme positions: |eta| in the hundreds must not overflow (t = exp(-|eta|), never exp(+|eta|))
+    big = _f32(q * 200.0)
+    ref.set_positions(big); tc.set_positions(big)
+    _, gb0, lb0 = ref.get_state(); _, gb1, lb1 = tc.get_state()
+    assert np.all(np.isfinite(gb1)) and np.all(np.isfinite(lb1))
+    assert np.max(_rel(gb1[1:], gb0[1:])) < 10 * TOL32 and np.max(np.abs(lb1[1:] - lb0[1:]) / np.abs(lb0[1:])) < 10 * TOL32
 
 
 @pytest.mark.parametrize("D,C", [(1000, 300), (70, 5), (128, 128), (257, 130)])
