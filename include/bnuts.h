@@ -195,6 +195,16 @@ int32_t bnuts_set_allreduce(bnuts_engine* e, bnuts_allreduce_fn fn, void* ctx);
 int32_t bnuts_nccl_unique_id(uint8_t* id /* [128] */);
 int32_t bnuts_set_nccl(bnuts_engine* e, const uint8_t* id /* [128] */, int32_t world, int32_t rank);
 
+/*   bnuts_p2p_export /   CUDA engines in different processes of one NVLink / NVSwitch node: the exchange is done by the
+ *   bnuts_p2p_connect    library's own kernels over peer memory instead of NCCL.  The kernel that folds a shard's
+ *                        partials also pushes the folded rows into every peer's receive slot (plain stores to
+ *                        peer pointers, i.e. NVLink writes) and raises a flag there; the kernel that feeds the
+ *                        chains waits for all flags and adds the slots in rank order (bit-identical on every rank).
+ *                        export: allocates the receive buffer and returns its 64-byte cudaIpcMemHandle_t;
+ *                        connect: the handles of all ranks in rank order (host-side all-gather), then as set_nccl. */
+int32_t bnuts_p2p_export(bnuts_engine* e, uint8_t* handle /* [64] */);
+int32_t bnuts_p2p_connect(bnuts_engine* e, const uint8_t* handles /* [world][64] */, int32_t world, int32_t rank);
+
 int32_t bnuts_counters(bnuts_engine* e, bnuts_counter_block* out);
 /* Measurement hook (no reference counterpart): when enabled, every launch of the
  * batched gradient kernel inside the run loop is bracketed by CUDA events on the

@@ -58,6 +58,7 @@ EXPORTS = [
     "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_set_metric_dense", "bnuts_get_metric_dense", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed",
     "bnuts_inject", "bnuts_leapfrog", "bnuts_find_local_optimum", "bnuts_find_initial_stepsize", "bnuts_warmup_stage", "bnuts_sample",
     "bnuts_counters", "bnuts_profile", "bnuts_chain_status", "bnuts_set_allreduce", "bnuts_nccl_unique_id", "bnuts_set_nccl",
+    "bnuts_p2p_export", "bnuts_p2p_connect",
 ]
 
 _P = C.c_void_p
@@ -90,6 +91,8 @@ def load_library(path=None):
     lib.bnuts_set_allreduce.argtypes = [_P, ALLREDUCE_FN, _P]
     lib.bnuts_nccl_unique_id.argtypes = [_P]
     lib.bnuts_set_nccl.argtypes = [_P, _P, C.c_int32, C.c_int32]
+    lib.bnuts_p2p_export.argtypes = [_P, _P]
+    lib.bnuts_p2p_connect.argtypes = [_P, _P, C.c_int32, C.c_int32]
     lib.bnuts_set_positions.argtypes = [_P, _P]
     lib.bnuts_get_state.argtypes = [_P, _P, _P, _P]
     lib.bnuts_set_metric_diag.argtypes = [_P, _P]
@@ -214,6 +217,18 @@ class Engine:
         """unique_id: the 128 bytes of nccl_unique_id(lib) from rank 0 (broadcast them with the host's own plumbing)."""
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         self._chk(self.lib.bnuts_set_nccl(self.h, buf, world, rank))
+
+    def p2p_export(self):
+        """64-byte IPC handle of this engine's receive buffer (peer-memory exchange over NVLink)."""
+        buf = (C.c_uint8 * 64)()
+        self._chk(self.lib.bnuts_p2p_export(self.h, buf))
+        return bytes(buf)
+
+    def p2p_connect(self, handles, rank):
+        """handles: the p2p_export() bytes of every rank, in rank order."""
+        blob = b"".join(bytes(h) for h in handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._chk(self.lib.bnuts_p2p_connect(self.h, buf, len(handles), rank))
 
     # ---- state
     def set_positions(self, q=None, allow_nonfinite=False):

@@ -132,6 +132,14 @@ int32_t bnuts_set_nccl(bnuts_engine* e, const uint8_t* id, int32_t world, int32_
   if (rc) return rc;
   BN_DISPATCH(e, enable_reduce(nullptr, nullptr));
 }
+int32_t bnuts_p2p_export(bnuts_engine* e, uint8_t* handle) {
+  if (!handle) return BNUTS_ERR_INVALID_ARGUMENT;
+  BN_DISPATCH(e, p2p_export(handle));
+}
+int32_t bnuts_p2p_connect(bnuts_engine* e, const uint8_t* handles, int32_t world, int32_t rank) {
+  if (!handles || world < 1 || world > 8 || rank < 0 || rank >= world) return BNUTS_ERR_INVALID_ARGUMENT;
+  BN_DISPATCH(e, p2p_connect(handles, world, rank));
+}
 int32_t bnuts_counters(bnuts_engine* e, bnuts_counter_block* out) {
   if (!out) return BNUTS_ERR_INVALID_ARGUMENT;
   BN_DISPATCH(e, get_counters(out));

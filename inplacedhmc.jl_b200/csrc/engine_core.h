@@ -75,6 +75,7 @@ template <class T, class X> struct EngineCore {
   double* d_xf_in = nullptr; double* d_xf_out = nullptr; size_t cap_xf = 0;   // transform scratch
   // row-sharded data: per-leapfrog sum of the gradient partials over the group
   bool reduce_on = false;
+  bool p2p_on = false; uint64_t p2p_seq = 0;   // peer-memory exchange instead of a collective call
   bnuts_allreduce_fn red_fn = nullptr; void* red_ctx = nullptr;
   T* red_g = nullptr;           // [C][Dp] folded gradient partials, summed across the group in place
   double* red_l = nullptr;      // [C]     folded log-density partials (Float64)
@@ -130,7 +131,19 @@ template <class T, class X> struct EngineCore {
     void** ps[] = {(void**)&red_g, (void**)&red_l, (void**)&wide_q, (void**)&wide_bh, (void**)&wide_bm, (void**)&wide_bl,
                    (void**)&d_active};
     for (void** p : ps) if (*p) { x.free(*p); *p = nullptr; }
-    reduce_on = false;
+    reduce_on = false; p2p_on = false;
+  }
+  int32_t p2p_export(uint8_t* handle) {
+    if (model.kind != MODEL_LOGISTIC) return fail(BNUTS_ERR_NO_MODEL, "row sharding needs the logistic model (set it first)");
+    return x.p2p_export(size_t(M.C) * M.Dp * sizeof(T), size_t(M.C) * sizeof(double), handle, err);
+  }
+  int32_t p2p_connect(const uint8_t* handles, int32_t world, int32_t rank) {
+    int32_t rc = x.p2p_connect(handles, world, rank, err);
+    if (rc) return rc;
+    rc = enable_reduce(nullptr, nullptr);
+    if (rc) return rc;
+    p2p_on = true; p2p_seq = 0;
+    return 0;
   }
   // ≙ no reference counterpart (the reference has no collective).  After this call the engine
   // treats its design matrix as one shard of the rows: every lockstep step the folded partials
@@ -479,7 +492,12 @@ template <class T, class X> struct EngineCore {
         M.stage_rows = (int32_t)np;
         counters.kernel_launches += 1;
         counters.gradient_rows += np;
-        if (reduce_on) {   // fold the partials of this shard, sum them over the group (one exchange per leapfrog)
+        if (reduce_on && p2p_on) {   // fold + push over NVLink in one kernel, wait + sum in rank order in another
+          p2p_seq += 1;
+          x.fold_push(M, (int)np, p2p_seq);
+          x.wait_sum(M, (int)np, p2p_seq, red_g, red_l);
+          counters.kernel_launches += 2;
+        } else if (reduce_on) {   // fold the partials of this shard, sum them over the group (one exchange per leapfrog)
           x.fold_partials(M, (int)np, red_g, red_l);
           int32_t rc = x.allreduce(red_g, np * M.Dp, sizeof(T) == 4, red_l, np, red_fn, red_ctx, err);
           if (rc) return rc;
@@ -497,6 +515,7 @@ template <class T, class X> struct EngineCore {
       counters.lockstep_steps += 1;
       if (np <= 0) break;
     }
+    if (p2p_on && x.p2p_failed()) return fail(BNUTS_ERR_CUDA, "peer-memory exchange timed out waiting for a rank");
     return x.check(err);
   }
   void ensure_out(int N, bool want_draws) {

@@ -161,6 +161,92 @@ __global__ void __launch_bounds__(ADV_THREADS) k_fold_partials(EngineMem<T> M, i
   }
 }
 
+// ---- peer-memory exchange (bnuts_p2p_*): every rank owns one receive buffer
+//   [ flags: 2 parities x 8 ranks x u64 | pad to 256 B | parity 0: rank 0 {G rows, L rows}, rank 1 {...}, ... | parity 1: ... ]
+// and holds the (IPC-mapped) base pointers of all ranks' buffers.
+struct P2PView {
+  unsigned char* peer[8];
+  int world, rank;
+  size_t g_bytes, l_bytes;      // per (parity, source rank) block: C*Dp*sizeof(T) + C*8
+  __host__ __device__ size_t block_off(int parity, int src) const { return 256 + ((size_t)parity * 8 + src) * (g_bytes + l_bytes); }
+  __host__ __device__ size_t flag_off(int parity, int src) const { return ((size_t)parity * 8 + src) * 8; }
+};
+// fold this shard's partial blocks (as k_fold_partials) and push the folded row into the receive slot
+// [parity][my rank] of EVERY rank over NVLink; the last CTA to finish raises the flag on every rank
+template <class T>
+__global__ void __launch_bounds__(ADV_THREADS) k_fold_push(EngineMem<T> M, int rows, P2PView V, unsigned long long seq, unsigned int* done) {
+  const int row = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  const int parity = (int)(seq & 1ull);
+  if (row < rows) {
+    const int64_t bs = (int64_t)rows * M.Dp;
+    const T* sg = M.stage_g + (int64_t)row * M.Dp;
+    double lin = 0.0;
+    for (int d = lane; d < M.Dp; d += 32) {
+      T acc = T(0);
+      if (d < M.D) {
+        for (int b = 0; b < M.stage_nb; ++b) acc = acc + sg[b * bs + d];
+        if (M.lin_w) lin = fma(M.lin_w[d], (double)M.stage_q[(int64_t)row * M.Dp + d], lin);
+      }
+      for (int r = 0; r < V.world; ++r)
+        reinterpret_cast<T*>(V.peer[r] + V.block_off(parity, V.rank))[(int64_t)row * M.Dp + d] = acc;
+    }
+    for (int off = 16; off >= 1; off >>= 1) lin += __shfl_xor_sync(0xffffffffu, lin, off);
+    if (lane == 0) {
+      double l = 0.0;
+      for (int b = 0; b < M.stage_nb; ++b)
+        l += M.stage_ld ? M.stage_ld[(int64_t)b * rows + row] : (double)M.stage_l[(int64_t)b * rows + row];
+      l = fma(0.5, lin, l);
+      for (int r = 0; r < V.world; ++r)
+        reinterpret_cast<double*>(V.peer[r] + V.block_off(parity, V.rank) + V.g_bytes)[row] = l;
+    }
+  }
+  // all stores of this CTA system-visible, then count it; the last CTA publishes the sequence number everywhere
+  __threadfence_system();
+  __syncthreads();
+  __shared__ unsigned int ticket;
+  if (threadIdx.x == 0) ticket = atomicAdd(done, 1u);
+  __syncthreads();
+  if (ticket == gridDim.x - 1 && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int r = 0; r < V.world; ++r)
+      *reinterpret_cast<volatile unsigned long long*>(V.peer[r] + V.flag_off(parity, V.rank)) = seq;
+    *done = 0u;
+    __threadfence_system();
+  }
+}
+// wait until every rank's rows of this step have arrived, then add the slots in rank order
+template <class T>
+__global__ void __launch_bounds__(ADV_THREADS) k_wait_sum(int rows, int Dp, P2PView V, unsigned long long seq, T* red_g, double* red_l,
+                                                          int* err_flag) {
+  const int parity = (int)(seq & 1ull);
+  const unsigned char* mine = V.peer[V.rank];
+  if (threadIdx.x < V.world) {
+    const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(mine + V.flag_off(parity, threadIdx.x));
+    const long long t0 = clock64();
+    while (*f < seq) {
+      if (clock64() - t0 > 8000000000ll) { *err_flag = 1; break; }   // ~4 s: a peer died; do not hang the GPU
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const int row = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (row >= rows) return;
+  const int lane = (int)(threadIdx.x & 31);
+  for (int d = lane; d < Dp; d += 32) {
+    T acc = T(0);
+    for (int r = 0; r < V.world; ++r)
+      acc = acc + __ldcv(reinterpret_cast<const T*>(mine + V.block_off(parity, r)) + (int64_t)row * Dp + d);
+    red_g[(int64_t)row * Dp + d] = acc;
+  }
+  if (lane == 0) {
+    double l = 0.0;
+    for (int r = 0; r < V.world; ++r) l += __ldcv(reinterpret_cast<const double*>(mine + V.block_off(parity, r) + V.g_bytes) + row);
+    red_l[row] = l;
+  }
+}
+
 // NCCL is bound at run time (dlopen) so the library loads on hosts without it; only bnuts_set_nccl needs it
 struct NcclApi {
   typedef struct { char internal[128]; } UniqueId;
@@ -353,6 +439,10 @@ struct CudaExec {
   LogisticTC tc;
   GaussTC gt;
   void* nccl_comm = nullptr;
+  // peer-memory exchange
+  unsigned char* p2p_buf = nullptr; size_t p2p_bytes = 0;
+  P2PView p2p{};
+  unsigned int* p2p_done = nullptr; int* p2p_err = nullptr;
   // measurement hook: CUDA-event pairs around the batched gradient launches
   bool profiling = false;
   std::vector<cudaEvent_t> ev;   // pairs
@@ -401,6 +491,10 @@ struct CudaExec {
   void shutdown() {
     if (nccl_comm && nccl().CommDestroy) nccl().CommDestroy(nccl_comm);
     nccl_comm = nullptr;
+    for (int r = 0; r < p2p.world; ++r) if (r != p2p.rank && p2p.peer[r]) cudaIpcCloseMemHandle(p2p.peer[r]);
+    if (p2p_buf) cudaFree(p2p_buf);
+    if (p2p_done) cudaFree(p2p_done);
+    if (p2p_err) cudaFree(p2p_err);
     tc.destroy();
     gt.destroy();
     if (d_scal) cudaFree(d_scal);
@@ -560,6 +654,51 @@ struct CudaExec {
     const int r = nccl().CommInitRank(&nccl_comm, world, u, rank);
     if (r != 0) { err = std::string("ncclCommInitRank: ") + nccl().GetErrorString(r); nccl_comm = nullptr; return BNUTS_ERR_CUDA; }
     return 0;
+  }
+  int32_t p2p_export(size_t g_bytes, size_t l_bytes, uint8_t* handle, std::string& err) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    note(cudaSetDevice(device), "cudaSetDevice");
+    if (p2p_buf) { cudaFree(p2p_buf); p2p_buf = nullptr; }
+    p2p = P2PView{};
+    p2p.g_bytes = g_bytes; p2p.l_bytes = l_bytes;
+    p2p_bytes = 256 + 2 * 8 * (g_bytes + l_bytes);
+    if (cudaMalloc(&p2p_buf, p2p_bytes) != cudaSuccess) { err = "device allocation failed (peer exchange buffer)"; return BNUTS_ERR_CUDA; }
+    note(cudaMemset(p2p_buf, 0, p2p_bytes), "memset");
+    if (!p2p_done) { note(cudaMalloc(&p2p_done, 4), "cudaMalloc"); note(cudaMalloc(&p2p_err, 4), "cudaMalloc"); }
+    note(cudaMemset(p2p_done, 0, 4), "memset"); note(cudaMemset(p2p_err, 0, 4), "memset");
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p2p_buf);
+    if (e != cudaSuccess) { err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return BNUTS_ERR_CUDA; }
+    std::memcpy(handle, &h, 64);
+    return check(err);
+  }
+  int32_t p2p_connect(const uint8_t* handles, int world, int rank, std::string& err) {
+    if (!p2p_buf) { err = "bnuts_p2p_export first"; return BNUTS_ERR_INVALID_ARGUMENT; }
+    note(cudaSetDevice(device), "cudaSetDevice");
+    p2p.world = world; p2p.rank = rank;
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) { p2p.peer[r] = p2p_buf; continue; }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, handles + (size_t)r * 64, 64);
+      void* ptr = nullptr;
+      const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { err = std::string("cudaIpcOpenMemHandle (peer access over NVLink needed): ") + cudaGetErrorString(e); return BNUTS_ERR_CUDA; }
+      p2p.peer[r] = static_cast<unsigned char*>(ptr);
+    }
+    return check(err);
+  }
+  bool p2p_failed() {
+    int v = 0;
+    d2h(&v, p2p_err, sizeof(int));
+    return v != 0;
+  }
+  template <class T> void fold_push(const EngineMem<T>& M, int rows, uint64_t seq) {
+    k_fold_push<T><<<warp_grid(rows), ADV_THREADS, 0, stream>>>(M, rows, p2p, (unsigned long long)seq, p2p_done);
+    note(cudaGetLastError(), "fold_push");
+  }
+  template <class T> void wait_sum(const EngineMem<T>& M, int rows, uint64_t seq, T* red_g, double* red_l) {
+    k_wait_sum<T><<<warp_grid(rows), ADV_THREADS, 0, stream>>>(rows, M.Dp, p2p, (unsigned long long)seq, red_g, red_l, p2p_err);
+    note(cudaGetLastError(), "wait_sum");
   }
   template <class T> int64_t assign_rows(const EngineMem<T>& V, const EngineMem<T>& Mc) {
     k_scan_rows<<<1, 1024, 0, stream>>>(V.stage_active, Mc.stage_row, V.C, d_scal);

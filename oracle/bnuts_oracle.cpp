@@ -881,6 +881,8 @@ int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double*) { return e 
 // row sharding is a property of the device engine's data layout; the oracle always sees all rows
 int32_t bnuts_set_allreduce(bnuts_engine*, bnuts_allreduce_fn, void*) { return BNUTS_ERR_UNSUPPORTED; }
 int32_t bnuts_nccl_unique_id(uint8_t*) { return BNUTS_ERR_UNSUPPORTED; }
+int32_t bnuts_p2p_export(bnuts_engine*, uint8_t*) { return BNUTS_ERR_UNSUPPORTED; }
+int32_t bnuts_p2p_connect(bnuts_engine*, const uint8_t*, int32_t, int32_t) { return BNUTS_ERR_UNSUPPORTED; }
 int32_t bnuts_set_nccl(bnuts_engine*, const uint8_t*, int32_t, int32_t) { return BNUTS_ERR_UNSUPPORTED; }
 int32_t bnuts_set_positions(bnuts_engine* e, const double* q) { DISPATCH(e, set_positions(E, q), set_positions(E, q)); }
 int32_t bnuts_get_state(bnuts_engine* e, double* q, double* g, double* l) { DISPATCH(e, get_state(E, q, g, l), get_state(E, q, g, l)); }

@@ -20,6 +20,7 @@ ap.add_argument("--rows", type=int, default=2_000_000)
 ap.add_argument("--dim", type=int, default=100)
 ap.add_argument("--chains", type=int, default=4096)
 ap.add_argument("--transitions", type=int, default=8)
+ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
 a = ap.parse_args()
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -29,14 +30,19 @@ bits, y, beta = synth(N, D)
 lo, hi = rank * N // world, (rank + 1) * N // world
 e = bn.Engine(C, D, dtype=bn.F32, seed=20261018, device=local, gradient_path=bn.GRAD_TENSOR)
 e.model_logistic(bits[lo:hi], y[lo:hi], 1.0)
-ids = [bn.nccl_unique_id() if rank == 0 else None]
-dist.broadcast_object_list(ids, src=0)
-e.set_nccl(ids[0], world, rank)
+if a.exchange == "nccl":
+    ids = [bn.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    e.set_nccl(ids[0], world, rank)
+else:   # the library's own kernels over peer memory (NVLink stores + flags)
+    hs = [None] * world
+    dist.all_gather_object(hs, e.p2p_export())
+    e.p2p_connect(hs, rank)
 rng = np.random.default_rng(7)
 q0 = np.asarray(beta[None, :] + rng.normal(size=(C, D)) * 2e-3, dtype=np.float32).astype(np.float64)
 e.set_positions(q0)
 _, g, l = e.get_state()
-out = {"world": world, "rows_total": N, "rows_per_rank": hi - lo, "dim": D, "chains": C}
+out = {"exchange": a.exchange, "world": world, "rows_total": N, "rows_per_rank": hi - lo, "dim": D, "chains": C}
 if rank == 0:   # the same chains on one engine that holds every row
     f = bn.Engine(C, D, dtype=bn.F32, seed=20261018, device=local, gradient_path=bn.GRAD_TENSOR)
     f.model_logistic(bits, y, 1.0); f.set_positions(q0)

@@ -113,6 +113,11 @@ struct HostExec {
   // ---- row-sharded mode (same semantics as the CUDA policy, serial loops)
   static int32_t nccl_unique_id(uint8_t*) { return BNUTS_ERR_UNSUPPORTED; }
   int32_t nccl_init(const uint8_t*, int, int, std::string& err) { err = "NCCL is CUDA-only"; return BNUTS_ERR_UNSUPPORTED; }
+  int32_t p2p_export(size_t, size_t, uint8_t*, std::string& err) { err = "peer-memory exchange is CUDA-only"; return BNUTS_ERR_UNSUPPORTED; }
+  int32_t p2p_connect(const uint8_t*, int, int, std::string& err) { err = "peer-memory exchange is CUDA-only"; return BNUTS_ERR_UNSUPPORTED; }
+  bool p2p_failed() { return false; }
+  template <class T> void fold_push(const EngineMem<T>&, int, uint64_t) {}
+  template <class T> void wait_sum(const EngineMem<T>&, int, uint64_t, T*, double*) {}
   template <class T> int64_t assign_rows(const EngineMem<T>& V, const EngineMem<T>& Mc) {
     int64_t n = 0;
     for (int c = 0; c < V.C; ++c) {
