@@ -271,7 +271,12 @@ def main():
         "gpu_launches": int(launches),
         "leapfrogs_timed": int(leap),
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (ach / peak_tf) if ach else None, "traffic": None, "kernel": "k_logistic_tc",
+                     "frac": (ach / peak_tf) if ach else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
+                     # (profiles/r1_ncu_full_details_k_logistic_tc_4096rows.csv: 292.4 MB + 14.5 MB; X is read once per
+                     # launch whatever the number of active rows: 256 MB algorithmic)
+                     "traffic": 306.9e6 if (N == 1_000_000 and D == 100) else None, "traffic_unit": "bytes per launch (ncu, full 4096-row launch)",
+                     "kernel": "k_logistic_tc",
                      "launches": int(grad_n), "avg_launch_ms": grad_ms / max(grad_n, 1), "avg_rows_per_launch": rows / max(grad_n, 1), "peak_source": peak_src,
                      "kernel_share_of_step": grad_ms / ms},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(qh.nbytes), "d2h_bytes_per_step": int(chain.nbytes + stats.nbytes)},
