@@ -45,7 +45,8 @@ namespace bn {
 
 namespace {
 
-constexpr int TC_THREADS = 576;       // 2 control warps + 16 elementwise warps
+constexpr int TC_THREADS = 608;       // warp 0 TMA, warp 1 GEMM1 issuer, warps 2-17 elementwise, warp 18 GEMM2 issuer
+constexpr int G2_WARP = 18;
 constexpr int ROWS = 128;            // data rows per block (GEMM1 N, GEMM2 K)
 constexpr int CHAINS = 128;          // chains per CTA (MMA M)
 #include "tc_ptx.h"
@@ -69,7 +70,7 @@ __device__ __forceinline__ float2 rcp2(float2 d, bool sw) {
   }
 }
 #ifndef BNUTS_TC_RCPSW
-#define BNUTS_TC_RCPSW 0x00   // bit k set: pair k of every 8 pairs uses the FMA-pipe reciprocal
+#define BNUTS_TC_RCPSW 0x55   // bit k set: pair k of every 8 pairs uses the FMA-pipe reciprocal
 #endif
 constexpr int RCPSW = BNUTS_TC_RCPSW;
 #ifndef BNUTS_TC_DEBUG
@@ -80,13 +81,6 @@ constexpr int TCDBG = BNUTS_TC_DEBUG;
 #define BNUTS_TC_GROUPS 2     // elementwise warp groups: 1 = all 16 warps share every row block (one 32-column chunk
 #endif                        // each, lowest latency per block); 2 = two groups of 8 ping-pong over the blocks
 constexpr int NG = BNUTS_TC_GROUPS;
-#ifndef BNUTS_TC_ORDER
-#define BNUTS_TC_ORDER 1      // MMA issuer: 0 = all waits of an iteration first, then GEMM1(i+2) and GEMM2(i) back to back;
-#endif                        // 1 = GEMM1(i+2) is issued before waiting for the residual of block i
-constexpr int ORDER = BNUTS_TC_ORDER;
-// with several groups a warp waits for S of block i + NG before it publishes R of block i; GEMM1(i + 2) must
-// then not depend on that R (ORDER 0 would deadlock)
-static_assert(NG == 1 || ORDER == 1, "BNUTS_TC_GROUPS > 1 needs BNUTS_TC_ORDER = 1");
 constexpr int EW_PER_GROUP = 16 / NG;     // warps per group
 constexpr int CPW = NG;                   // 32-column chunks per warp and block
 // timing trace (debug builds only, -DBNUTS_TC_TRACE): CTA (0,0) records clock64() at fixed points of
@@ -111,7 +105,7 @@ template <int DT> struct SmemPlan {
   static constexpr int OFF_B = 0;                    // 3 terms
   static constexpr int OFF_X = 3 * B_BYTES;
   static constexpr int OFF_BAR = OFF_X + NS * X_BYTES;
-  static constexpr int NBAR = 1 + 2 * NS + 2 * NSB + 2;
+  static constexpr int NBAR = 1 + 2 * NS + 3 * NSB + 2;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
 };
 
@@ -138,7 +132,8 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint64_t* x_empty = x_full + NS;      // [NS]
   uint64_t* s_full = x_empty + NS;      // [NSB] GEMM1 done
   uint64_t* r_full = s_full + NSB;      // [NSB] residual written to TMEM
-  uint64_t* g_full = r_full + NSB;      // accumulator complete for its flush period
+  uint64_t* sr_empty = r_full + NSB;    // [NSB] GEMM2 done with the buffer (it may be overwritten by GEMM1)
+  uint64_t* g_full = sr_empty + NSB;    // accumulator complete for its flush period
   uint64_t* g_empty = g_full + 1;       // accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
 
@@ -153,7 +148,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (smem_u32(smem) & 1023u) asm volatile("trap;");
     mbar_init(bar_b, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 32 * EW_PER_GROUP); }
+    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 32 * EW_PER_GROUP); mbar_init(&sr_empty[i], 1); }
     mbar_init(g_full, 1);
     mbar_init(g_empty, 32 * EW_PER_GROUP);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -190,26 +185,31 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    // The whole warp runs this loop convergently so descriptors and addresses stay in uniform
-    // registers; only the tcgen05.mma / tcgen05.commit instructions are issued by lane 0.
+    // ===================================================== GEMM1 issuer
+    // Two warps issue the MMAs: this one GEMM1 (S = B·X̃ᵀ), warp G2_WARP GEMM2 (G += R·X̃).  Measured with one
+    // issuer: its own bookkeeping (barrier round trips, commits, descriptor set-up, ~1 100 clk per row block on
+    // top of ~1 800 clk of queue-throttled MMA issue) was as long as the elementwise stage, so small launches
+    // (one chain tile, little elementwise work) still ran at 1.9 us per block.  With two issuers each one's
+    // waits overlap the other's MMAs.  tcgen05.mma of DIFFERENT threads are not ordered by the hardware, so
+    // the re-use of an S/R buffer is ordered explicitly: GEMM2(i) commits sr_empty, GEMM1(i + NSB) waits for it.
+    // The whole warp runs convergently so descriptors stay in uniform registers; one elected lane issues.
     if (nb > 0) {
       constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
-      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
       const uint32_t aX = smem_u32(sX);
       // descriptor halves: the high words are constants, the low words carry the start address
-      const uint64_t dKM = desc_kmajor(0, 0), dMN = desc_mnmajor(0, 0);
+      const uint64_t dKM = desc_kmajor(0, 0);
       const uint32_t km_hi = (uint32_t)(dKM >> 32), km_lo0 = (uint32_t)dKM;
-      const uint32_t mn_hi = (uint32_t)(dMN >> 32), mn_lo0 = (uint32_t)dMN;
       uint32_t bB[3];
 #pragma unroll
       for (int term = 0; term < 3; ++term) bB[term] = km_lo0 + ((smem_u32(sB) + (uint32_t)term * P::B_BYTES) >> 4);
       mbar_wait(bar_b, 0);
-      // GEMM1 of block i: S[buf] = sum over terms of B_term · X_iᵀ.  No wait for the S/R buffer: its previous
-      // user is GEMM2(i - 3), issued earlier by this same thread, and tcgen05.mma instructions of one thread
-      // execute in issue order; the elementwise warps' accesses to it were ordered before that GEMM2 by r_full.
-      auto gemm1 = [&](int i) {
+      for (int i = 0; i < nb; ++i) {
         const int st = i % NS, buf = i % NSB;
+        TC_TRACE(1, i, 0);
+        mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
+        if (i >= NSB) mbar_wait(&sr_empty[buf], (uint32_t)(i / NSB - 1) & 1u);
+        TC_TRACE(1, i, 1);
+        tc_fence_after();
         const uint32_t xlo = km_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
         const uint32_t d = tmem_S + (uint32_t)buf * 128u;
 #pragma unroll
@@ -228,27 +228,25 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         TC_TRACE(1, i, 7);
         if (elect_one()) tc_commit(&s_full[buf]);
         TC_TRACE(1, i, 2);
-      };
-      auto wait_x = [&](int i) { mbar_wait(&x_full[i % NS], (uint32_t)(i / NS) & 1u); };
-      wait_x(0);
-      tc_fence_after();
-      gemm1(0);
-      if (nb > 1) { wait_x(1); tc_fence_after(); gemm1(1); }
+        __syncwarp();
+      }
+    }
+  } else if (warp == G2_WARP) {
+    // ===================================================== GEMM2 issuer
+    if (nb > 0) {
+      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t aX = smem_u32(sX);
+      const uint64_t dMN = desc_mnmajor(0, 0);
+      const uint32_t mn_hi = (uint32_t)(dMN >> 32), mn_lo0 = (uint32_t)dMN;
       int period = 0, in_period = 0;
       for (int i = 0; i < nb; ++i) {
-        // all waits of the iteration first, then GEMM1(i+2) and GEMM2(i) back to back, so the tensor
-        // pipe's queue stays fed while this thread does its bookkeeping
         const int st = i % NS, buf = i % NSB, u = i / NSB;
-        TC_TRACE(1, i, 0);
-        if (i + 2 < nb) wait_x(i + 2);
-        TC_TRACE(1, i, 1);
-        if (ORDER == 1 && i + 2 < nb) { tc_fence_after(); gemm1(i + 2); }
+        TC_TRACE(1, i, 3);
         mbar_wait(&r_full[buf], (uint32_t)u & 1u);
         TC_TRACE(1, i, 4);
         if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
         TC_TRACE(1, i, 5);
         tc_fence_after();
-        if (ORDER == 0 && i + 2 < nb) gemm1(i + 2);
         const uint32_t xm = mn_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
         const uint32_t a = tmem_S + (uint32_t)buf * 128u;
         const uint32_t acc0 = in_period > 0 ? 1u : 0u;
@@ -261,7 +259,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                         (term | hb) ? 1u : acc0);
           }
         TC_TRACE(1, i, 8);
-        if (elect_one()) tc_commit(&x_empty[st]);
+        if (elect_one()) { tc_commit(&x_empty[st]); tc_commit(&sr_empty[buf]); }
         TC_TRACE(1, i, 6);
         ++in_period;
         if (i + 1 == nb || in_period == fe) {
@@ -296,25 +294,40 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // Work items of this warp: (block i, chunk cc), i = grp, grp + NG, ..., cc < CPW.  The TMEM load of
     // the next item is issued before the stores / barrier traffic of the current one, so its latency
     // (and the s_full wait of the next block, normally already complete) is off the critical path.
+    // A warp whose 32 chains are all beyond the staged rows (last, partial tile) does no elementwise work: it
+    // only keeps the barrier protocol going, so the MUFU pipe and the issue slots go to the warps with real rows
+    // (garbage in the unused TMEM lanes stays in output rows nobody reads: a lane is a chain in both GEMMs).
+    const bool live = (tile * CHAINS + q * 32) < nrows;
     uint32_t v[32];
-    auto load_item = [&](int i, int cc) {
+    // `blocking = false`: only if S of that block is already there (the load is then a pure prefetch).  Waiting
+    // here for S(i + NG) BEFORE publishing R(i) would chain every block's hand-off to the GEMM1 of a later block
+    // (measured with the clock64 trace: 1 700 clk per block lost in exactly that wait).
+    auto load_item = [&](int i, int cc, bool blocking) -> bool {
       const int buf = i % NSB, u = i / NSB;
       if (cc == 0) {
-        if (warp == 2) TC_TRACE(2, i, 0);
-        mbar_wait(&s_full[buf], (uint32_t)u & 1u);
-        if (warp == 2) TC_TRACE(2, i, 1);
+        if (!blocking) {
+          if (!mbar_test(&s_full[buf], (uint32_t)u & 1u)) return false;
+        } else {
+          if (warp == 2) TC_TRACE(2, i, 0);
+          mbar_wait(&s_full[buf], (uint32_t)u & 1u);
+          if (warp == 2) TC_TRACE(2, i, 1);
+        }
         tc_fence_after();
       }
       tmem_ld32(tmem_S + (uint32_t)buf * 128u + lane_sel + (uint32_t)(CPW * h + cc) * 32u, v);
+      return true;
     };
-    if (grp < nb && !(TCDBG & 1)) load_item(grp, 0);
+    bool have_next = false;
+    if (grp < nb && !(TCDBG & 1) && live) have_next = load_item(grp, 0, true);
     for (int i = grp; i < nb; i += NG) {
       const int buf = i % NSB;
       float bsum = 0.f;   // sum over this thread's elements of  log2(1 + 2^-|u|)
       float asum = 0.f;   // sum of |eta|
+      if (!live) mbar_wait(&s_full[buf], (uint32_t)(i / NSB) & 1u);   // stay in phase with the buffer, then just arrive
 #pragma unroll 1
-      for (int cc = 0; cc < ((TCDBG & 1) ? 0 : CPW); ++cc) {
+      for (int cc = 0; cc < (((TCDBG & 1) || !live) ? 0 : CPW); ++cc) {
         const int ch = CPW * h + cc;
+        if (!have_next) have_next = load_item(i, cc, true);
         const uint32_t tS = tmem_S + (uint32_t)buf * 128u + lane_sel + (uint32_t)ch * 32u;
         if (warp == 2) TC_TRACE(2, i, 3);
         tmem_ld_wait();
@@ -344,9 +357,10 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         bsum += lg2_approx(prod.x * prod.y);
         asum += as0 + as1;
         if (warp == 2) TC_TRACE(2, i, 5);
-        // next item's S -> registers (v is dead now)
-        if (cc + 1 < CPW) load_item(i, cc + 1);
-        else if (i + NG < nb) load_item(i + NG, 0);
+        // next item's S -> registers (v is dead now): always within the block, across blocks only if it is ready
+        have_next = false;
+        if (cc + 1 < CPW) have_next = load_item(i, cc + 1, true);
+        else if (i + NG < nb) have_next = load_item(i + NG, 0, false);
         tmem_st16(tS, hi);
         tmem_st16(tS + 16u, lo);
       }
@@ -368,7 +382,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll 1
         for (int cc = 0; cc < CPW; ++cc) {
           const int ch = CPW * h + cc;
-          if (ch * 32 < dk) {
+          if (ch * 32 < dk && live) {
             uint32_t w[32];
             tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, w);
             tmem_ld_wait();
