@@ -73,6 +73,9 @@ __device__ __forceinline__ float2 rcp2(float2 d, bool sw) {
 #define BNUTS_TC_RCPSW 0x55   // bit k set: pair k of every 8 pairs uses the FMA-pipe reciprocal
 #endif
 constexpr int RCPSW = BNUTS_TC_RCPSW;
+#ifndef BNUTS_TC_PREFETCH
+#define BNUTS_TC_PREFETCH 0   // measured: no gain (2.98-3.07 ms without, 3.01 ms with), the 4 X stages already cover the HBM latency
+#endif
 #ifndef BNUTS_TC_DEBUG
 #define BNUTS_TC_DEBUG 0      // timing experiments only (results are wrong): 1 skip elementwise, 2 skip GEMM1, 4 skip GEMM2
 #endif
@@ -173,9 +176,14 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         tma_load_2d(&tmBm, sB + 1 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
         tma_load_2d(&tmBl, sB + 2 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
       }
+      constexpr int PF = BNUTS_TC_PREFETCH;   // L2 prefetch distance in row blocks (0: none)
+      for (int i = 0; i < PF && i < nb; ++i)
+        for (int kc = 0; kc < KC; ++kc) tma_prefetch_2d(&tmX, kc * 64, (b0 + i) * ROWS);
       for (int i = 0; i < nb; ++i) {
         const int st = i % NS;
         const uint32_t ph = (uint32_t)(i / NS) & 1u;
+        if (PF > 0 && i + PF < nb)
+          for (int kc = 0; kc < KC; ++kc) tma_prefetch_2d(&tmX, kc * 64, (b0 + i + PF) * ROWS);
         TC_TRACE(0, i, 0);
         mbar_wait(&x_empty[st], ph ^ 1u);
         TC_TRACE(0, i, 1);
@@ -443,6 +451,346 @@ template <int DT, int NK> void launch(LogisticTC& tc, cudaStream_t s, int nrows,
                                                            (int)(tc.Npad / ROWS), nsplit, tc.flush_every, tc.nterms);
 }
 
+
+// =====================================================================================================
+// Variant with 64-row blocks and the position operand resident in TMEM (k_logistic_tc64).
+//
+// Why: the loop S -> elementwise -> R -> GEMM2 -> buffer free -> GEMM1 is several thousand cycles long and the
+// 128-row kernel above has only three S/R buffers for it (TMEM and shared memory are full).  Here the chains'
+// β terms are loaded ONCE into TMEM (lane = chain, 8 columns per K step: the A-operand layout the residual
+// already uses) so GEMM1 takes A from TMEM: shared memory holds only X̃ stages (12 x 16 KB instead of 4 x 32 KB
+// + 96 KB of β tiles), an N = 64 MMA no longer re-reads a 4 KB A tile from shared memory (the SS form would be
+// shared-memory bound at N = 64), and the S/R buffers shrink to 64 columns: four of them (two-term mode) or
+// three (three-term mode) fit next to G and β.  Same arithmetic, same barriers, finer-grained pipeline.
+constexpr int ROWS2 = 64;
+constexpr int CHUNK2 = ROWS2 * 128;   // 64 rows x 64 bf16, one SW128 box
+template <int DT> struct SmemPlan2 {
+  static constexpr int KC = DT / 64;
+  static constexpr int X_BYTES = KC * CHUNK2;
+  static constexpr int NS = (DT == 128) ? 12 : 16;   // X stages
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_BAR = NS * X_BYTES;
+  static constexpr int NBAR = 1 + 2 * NS + 3 * 4 + 2;
+  static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
+};
+// GEMM1, A from TMEM: N4 consecutive K steps; A advances 8 TMEM columns, B 32 B (2 descriptor units)
+#define BN_MMA_TSK(ACC) "mov.b64 rb, {bl, %3};\n\t@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], rb, %4, " ACC ";\n\t"
+#define BN_TSK_HEAD "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 rb;\n\t.reg .b32 ta, bl;\n\t" \
+                    "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\tmov.b32 ta, %1;\n\tmov.b32 bl, %2;\n\t"
+#define BN_TSK_STEP "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 2;\n\t"
+#define BN_TSK_ARGS ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory"
+template <int N4>
+__device__ __forceinline__ void mma_tsk_run(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t acc_first) {
+  static_assert(N4 >= 1 && N4 <= 4, "1..4 K steps per chunk");
+  if constexpr (N4 == 1)
+    asm volatile(BN_TSK_HEAD BN_MMA_TSK("pa") "}\n" BN_TSK_ARGS);
+  else if constexpr (N4 == 2)
+    asm volatile(BN_TSK_HEAD BN_MMA_TSK("pa") BN_TSK_STEP BN_MMA_TSK("pt") "}\n" BN_TSK_ARGS);
+  else if constexpr (N4 == 3)
+    asm volatile(BN_TSK_HEAD BN_MMA_TSK("pa") BN_TSK_STEP BN_MMA_TSK("pt") BN_TSK_STEP BN_MMA_TSK("pt") "}\n" BN_TSK_ARGS);
+  else
+    asm volatile(BN_TSK_HEAD BN_MMA_TSK("pa") BN_TSK_STEP BN_MMA_TSK("pt") BN_TSK_STEP BN_MMA_TSK("pt") BN_TSK_STEP BN_MMA_TSK("pt") "}\n"
+                 BN_TSK_ARGS);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+template <int DT, int NK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_logistic_tc64(const __grid_constant__ CUtensorMap tmX, const uint16_t* __restrict__ bh, const uint16_t* __restrict__ bm,
+                const uint16_t* __restrict__ bl, int Dt, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total,
+                int nsplit, int flush_every, int nterms) {
+  using P = SmemPlan2<DT>;
+  constexpr int dk = NK * 16;
+  constexpr int NS = P::NS;
+  constexpr int KC = P::KC;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sX = smem + P::OFF_X;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
+  uint64_t* bar_b = bars;               // β terms written to TMEM
+  uint64_t* x_full = bars + 1;          // [NS]
+  uint64_t* x_empty = x_full + NS;      // [NS]
+  uint64_t* s_full = x_empty + NS;      // [4] GEMM1 done
+  uint64_t* r_full = s_full + 4;        // [4] residual written to TMEM
+  uint64_t* sr_empty = r_full + 4;      // [4] GEMM2 done with the buffer
+  uint64_t* g_full = sr_empty + 4;
+  uint64_t* g_empty = g_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int b0 = (int)(((long long)nblk_total * split) / nsplit);
+  const int b1 = (int)(((long long)nblk_total * (split + 1)) / nsplit);
+  const int nb = b1 - b0;
+  const int fe = flush_every > 0 ? 2 * flush_every : 0x7fffffff;   // flush period in 64-row blocks
+  // TMEM map (columns): G [0, dk) | β term t [128 + t dk/2, ...) | S/R buffer b [SB0 + 64 b, ...)
+  const int SB0 = (128 + nterms * (dk / 2) + 63) & ~63;
+  const int nsb = (512 - SB0) / 64 >= 4 ? 4 : 3;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) asm volatile("trap;");
+    mbar_init(bar_b, 128);
+    for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 256); mbar_init(&sr_empty[i], 1); }
+    mbar_init(g_full, 1);
+    mbar_init(g_empty, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_G = tmem;
+  const uint32_t tmem_B = tmem + 128u;
+  const uint32_t tmem_S = tmem + (uint32_t)SB0;
+  // buffer and phase of block i without runtime divisions (nsb is 3 or 4)
+  auto buf_of = [&](int i) { return nsb == 4 ? (i & 3) : (i % 3); };
+  auto round_of = [&](int i) { return nsb == 4 ? (i >> 2) : (i / 3); };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0 && nb > 0) {
+      constexpr int PF = 16;   // L2 prefetch distance in row blocks
+      for (int i = 0; i < PF && i < nb; ++i)
+        for (int kc = 0; kc < KC; ++kc) tma_prefetch_2d(&tmX, kc * 64, (b0 + i) * ROWS2);
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS;
+        const uint32_t ph = (uint32_t)(i / NS) & 1u;
+        if (i + PF < nb)
+          for (int kc = 0; kc < KC; ++kc) tma_prefetch_2d(&tmX, kc * 64, (b0 + i + PF) * ROWS2);
+        mbar_wait(&x_empty[st], ph ^ 1u);
+        mbar_expect_tx(&x_full[st], P::X_BYTES);
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK2, &x_full[st], kc * 64, (b0 + i) * ROWS2);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== GEMM1 issuer: S[buf] = β (TMEM) · X̃_iᵀ (smem, K-major)
+    if (nb > 0) {
+      constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS2 >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t aX = smem_u32(sX);
+      const uint64_t dKM = desc_kmajor(0, 0);
+      const uint32_t km_hi = (uint32_t)(dKM >> 32), km_lo0 = (uint32_t)dKM;
+      mbar_wait(bar_b, 0);
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS, buf = buf_of(i), rnd = round_of(i);
+        mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
+        if (rnd >= 1) mbar_wait(&sr_empty[buf], (uint32_t)(rnd - 1) & 1u);
+        tc_fence_after();
+        const uint32_t xlo = km_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
+        const uint32_t d = tmem_S + (uint32_t)buf * 64u;
+#pragma unroll
+        for (int term = 0; term < 3; ++term)
+          if (term < nterms) {
+#pragma unroll
+            for (int c = 0; c < (NK + 3) / 4; ++c) {
+              constexpr int LAST = NK - ((NK + 3) / 4 - 1) * 4;
+              const uint32_t a = tmem_B + (uint32_t)(term * (dk / 2) + c * 32);
+              const uint32_t b = xlo + (uint32_t)(c * (CHUNK2 >> 4));
+              const uint32_t acc = (term | c) ? 1u : 0u;
+              if (c + 1 < (NK + 3) / 4) mma_tsk_run<4>(d, a, b, km_hi, IDESC1, acc);
+              else mma_tsk_run<LAST>(d, a, b, km_hi, IDESC1, acc);
+            }
+          }
+        if (elect_one()) tc_commit(&s_full[buf]);
+        __syncwarp();
+      }
+    }
+  } else if (warp == G2_WARP) {
+    // ===================================================== GEMM2 issuer: G += R (TMEM) · X̃_i (smem, MN-major)
+    if (nb > 0) {
+      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t aX = smem_u32(sX);
+      const uint64_t dMN = make_desc(0, (uint32_t)CHUNK2, 1024u);   // 64-column chunks are CHUNK2 apart
+      const uint32_t mn_hi = (uint32_t)(dMN >> 32), mn_lo0 = (uint32_t)dMN;
+      int period = 0, in_period = 0;
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS, buf = buf_of(i), rnd = round_of(i);
+        mbar_wait(&r_full[buf], (uint32_t)rnd & 1u);
+        if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
+        tc_fence_after();
+        const uint32_t xm = mn_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
+        const uint32_t a = tmem_S + (uint32_t)buf * 64u;
+        const uint32_t acc0 = in_period > 0 ? 1u : 0u;
+#pragma unroll
+        for (int term = 0; term < 2; ++term)
+          mma_ts_run4(tmem_G, a + (uint32_t)(term * 16), xm, mn_hi, IDESC2, term ? 1u : acc0);
+        if (elect_one()) { tc_commit(&x_empty[st]); tc_commit(&sr_empty[buf]); }
+        ++in_period;
+        if (i + 1 == nb || in_period == fe) {
+          if (elect_one()) tc_commit(g_full);
+          ++period;
+          in_period = 0;
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================== elementwise + epilogue (16 warps, two groups of 8)
+    const int ew = warp - 2;
+    const int grp = ew >> 3;
+    const int h = (ew >> 2) & 1;                      // 32-column half of the 64-row block
+    const int q = warp & 3;
+    const int row = tile * CHAINS + q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool live = (tile * CHAINS + q * 32) < nrows;
+    // ---- position operand -> TMEM, once: lane = chain, word w of term t = bf16 pair (k = 2w, 2w + 1)
+    if (ew < 4) {
+      const uint16_t* src[3] = {bh, bm, bl};
+      for (int t = 0; t < nterms; ++t) {
+        const uint4* p = reinterpret_cast<const uint4*>(src[t] + (size_t)row * Dt);
+#pragma unroll 1
+        for (int w8 = 0; w8 < dk / 16; ++w8) {       // 8 words = 16 bf16 = one K step per iteration
+          uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+          if (row < nrows) { a = p[2 * w8]; b = p[2 * w8 + 1]; }
+          const uint32_t r8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          tmem_st8(tmem_B + lane_sel + (uint32_t)(t * (dk / 2) + w8 * 8), r8);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_b);
+    }
+    double lsum = 0.0;
+    const float2 L2E2 = make_float2(1.4426950408889634f, 1.4426950408889634f);
+    const float2 ONE2 = make_float2(1.0f, 1.0f), MHALF2 = make_float2(-0.5f, -0.5f), HALF2 = make_float2(0.5f, 0.5f);
+    const float2 MONE2 = make_float2(-1.0f, -1.0f);
+    const float LN2 = 0.6931471805599453f;
+    float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
+    int fpos = grp, fper = 0;
+    while (fpos >= fe) { fpos -= fe; ++fper; }
+    uint32_t v[32];
+    auto load_item = [&](int i, bool blocking) -> bool {
+      const int buf = buf_of(i), rnd = round_of(i);
+      if (!blocking) {
+        if (!mbar_test(&s_full[buf], (uint32_t)rnd & 1u)) return false;
+      } else {
+        mbar_wait(&s_full[buf], (uint32_t)rnd & 1u);
+      }
+      tc_fence_after();
+      tmem_ld32(tmem_S + (uint32_t)buf * 64u + lane_sel + (uint32_t)h * 32u, v);
+      return true;
+    };
+    bool have_next = false;
+    if (grp < nb && live) have_next = load_item(grp, true);
+    for (int i = grp; i < nb; i += 2) {
+      const int buf = buf_of(i);
+      float bsum = 0.f, asum = 0.f;
+      if (!live) {
+        mbar_wait(&s_full[buf], (uint32_t)round_of(i) & 1u);
+      } else {
+        if (!have_next) have_next = load_item(i, true);
+        const uint32_t tS = tmem_S + (uint32_t)buf * 64u + lane_sel + (uint32_t)h * 32u;
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+        float2 prod = ONE2;
+        float as0 = 0.f, as1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float e0 = __uint_as_float(v[2 * j]), e1 = __uint_as_float(v[2 * j + 1]);
+          const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
+          const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
+          prod = __fmul2_rn(prod, d2);
+          as0 += fabsf(e0); as1 += fabsf(e1);
+          const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
+          const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
+                                        __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
+          const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
+          const uint32_t hh = pack_bf16(r2.x, r2.y);
+          const float2 hv = make_float2(__uint_as_float(hh << 16), __uint_as_float(hh & 0xffff0000u));
+          const float2 l2 = __ffma2_rn(hv, MONE2, r2);
+          hi[j] = hh;
+          lo[j] = pack_bf16(l2.x, l2.y);
+        }
+        bsum = lg2_approx(prod.x * prod.y);
+        asum = as0 + as1;
+        have_next = false;
+        if (i + 2 < nb) have_next = load_item(i + 2, false);
+        tmem_st16(tS, hi);
+        tmem_st16(tS + 16u, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&r_full[buf]);
+      lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);
+      const bool closes = (i + 1 == nb) || (fpos == fe - 1);
+      const int period = fper;
+      fpos += 2;
+      while (fpos >= fe) { fpos -= fe; ++fper; }
+      if (closes) {
+        mbar_wait(g_full, (uint32_t)period & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ch = 2 * h + cc;
+          if (ch * 32 < dk && live) {
+            uint32_t w[32];
+            tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, w);
+            tmem_ld_wait();
+            if (row < nrows) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const int d = ch * 32 + j;
+                if (d < dk && d < Dp) {
+                  float4 a = make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]), __uint_as_float(w[j + 2]),
+                                         __uint_as_float(w[j + 3]));
+                  float4* gp = reinterpret_cast<float4*>(gout + d);
+                  if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+                  *gp = a;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(g_empty);
+      }
+    }
+    // rows >= N of the last block are zero padding: eta = 0 -> each contributed -log 2 (once per row: column half 0)
+    if (h == 0 && nb > 0 && grp == ((nb - 1) & 1) && b1 == nblk_total)
+      lsum += (double)((long long)nblk_total * ROWS2 - N) * 0.6931471805599453;
+    double* lp = reinterpret_cast<double*>(sX);   // X stages are dead by now
+    const int part = grp * 2 + h;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (part > 0) lp[(part - 1) * 128 + q * 32 + lane] = lsum;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (part == 0 && row < nrows) {
+      if (nb == 0) for (int d = 0; d < Dp; ++d) gout[d] = 0.f;
+      const int k = q * 32 + lane;
+      Ld[(size_t)split * nrows + row] = ((lsum + lp[k]) + lp[128 + k]) + lp[256 + k];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+template <int DT, int NK> void launch64(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
+  using P = SmemPlan2<DT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    tc.last = cudaFuncSetAttribute(k_logistic_tc64<DT, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    attr_done = true;
+  }
+  const int tiles = (nrows + CHAINS - 1) / CHAINS;
+  dim3 grid(tiles, nsplit);
+  CUtensorMap m;
+  std::memcpy(&m, tc.tmaps[4], sizeof(CUtensorMap));
+  k_logistic_tc64<DT, NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m, tc.bh, tc.bm, tc.bl, tc.Dt, tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
+                                                            (int)(tc.Npad / ROWS2), nsplit, tc.flush_every, tc.nterms);
+}
+
 }  // namespace
 
 // number of row splits for `nrows` active rows: fill the SMs in as few full waves as possible
@@ -465,6 +813,19 @@ int LogisticTC::plan_splits(int nrows) const {
 void LogisticTC::run(cudaStream_t s, int nrows) {
   if (!ready || nrows <= 0) return;
   last_nsplit = plan_splits(nrows);
+  if (variant == 64) {
+    switch (dk / 16) {
+      case 1: launch64<64, 1>(*this, s, nrows, last_nsplit); break;
+      case 2: launch64<64, 2>(*this, s, nrows, last_nsplit); break;
+      case 3: launch64<64, 3>(*this, s, nrows, last_nsplit); break;
+      case 4: launch64<64, 4>(*this, s, nrows, last_nsplit); break;
+      case 5: launch64<128, 5>(*this, s, nrows, last_nsplit); break;
+      case 6: launch64<128, 6>(*this, s, nrows, last_nsplit); break;
+      case 7: launch64<128, 7>(*this, s, nrows, last_nsplit); break;
+      default: launch64<128, 8>(*this, s, nrows, last_nsplit); break;
+    }
+    return;
+  }
   switch (dk / 16) {
     case 1: launch<64, 1>(*this, s, nrows, last_nsplit); break;
     case 2: launch<64, 2>(*this, s, nrows, last_nsplit); break;
@@ -584,6 +945,9 @@ int32_t logistic_tc_maps(LogisticTC& tc, std::string& err) {
     err = "cuTensorMapEncodeTiled failed";
     return BNUTS_ERR_CUDA;
   }
+  if (!encode_map(tc.tmaps[4], tc.Xb, (uint64_t)tc.Npad, (uint64_t)tc.Dt, 64)) { err = "cuTensorMapEncodeTiled failed"; return BNUTS_ERR_CUDA; }
+  const char* ve = std::getenv("BNUTS_TC_VARIANT");
+  if (ve) tc.variant = std::atoi(ve);
   tc.ready = true;
   return 0;
 }

@@ -31,7 +31,8 @@ struct LogisticTC {
   float* G = nullptr;        // [nsplit][rows][Dp]
   double* Ld = nullptr;      // [nsplit][C] log-density partials (Float64: ~1e5..1e6 in magnitude)
   // opaque tensor maps (4 x CUtensorMap, 128 B each, 64 B aligned): X, βh, βm, βl
-  alignas(64) unsigned char tmaps[4][128];
+  alignas(64) unsigned char tmaps[5][128];   // X (128-row box), βh, βm, βl, X (64-row box)
+  int32_t variant = 128;     // 128: k_logistic_tc (β in shared memory, 128-row blocks); 64: k_logistic_tc64 (β in TMEM, 64-row blocks)
   bool ready = false;
   cudaError_t last = cudaSuccess;
 

@@ -59,6 +59,10 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, void* dst, uint64_
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a tile a few blocks ahead of its load, so the load itself never waits on HBM
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -212,12 +216,12 @@ EncodeTiledFn get_encode() {
 }
 
 // bf16 matrix [rows][cols] row-major, box = 128 rows x 64 columns, 128-byte swizzle
-bool encode_map(void* out, const void* base, uint64_t rows, uint64_t cols) {
+bool encode_map(void* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows = 128) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -1,3 +1,4 @@
-for v in g1r0x00 g1r0x55 g2r0x00 g2r0x55; do
-BNUTS_LIB=build/libbnuts_$v.so REF=1 CS=4096,128 timeout 120 python scripts/gpu_kernel_time.py 2>&1 | tail -2
-done
+for rep in 1 2; do
+for lib in "" build/libbnuts_pf0.so; do
+BNUTS_LIB=$lib REF=1 CS=4096,512 timeout 120 python scripts/gpu_kernel_time.py 2>&1 | tail -2
+done; done

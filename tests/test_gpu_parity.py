@@ -162,6 +162,21 @@ def test_tensor_reference_point(bn, oracle_lib, cuda_lib):
     assert g3c.tobytes() == g3.tobytes()
 
 
+def test_tensor_variant_64_row_blocks(bn, oracle_lib, cuda_lib, monkeypatch):
+    """k_logistic_tc64 (beta operand resident in TMEM, 64-row blocks): same tolerance as the default kernel."""
+    monkeypatch.setenv("BNUTS_TC_VARIANT", "64")
+    for (N, D, C) in [(3000, 100, 200), (200, 17, 5), (700, 128, 130)]:
+        X, y, beta = make_logistic(N, D)
+        rng = np.random.default_rng(1)
+        q = _f32(beta[None, :] + rng.normal(size=(C, D)) * 0.3)
+        ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0, row_blocks=1); ref.set_positions(q)
+        tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0); tc.set_positions(q)
+        _, g0, l0 = ref.get_state(); _, g1, l1 = tc.get_state()
+        assert np.max(_rel(g1, g0)) < TOL32 and np.max(np.abs(l1 - l0) / np.abs(l0)) < TOL32
+        if D + 3 <= 128:
+            tc.logistic_set_reference(None)
+
+
 def test_tensor_per_leapfrog_parity(bn, oracle_lib, cuda_lib):
     N, D, C = 3000, 100, 256
     X, y, beta = make_logistic(N, D)
