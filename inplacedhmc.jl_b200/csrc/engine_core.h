@@ -452,6 +452,7 @@ template <class T, class X> struct EngineCore {
   int32_t run_pipelined(bool pending) {
     constexpr int LAG = 2;
     int64_t np_known = pending ? x.read_count() : -1;   // -1: nothing known yet (first step has no gradient)
+    x.reset_counters();
     int64_t step = 0, completed = -1;
     bool first = !pending;
     for (;;) {
@@ -460,7 +461,7 @@ template <class T, class X> struct EngineCore {
         M.stage_rows = (int32_t)np_known;
         counters.kernel_launches += 1;
       }
-      x.advance_async(M, rp, 1, (int)(step % X::RING));
+      x.advance_async(M, rp, 1, (int)(step % X::RING), (int)(step & 1));
       counters.kernel_launches += 1;
       counters.lockstep_steps += 1;
       ++step;

@@ -39,6 +39,33 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(EngineMem<T> M, RunPara
   if (p && lane == 0 && !M.stage_q) atomicAdd(pending, 1ull);  // batched targets count through take_row()
 }
 
+// Same, for the pipelined run loop: no memset / copy / event around it.  The request counter alternates between
+// two device words (this launch counts into `cnt` and clears `cnt_next` for the following one); the last CTA to
+// finish publishes {sequence number, count} into a pinned, device-mapped host word the host polls.
+template <class T>
+__global__ void __launch_bounds__(ADV_THREADS) k_advance_ring(EngineMem<T> M, RunParams<T> rp, int iters, unsigned long long* cnt,
+                                                              unsigned long long* cnt_next, unsigned int* done,
+                                                              volatile unsigned long long* host_slot, unsigned int seq) {
+  const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (c < M.C) {
+    const int lane = (int)(threadIdx.x & 31);
+    const bool p = advance_chain(M, rp, c, WarpLanes{lane}, iters);
+    if (p && lane == 0 && !M.stage_q) atomicAdd(cnt, 1ull);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(done, 1u);
+    if (ticket == gridDim.x - 1) {
+      const unsigned long long n = atomicAdd(cnt, 0ull);
+      *cnt_next = 0ull;
+      *done = 0u;
+      __threadfence_system();
+      *host_slot = ((unsigned long long)seq << 32) | (n & 0xffffffffull);
+    }
+  }
+}
+
 template <class T> __global__ void __launch_bounds__(ADV_THREADS) k_metric(EngineMem<T> M, int N, double lambda) {
   const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (c >= M.C) return;
@@ -500,7 +527,8 @@ struct CudaExec {
     if (d_scal) cudaFree(d_scal);
     if (h_scal) cudaFreeHost(h_scal);
     if (d_status) cudaFree(d_status);
-    if (h_ring) { cudaFreeHost(h_ring); for (int i = 0; i < RING; ++i) cudaEventDestroy(ring_ev[i]); h_ring = nullptr; }
+    if (h_ring) { cudaFreeHost(const_cast<unsigned long long*>(h_ring)); h_ring = nullptr; }
+    if (d_done) cudaFree(d_done);
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
   }
   template <class U> U* alloc(size_t n) {
@@ -539,26 +567,46 @@ struct CudaExec {
     note(cudaMemsetAsync(d_scal, 0, sizeof(unsigned long long), stream), "memset");
     k_prepare<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, a);
   }
-  // ---- pipelined run loop (engine_core.h run_pipelined): request counts return through a ring of pinned slots
+  // ---- pipelined run loop (engine_core.h run_pipelined): request counts return through a ring of pinned,
+  // device-mapped host words written by the last CTA of k_advance_ring; two stream operations per lockstep step
+  // (gradient kernel, k_advance_ring), no memset, no copy, no event
   static constexpr int RING = 4;
-  unsigned long long* h_ring = nullptr;   // pinned [RING]
-  cudaEvent_t ring_ev[RING] = {};
-  template <class T> void advance_async(const EngineMem<T>& M, const RunParams<T>& rp, int iters, int slot) {
+  volatile unsigned long long* h_ring = nullptr;   // pinned + mapped [RING]
+  unsigned long long* d_ring = nullptr;            // device alias of h_ring
+  unsigned int* d_done = nullptr;
+  unsigned int ring_seq = 0, ring_expect[RING] = {};
+  template <class T> void advance_async(const EngineMem<T>& M, const RunParams<T>& rp, int iters, int slot, int parity) {
     if (!h_ring) {
-      note(cudaMallocHost(&h_ring, RING * sizeof(unsigned long long)), "cudaMallocHost");
-      for (int i = 0; i < RING; ++i) note(cudaEventCreateWithFlags(&ring_ev[i], cudaEventDisableTiming), "event create");
+      void* hp = nullptr; void* dp = nullptr;
+      note(cudaHostAlloc(&hp, RING * sizeof(unsigned long long), cudaHostAllocMapped), "cudaHostAlloc");
+      note(cudaHostGetDevicePointer(&dp, hp, 0), "cudaHostGetDevicePointer");
+      h_ring = static_cast<volatile unsigned long long*>(hp); d_ring = static_cast<unsigned long long*>(dp);
+      for (int i = 0; i < RING; ++i) h_ring[i] = 0ull;
+      note(cudaMalloc(&d_done, sizeof(unsigned int)), "cudaMalloc");
+      note(cudaMemsetAsync(d_done, 0, sizeof(unsigned int), stream), "memset");
     }
-    note(cudaMemsetAsync(d_scal, 0, sizeof(unsigned long long), stream), "memset");
-    k_advance<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, iters, d_scal);
+    ring_seq += 1;
+    if (ring_seq == 0) ring_seq = 1;
+    ring_expect[slot] = ring_seq;
+    EngineMem<T> Ml = M;
+    Ml.stage_count = d_scal + parity;
+    k_advance_ring<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(Ml, rp, iters, d_scal + parity, d_scal + (parity ^ 1), d_done,
+                                                                  d_ring + slot, ring_seq);
     note(cudaGetLastError(), "k_advance");
-    note(cudaMemcpyAsync(h_ring + slot, d_scal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "pending d2h");
-    note(cudaEventRecord(ring_ev[slot], stream), "event record");
   }
-  bool count_ready(int slot) { return cudaEventQuery(ring_ev[slot]) == cudaSuccess; }
+  bool count_ready(int slot) { return (unsigned int)(h_ring[slot] >> 32) == ring_expect[slot]; }
   int64_t count_wait(int slot) {
-    note(cudaEventSynchronize(ring_ev[slot]), "count wait");
-    return first_err == cudaSuccess ? (int64_t)h_ring[slot] : 0;
+    for (unsigned long long spins = 0; !count_ready(slot); ++spins) {
+      if ((spins & 0xfff) == 0xfff) {                 // the kernel may have faulted: never spin on a dead stream
+        const cudaError_t e = cudaStreamQuery(stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) { note(e, "k_advance"); return 0; }
+        if (e == cudaSuccess && !count_ready(slot)) { note(cudaErrorUnknown, "request count never arrived"); return 0; }
+      }
+    }
+    return first_err == cudaSuccess ? (int64_t)(h_ring[slot] & 0xffffffffull) : 0;
   }
+  // both counter words clear at the start of a run
+  void reset_counters() { note(cudaMemsetAsync(d_scal, 0, 2 * sizeof(unsigned long long), stream), "memset"); }
   bool failed() const { return first_err != cudaSuccess; }
   template <class T> int64_t advance(const EngineMem<T>& M, const RunParams<T>& rp, int iters) {
     note(cudaMemsetAsync(d_scal, 0, sizeof(unsigned long long), stream), "memset");

@@ -47,9 +47,10 @@ struct HostExec {
   // pipelined run loop: on the host every count is available at once (same control flow, no lag)
   static constexpr int RING = 4;
   int64_t ring[RING] = {};
-  template <class T> void advance_async(const EngineMem<T>& M, const RunParams<T>& rp, int iters, int slot) {
+  template <class T> void advance_async(const EngineMem<T>& M, const RunParams<T>& rp, int iters, int slot, int) {
     ring[slot] = advance(M, rp, iters);
   }
+  void reset_counters() {}
   bool count_ready(int) { return true; }
   int64_t count_wait(int slot) { return ring[slot]; }
   bool failed() const { return false; }
