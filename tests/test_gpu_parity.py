@@ -262,3 +262,37 @@ def test_cuda_sampling_moments_funnel_free_running(bn, cuda_lib):
     assert abs(v.mean()) < 0.8 and 2.2 < v.std() < 3.5
     c = e.counters()
     assert c["leapfrogs"] >= st["steps"].sum() and c["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_row_sharded_machinery_single_rank(bn, cuda_lib, exchange):
+    """A group of one: deterministic row assignment (scan + gather), folded partials and the exchange kernels /
+    NCCL call run on one GPU; results must equal the ordinary engine up to the association of the fold
+    (the 2-GPU run is scripts/gpu_c5.py, measured in profiles/)."""
+    N, D, C = 6000, 100, 300
+    X, y, beta = make_logistic(N, D)
+    rng = np.random.default_rng(12)
+    q = _f32(beta[None, :] + rng.normal(size=(C, D)) * 0.05)
+    outs = []
+    for sharded in (False, True):
+        e = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR, seed=4, max_depth=6)
+        e.model_logistic(X, y, 1.0)
+        if sharded and exchange == "nccl":
+            try:
+                e.set_nccl(bn.nccl_unique_id(cuda_lib), 1, 0)
+            except bn.BnutsError as ex:
+                pytest.skip(f"NCCL not loadable here: {ex}")
+        elif sharded:
+            e.p2p_connect([e.p2p_export()], 0)
+        e.set_positions(q)
+        _, g, l = e.get_state()
+        e.set_stepsize(0.01)
+        ch, st = e.sample(4)
+        outs.append((g, l, ch, st))
+        e.close()
+    (g0, l0, ch0, st0), (g1, l1, ch1, st1) = outs
+    assert np.max(_rel(g1, g0)) < 1e-6 and np.max(np.abs(l1 - l0) / np.abs(l0)) < 1e-7
+    same = (st0["steps"] == st1["steps"]).mean()
+    assert same > 0.9, same
+    ok = (st0["steps"] == st1["steps"]).all(axis=1)
+    assert np.max(_rel(ch1[ok, 0], ch0[ok, 0])) < 1e-4
