@@ -451,6 +451,7 @@ template <class T, class X> struct EngineCore {
   // come back through a small ring of pinned slots (async copy + event); the host runs at most LAG steps ahead.
   int32_t run_pipelined(bool pending) {
     constexpr int LAG = 2;
+    x.use();
     int64_t np_known = pending ? x.read_count() : -1;   // -1: nothing known yet (first step has no gradient)
     x.reset_counters();
     int64_t step = 0, completed = -1;
@@ -483,6 +484,7 @@ template <class T, class X> struct EngineCore {
   }
   int32_t run(bool pending) {
     const bool batched = model.batched();
+    x.use();
     if (batched && !reduce_on && X::RING > 0) return run_pipelined(pending);
     const int iters = batched ? 1 : (1 << 30);
     int64_t np = 0;

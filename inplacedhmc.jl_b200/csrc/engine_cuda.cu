@@ -538,8 +538,10 @@ struct CudaExec {
     return static_cast<U*>(p);
   }
   void free(void* p) { cudaFree(p); }
-  void h2d(void* d, const void* s, size_t n) { note(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream), "h2d"); note(cudaStreamSynchronize(stream), "h2d sync"); }
-  void d2h(void* d, const void* s, size_t n) { note(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream), "d2h"); note(cudaStreamSynchronize(stream), "d2h sync"); }
+  // engines on several devices may be driven from one host thread: every entry re-selects the engine's device
+  void use() { note(cudaSetDevice(device), "cudaSetDevice"); }
+  void h2d(void* d, const void* s, size_t n) { use(); note(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream), "h2d"); note(cudaStreamSynchronize(stream), "h2d sync"); }
+  void d2h(void* d, const void* s, size_t n) { use(); note(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream), "d2h"); note(cudaStreamSynchronize(stream), "d2h sync"); }
   void d2d(void* d, const void* s, size_t n) { note(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream), "d2d"); }
   void rows_times_matrix(const double* in, double* out, int64_t R, int D, const double* mat) {
     dim3 grid((D + 63) / 64, (unsigned)((R + 63) / 64));

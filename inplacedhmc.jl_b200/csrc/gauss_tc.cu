@@ -130,8 +130,13 @@ k_gauss_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUt
 
 void GaussTC::run(cudaStream_t s, int nrows) {
   if (!ready || nrows <= 0) return;
-  static bool attr_done = false;
-  if (!attr_done) { cudaFuncSetAttribute(k_gauss_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM); attr_done = true; }
+  static unsigned long long attr_done = 0;   // per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
+    cudaFuncSetAttribute(k_gauss_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+    attr_done |= 1ull << (dev & 63);
+  }
   CUtensorMap m[6];
   for (int i = 0; i < 6; ++i) std::memcpy(&m[i], tmaps[i], sizeof(CUtensorMap));
   dim3 grid((nrows + 127) / 128, Np / 128);

@@ -438,10 +438,13 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
 template <int DT, int NK> void launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
   using P = SmemPlan<DT>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the attribute is per device: one bit per device ordinal (engines on several GPUs may live in one process)
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
     tc.last = cudaFuncSetAttribute(k_logistic_tc<DT, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
-    attr_done = true;
+    attr_done |= 1ull << (dev & 63);
   }
   const int tiles = (nrows + CHAINS - 1) / CHAINS;
   dim3 grid(tiles, nsplit);
@@ -778,10 +781,13 @@ k_logistic_tc64(const __grid_constant__ CUtensorMap tmX, const uint16_t* __restr
 
 template <int DT, int NK> void launch64(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
   using P = SmemPlan2<DT>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the attribute is per device: one bit per device ordinal (engines on several GPUs may live in one process)
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
     tc.last = cudaFuncSetAttribute(k_logistic_tc64<DT, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
-    attr_done = true;
+    attr_done |= 1ull << (dev & 63);
   }
   const int tiles = (nrows + CHAINS - 1) / CHAINS;
   dim3 grid(tiles, nsplit);

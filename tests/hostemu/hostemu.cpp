@@ -34,6 +34,7 @@ struct HostExec {
   }
   void zero(void* d, size_t n) { std::memset(d, 0, n); }
   void sync() {}
+  void use() {}
   int32_t check(std::string&) { return 0; }
   int32_t profile(int32_t, double* ms, int64_t* n) { if (ms) *ms = 0; if (n) *n = 0; return 0; }
 
