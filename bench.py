@@ -133,6 +133,8 @@ def main():
     ap.add_argument("--transitions", type=int, default=64, help="NUTS transitions per chain per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference", action="store_true", help="keep the exact three-term position operand")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (BASELINE config 3: --chains in total, sharded over the GPUs) or weak (--chains per GPU)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -166,7 +168,7 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t[0])
 
     N, D = a.rows, a.dim
-    C = a.chains // world                       # chains shard across GPUs, no communication
+    C = a.chains // world if a.scaling == "strong" else a.chains   # chains shard across GPUs, no communication
     bits, y, beta = synth(N, D)
     e = bn.Engine(C, D, dtype=bn.F32, seed=20261018, chain_offset=rank * C, device=local, gradient_path=bn.GRAD_TENSOR)
     e.model_logistic(bits, y, 1.0)
@@ -257,7 +259,7 @@ def main():
     ach = 4.0 * N * D * rows / (grad_ms * 1e-3) / 1e12 if grad_n else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f32 (exact bf16 operand splits on tcgen05, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": "c3: Bayesian logistic regression N=%d D=%d, %d chains total, max_depth 10" % (N, D, C * world),
                    "chains_per_gpu": C, "parallelism": "chains sharded, no collective",
