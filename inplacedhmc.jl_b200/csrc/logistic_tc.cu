@@ -31,9 +31,11 @@
 // outside the tensor core (bounds accumulator rounding drift).  Three S/R buffers in
 // TMEM give the elementwise warps two block-times of slack behind the tensor pipe.
 //
-// Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2-17 elementwise/epilogue: TMEM lane group = warp % 4 (hardware rule), the
-// four warps of a lane group each own one 32-row quarter of every 128-row block.
+// Warp roles (608 threads): warp 0 TMA producer, warp 1 GEMM1 issuer + TMEM owner, warp 18 GEMM2 issuer,
+// warps 2-17 elementwise/epilogue: TMEM lane group = warp % 4 (hardware rule); two groups of eight warps
+// ping-pong over the row blocks, a warp owns two 32-row chunks of its group's blocks.
+// A second kernel in this file, k_logistic_tc64, keeps the position operand in TMEM and works on 64-row
+// blocks (BNUTS_TC_VARIANT=64): same results, measured slower, kept as a documented variant.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -283,8 +285,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // ===================================================== elementwise + epilogue (16 warps)
     // NG groups of 16/NG warps; group g takes blocks i = g mod NG.  Inside a group: TMEM lane group
     // q = warp % 4 (hardware rule), column part h; a warp owns CPW = NG chunks of 32 columns per block.
-    // Measured: the latency of one block through this stage, not its throughput, limits the kernel (the
-    // S -> R -> GEMM2 chain has only three TMEM buffers of slack), so NG = 1 (shortest latency) is the default.
+    // Measured (clock64 trace): the latency of one block around the loop S -> elementwise -> R -> GEMM2 ->
+    // buffer free -> GEMM1, not the throughput of any pipe, limits the kernel (three TMEM buffers of slack);
+    // NG = 2 (3.02 ms per full launch) beats NG = 1 (3.17 ms) once S is prefetched without blocking.
     const int ew = warp - 2;
     const int grp = ew / EW_PER_GROUP;
     const int h = (ew % EW_PER_GROUP) >> 2;
