@@ -23,6 +23,10 @@
 namespace bn {
 
 constexpr int ADV_THREADS = 128;  // 4 chains per CTA
+#ifndef BNUTS_ADV_MIN_BLOCKS
+#define BNUTS_ADV_MIN_BLOCKS 4
+#endif
+constexpr int ADV_MIN_BLOCKS = BNUTS_ADV_MIN_BLOCKS;   // register budget of k_advance = 65536 / (128 x this); measured 2 / 3 / 4: funnel f64 74 / 87 / 89 M leapfrog steps/s, c2 25.4 / 25.4 / 29.3 M
 
 template <class T> __global__ void __launch_bounds__(ADV_THREADS) k_prepare(EngineMem<T> M, RunParams<T> rp, PrepareArgs a) {
   const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -31,7 +35,7 @@ template <class T> __global__ void __launch_bounds__(ADV_THREADS) k_prepare(Engi
 }
 
 template <class T>
-__global__ void __launch_bounds__(ADV_THREADS) k_advance(EngineMem<T> M, RunParams<T> rp, int iters, unsigned long long* pending) {
+__global__ void __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS) k_advance(EngineMem<T> M, RunParams<T> rp, int iters, unsigned long long* pending) {
   const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (c >= M.C) return;
   const int lane = (int)(threadIdx.x & 31);
@@ -43,7 +47,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(EngineMem<T> M, RunPara
 // two device words (this launch counts into `cnt` and clears `cnt_next` for the following one); the last CTA to
 // finish publishes {sequence number, count} into a pinned, device-mapped host word the host polls.
 template <class T>
-__global__ void __launch_bounds__(ADV_THREADS) k_advance_ring(EngineMem<T> M, RunParams<T> rp, int iters, unsigned long long* cnt,
+__global__ void __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS) k_advance_ring(EngineMem<T> M, RunParams<T> rp, int iters, unsigned long long* cnt,
                                                               unsigned long long* cnt_next, unsigned int* done,
                                                               volatile unsigned long long* host_slot, unsigned int seq) {
   const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
