@@ -800,6 +800,312 @@ template <int DT, int NK> void launch64(LogisticTC& tc, cudaStream_t s, int nrow
                                                             (int)(tc.Npad / ROWS2), nsplit, tc.flush_every, tc.nterms);
 }
 
+
+// =====================================================================================================
+// Variant for 128 < D <= 256 (k_logistic_tc256; BASELINE config 5 has D = 256).
+//
+// With exact operand splits a D = 256 problem does not fit the layouts above: three β tiles would be 192 KB and
+// G (256 columns) leaves no room for 128-column S/R buffers.  Here: 64-row blocks (as k_logistic_tc64), K = dk
+// exactly (no spare K columns), TWO-TERM mode only — the position operand is always β − β₀ split in two bf16
+// terms, and η̃₀ = X̃β₀ is added in the elementwise stage from a per-row fp32 vector that travels with each X̃
+// stage.  Without a reference point β₀ = 0 and the operand is a 16-bit β (relative gradient error ~1e-5..1e-4:
+// enough for FindLocalOptimum, which then supplies the reference).  Shared memory: 2 β tiles (KC x 16 KB each)
+// + 3 stages of 64-row X̃ blocks (KC x 8 KB + 256 B of η̃₀); TMEM: G [0, 256) + four 64-column S/R buffers.
+// GEMM1 is an SS MMA with N = 64 (shared-memory bound: 6 KB of operands per 32 clk); GEMM2 one N = dk MMA per K step.
+template <int KC> struct SmemPlan3 {
+  static constexpr int B_BYTES = KC * CHUNK_BYTES;       // one β term: 128 chains x (KC x 64) columns
+  static constexpr int X_BYTES = KC * CHUNK2;            // one X stage: 64 rows x (KC x 64) columns
+  static constexpr int NS = 3;
+  static constexpr int OFF_B = 0;
+  static constexpr int OFF_X = 2 * B_BYTES;
+  static constexpr int OFF_E = OFF_X + NS * X_BYTES;     // eta0: NS x 64 floats
+  static constexpr int OFF_BAR = OFF_E + NS * ROWS2 * 4;
+  static constexpr int NBAR = 1 + 2 * NS + 3 * 4 + 2;
+  static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
+};
+
+template <int NK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
+                 const __grid_constant__ CUtensorMap tmBm, const float* __restrict__ eta0, float* G, double* Ld, int nrows, int Dp,
+                 long long N, int nblk_total, int nsplit, int flush_every) {
+  constexpr int KC = (NK + 3) / 4;
+  using P = SmemPlan3<KC>;
+  constexpr int dk = NK * 16;
+  constexpr int NS = P::NS;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sB = smem + P::OFF_B;
+  unsigned char* sX = smem + P::OFF_X;
+  float* sE = reinterpret_cast<float*>(smem + P::OFF_E);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
+  uint64_t* bar_b = bars;
+  uint64_t* x_full = bars + 1;
+  uint64_t* x_empty = x_full + NS;
+  uint64_t* s_full = x_empty + NS;
+  uint64_t* r_full = s_full + 4;
+  uint64_t* sr_empty = r_full + 4;
+  uint64_t* g_full = sr_empty + 4;
+  uint64_t* g_empty = g_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int b0 = (int)(((long long)nblk_total * split) / nsplit);
+  const int b1 = (int)(((long long)nblk_total * (split + 1)) / nsplit);
+  const int nb = b1 - b0;
+  const int fe = flush_every > 0 ? 2 * flush_every : 0x7fffffff;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) asm volatile("trap;");
+    mbar_init(bar_b, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 256); mbar_init(&sr_empty[i], 1); }
+    mbar_init(g_full, 1);
+    mbar_init(g_empty, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_G = tmem;             // [0, 256)
+  const uint32_t tmem_S = tmem + 256u;      // 4 x 64 columns
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0 && nb > 0) {
+      mbar_expect_tx(bar_b, 2 * P::B_BYTES);
+      for (int kc = 0; kc < KC; ++kc) {
+        tma_load_2d(&tmBh, sB + 0 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+        tma_load_2d(&tmBm, sB + 1 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+      }
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS;
+        const uint32_t ph = (uint32_t)(i / NS) & 1u;
+        mbar_wait(&x_empty[st], ph ^ 1u);
+        mbar_expect_tx(&x_full[st], P::X_BYTES + ROWS2 * 4);
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK2, &x_full[st], kc * 64, (b0 + i) * ROWS2);
+        bulk_load_1d(sE + st * ROWS2, eta0 + (size_t)(b0 + i) * ROWS2, ROWS2 * 4, &x_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== GEMM1 issuer: S[buf] = (β − β₀) · X̃_iᵀ, both from smem
+    if (nb > 0) {
+      constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS2 >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t aX = smem_u32(sX);
+      const uint64_t dKM = desc_kmajor(0, 0);
+      const uint32_t km_hi = (uint32_t)(dKM >> 32), km_lo0 = (uint32_t)dKM;
+      const uint32_t bB0 = km_lo0 + (smem_u32(sB) >> 4);
+      mbar_wait(bar_b, 0);
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS, buf = i & 3, rnd = i >> 2;
+        mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
+        if (rnd >= 1) mbar_wait(&sr_empty[buf], (uint32_t)(rnd - 1) & 1u);
+        tc_fence_after();
+        const uint32_t xlo = km_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
+        const uint32_t d = tmem_S + (uint32_t)buf * 64u;
+#pragma unroll
+        for (int term = 0; term < 2; ++term)
+#pragma unroll
+          for (int c = 0; c < KC; ++c) {
+            constexpr int LAST = NK - (KC - 1) * 4;
+            const uint32_t a = bB0 + (uint32_t)((term * P::B_BYTES + c * CHUNK_BYTES) >> 4);
+            const uint32_t b = xlo + (uint32_t)(c * (CHUNK2 >> 4));
+            const uint32_t acc = (term | c) ? 1u : 0u;
+            if (c + 1 < KC) mma_ss_run<4>(d, a, km_hi, b, km_hi, IDESC1, acc);
+            else mma_ss_run<LAST>(d, a, km_hi, b, km_hi, IDESC1, acc);
+          }
+        if (elect_one()) tc_commit(&s_full[buf]);
+        __syncwarp();
+      }
+    }
+  } else if (warp == G2_WARP) {
+    // ===================================================== GEMM2 issuer: G += R (TMEM) · X̃_i (smem, MN-major), N = dk
+    if (nb > 0) {
+      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t aX = smem_u32(sX);
+      const uint64_t dMN = make_desc(0, (uint32_t)CHUNK2, 1024u);
+      const uint32_t mn_hi = (uint32_t)(dMN >> 32), mn_lo0 = (uint32_t)dMN;
+      int period = 0, in_period = 0;
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS, buf = i & 3, rnd = i >> 2;
+        mbar_wait(&r_full[buf], (uint32_t)rnd & 1u);
+        if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
+        tc_fence_after();
+        const uint32_t xm = mn_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
+        const uint32_t a = tmem_S + (uint32_t)buf * 64u;
+        const uint32_t acc0 = in_period > 0 ? 1u : 0u;
+#pragma unroll
+        for (int term = 0; term < 2; ++term)
+          mma_ts_run4(tmem_G, a + (uint32_t)(term * 16), xm, mn_hi, IDESC2, term ? 1u : acc0);
+        if (elect_one()) { tc_commit(&x_empty[st]); tc_commit(&sr_empty[buf]); }
+        ++in_period;
+        if (i + 1 == nb || in_period == fe) {
+          if (elect_one()) tc_commit(g_full);
+          ++period;
+          in_period = 0;
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================== elementwise + epilogue (16 warps, two groups of 8)
+    const int ew = warp - 2;
+    const int grp = ew >> 3;
+    const int h = (ew >> 2) & 1;
+    const int q = warp & 3;
+    const int row = tile * CHAINS + q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool live = (tile * CHAINS + q * 32) < nrows;
+    double lsum = 0.0;
+    const float2 L2E2 = make_float2(1.4426950408889634f, 1.4426950408889634f);
+    const float2 ONE2 = make_float2(1.0f, 1.0f), MHALF2 = make_float2(-0.5f, -0.5f), HALF2 = make_float2(0.5f, 0.5f);
+    const float2 MONE2 = make_float2(-1.0f, -1.0f);
+    const float LN2 = 0.6931471805599453f;
+    float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
+    int fpos = grp, fper = 0;
+    while (fpos >= fe) { fpos -= fe; ++fper; }
+    uint32_t v[32];
+    auto load_item = [&](int i, bool blocking) -> bool {
+      const int buf = i & 3, rnd = i >> 2;
+      if (!blocking) {
+        if (!mbar_test(&s_full[buf], (uint32_t)rnd & 1u)) return false;
+      } else {
+        mbar_wait(&s_full[buf], (uint32_t)rnd & 1u);
+      }
+      tc_fence_after();
+      tmem_ld32(tmem_S + (uint32_t)buf * 64u + lane_sel + (uint32_t)h * 32u, v);
+      return true;
+    };
+    bool have_next = false;
+    if (grp < nb && live) have_next = load_item(grp, true);
+    for (int i = grp; i < nb; i += 2) {
+      const int buf = i & 3, st = i % NS;
+      float bsum = 0.f, asum = 0.f;
+      if (!live) {
+        mbar_wait(&s_full[buf], (uint32_t)(i >> 2) & 1u);
+      } else {
+        if (!have_next) have_next = load_item(i, true);
+        mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);     // eta0 of this block is visible (long complete)
+        const float4* e4 = reinterpret_cast<const float4*>(sE + st * ROWS2 + h * 32);
+        const uint32_t tS = tmem_S + (uint32_t)buf * 64u + lane_sel + (uint32_t)h * 32u;
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+        float2 prod = ONE2;
+        float as0 = 0.f, as1 = 0.f;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 eo = e4[j4];
+          const float off[4] = {eo.x, eo.y, eo.z, eo.w};
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * j4 + jj;
+            const float e0 = __uint_as_float(v[2 * j]) + off[2 * jj], e1 = __uint_as_float(v[2 * j + 1]) + off[2 * jj + 1];
+            const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
+            const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
+            prod = __fmul2_rn(prod, d2);
+            as0 += fabsf(e0); as1 += fabsf(e1);
+            const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
+            const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (__float_as_uint(e0) & 0x80000000u)),
+                                          __uint_as_float(__float_as_uint(hm.y) | (__float_as_uint(e1) & 0x80000000u)));
+            const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
+            const uint32_t hh = pack_bf16(r2.x, r2.y);
+            const float2 hv = make_float2(__uint_as_float(hh << 16), __uint_as_float(hh & 0xffff0000u));
+            const float2 l2 = __ffma2_rn(hv, MONE2, r2);
+            hi[j] = hh;
+            lo[j] = pack_bf16(l2.x, l2.y);
+          }
+        }
+        bsum = lg2_approx(prod.x * prod.y);
+        asum = as0 + as1;
+        have_next = false;
+        if (i + 2 < nb) have_next = load_item(i + 2, false);
+        tmem_st16(tS, hi);
+        tmem_st16(tS + 16u, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&r_full[buf]);
+      lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);
+      const bool closes = (i + 1 == nb) || (fpos == fe - 1);
+      const int period = fper;
+      fpos += 2;
+      while (fpos >= fe) { fpos -= fe; ++fper; }
+      if (closes) {
+        mbar_wait(g_full, (uint32_t)period & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int ch = 4 * h + cc;
+          if (ch * 32 < dk && live) {
+            uint32_t w[32];
+            tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, w);
+            tmem_ld_wait();
+            if (row < nrows) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const int d = ch * 32 + j;
+                if (d < dk && d < Dp) {
+                  float4 a = make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]), __uint_as_float(w[j + 2]),
+                                         __uint_as_float(w[j + 3]));
+                  float4* gp = reinterpret_cast<float4*>(gout + d);
+                  if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+                  *gp = a;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(g_empty);
+      }
+    }
+    // rows >= N of the last block are zero padding (X̃ = 0, eta0 = 0): each contributed -log 2
+    if (h == 0 && nb > 0 && grp == ((nb - 1) & 1) && b1 == nblk_total)
+      lsum += (double)((long long)nblk_total * ROWS2 - N) * 0.6931471805599453;
+    double* lp = reinterpret_cast<double*>(sX);   // X stages are dead by now
+    const int part = grp * 2 + h;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (part > 0) lp[(part - 1) * 128 + q * 32 + lane] = lsum;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (part == 0 && row < nrows) {
+      if (nb == 0) for (int d = 0; d < Dp; ++d) gout[d] = 0.f;
+      const int k = q * 32 + lane;
+      Ld[(size_t)split * nrows + row] = ((lsum + lp[k]) + lp[128 + k]) + lp[256 + k];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+template <int NK> void launch256(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
+  using P = SmemPlan3<(NK + 3) / 4>;
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
+    tc.last = cudaFuncSetAttribute(k_logistic_tc256<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    attr_done |= 1ull << (dev & 63);
+  }
+  const int tiles = (nrows + CHAINS - 1) / CHAINS;
+  dim3 grid(tiles, nsplit);
+  CUtensorMap m[3];
+  std::memcpy(&m[0], tc.tmaps[4], sizeof(CUtensorMap));
+  std::memcpy(&m[1], tc.tmaps[1], sizeof(CUtensorMap));
+  std::memcpy(&m[2], tc.tmaps[2], sizeof(CUtensorMap));
+  k_logistic_tc256<NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], tc.eta0, tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
+                                                        (int)(tc.Npad / ROWS2), nsplit, tc.flush_every);
+}
+
 }  // namespace
 
 // number of row splits for `nrows` active rows: fill the SMs in as few full waves as possible
@@ -822,6 +1128,19 @@ int LogisticTC::plan_splits(int nrows) const {
 void LogisticTC::run(cudaStream_t s, int nrows) {
   if (!ready || nrows <= 0) return;
   last_nsplit = plan_splits(nrows);
+  if (variant == 256) {
+    switch (dk / 16) {
+      case 9: launch256<9>(*this, s, nrows, last_nsplit); break;
+      case 10: launch256<10>(*this, s, nrows, last_nsplit); break;
+      case 11: launch256<11>(*this, s, nrows, last_nsplit); break;
+      case 12: launch256<12>(*this, s, nrows, last_nsplit); break;
+      case 13: launch256<13>(*this, s, nrows, last_nsplit); break;
+      case 14: launch256<14>(*this, s, nrows, last_nsplit); break;
+      case 15: launch256<15>(*this, s, nrows, last_nsplit); break;
+      default: launch256<16>(*this, s, nrows, last_nsplit); break;
+    }
+    return;
+  }
   if (variant == 64) {
     switch (dk / 16) {
       case 1: launch64<64, 1>(*this, s, nrows, last_nsplit); break;
@@ -855,7 +1174,8 @@ void LogisticTC::destroy() {
   if (Xb) cudaFree(Xb);
   if (colsum) cudaFree(colsum);
   if (beta_ref) cudaFree(beta_ref);
-  Xb = nullptr; colsum = nullptr; beta_ref = nullptr; ready = false; nterms = 3;
+  if (eta0) cudaFree(eta0);
+  Xb = nullptr; colsum = nullptr; beta_ref = nullptr; eta0 = nullptr; ready = false; nterms = 3; variant = 128;
 }
 
 namespace {
@@ -884,7 +1204,23 @@ __global__ void k_init_stage(uint16_t* bh, int C, int D, int Dt) {
 }
 }  // namespace
 
+namespace {
+__global__ void k_write_eta0(const uint16_t* __restrict__ Xb, const float* __restrict__ beta_ref, float* eta0, long long N, int D, int Dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double acc = 0.0;
+  if (beta_ref) {
+    const uint16_t* xr = Xb + i * Dt;
+    for (int d = 0; d < D; ++d) acc = fma((double)bf16_val(xr[d]), (double)beta_ref[d], acc);
+  }
+  eta0[i] = (float)acc;
+}
+}  // namespace
 void logistic_tc_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev) {
+  if (tc.variant == 256) {
+    k_write_eta0<<<(unsigned)((tc.N + 255) / 256), 256, 0, s>>>(tc.Xb, beta_ref_dev, tc.eta0, (long long)tc.N, tc.D, tc.Dt);
+    return;
+  }
   if (!tc.aug) return;
   k_write_reference<<<(unsigned)((tc.N + 255) / 256), 256, 0, s>>>(tc.Xb, beta_ref_dev, (long long)tc.N, tc.D, tc.Dt);
 }
@@ -900,6 +1236,13 @@ int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, i
   tc.aug = (D + 3 <= 128) ? 1 : 0;
   tc.dk = (D + (tc.aug ? 3 : 0) + 15) / 16 * 16;
   tc.Dt = (tc.dk <= 64) ? 64 : 128;
+  if (D > 128) {   // k_logistic_tc256: K = dk exactly, two-term mode with eta0 = X~ beta_ref added elementwise
+    tc.aug = 0;
+    tc.dk = (D + 15) / 16 * 16;
+    tc.Dt = (tc.dk + 63) / 64 * 64;
+    tc.variant = 256;
+    tc.nterms = 2;
+  }
   tc.Npad = (N + ROWS - 1) / ROWS * ROWS;
   const char* fe = std::getenv("BNUTS_TC_FLUSH");
   if (fe) tc.flush_every = std::atoi(fe);
@@ -929,6 +1272,10 @@ int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, i
   cudaMemcpy(tc.Xb, xp.data(), xp.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(tc.colsum, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice);
   cudaMemset(tc.beta_ref, 0, size_t(Dp) * 4);
+  if (tc.variant == 256) {
+    if (cudaMalloc(&tc.eta0, size_t(tc.Npad) * 4) != cudaSuccess) { err = "device allocation failed (eta0)"; return BNUTS_ERR_CUDA; }
+    cudaMemset(tc.eta0, 0, size_t(tc.Npad) * 4);
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&tc.sms, cudaDevAttrMultiProcessorCount, dev);
@@ -956,7 +1303,7 @@ int32_t logistic_tc_maps(LogisticTC& tc, std::string& err) {
   }
   if (!encode_map(tc.tmaps[4], tc.Xb, (uint64_t)tc.Npad, (uint64_t)tc.Dt, 64)) { err = "cuTensorMapEncodeTiled failed"; return BNUTS_ERR_CUDA; }
   const char* ve = std::getenv("BNUTS_TC_VARIANT");
-  if (ve) tc.variant = std::atoi(ve);
+  if (ve && tc.variant != 256) tc.variant = std::atoi(ve) == 64 ? 64 : 128;
   tc.ready = true;
   return 0;
 }

@@ -26,6 +26,7 @@ struct LogisticTC {
   uint16_t* Xb = nullptr;    // [Npad][Dt] bf16, rows sign-folded: X~_i = (2 y_i - 1) X_i
   double* colsum = nullptr;  // [Dp] column sums of X~ (linear part of the log density)
   float* beta_ref = nullptr; // [Dp] reference point (zeros when none is set)
+  float* eta0 = nullptr;     // [Npad] X~ beta_ref per row (k_logistic_tc256 only)
   // borrowed from the engine
   const uint16_t* bh = nullptr; const uint16_t* bm = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
   float* G = nullptr;        // [nsplit][rows][Dp]
@@ -60,7 +61,7 @@ int32_t logistic_tc_setup(LogisticTC& tc, E& eng, const void* Xh, int32_t xd, co
     return BNUTS_ERR_UNSUPPORTED;
   } else {
     auto& M = eng.M;
-    if (M.D > 128) { err = "tensor gradient path supports D <= 128 in this build"; return BNUTS_ERR_UNSUPPORTED; }
+    if (M.D > 256) { err = "tensor gradient path supports D <= 256 in this build"; return BNUTS_ERR_UNSUPPORTED; }
     // X must be exactly representable in bf16 (the data operand of the MMA is not split)
     const size_t n = size_t(N) * M.D;
     std::vector<uint16_t> xb(n);
@@ -112,12 +113,12 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
     auto& M = eng.M;
     auto& x = eng.x;
     if (!tc.ready) { err = "reference point needs the tensor gradient path"; return BNUTS_ERR_UNSUPPORTED; }
-    // back to the exact path
-    tc.nterms = 3;
+    // back to the exact path (D <= 128) / to the zero reference (D > 128: always two terms, see k_logistic_tc256)
+    tc.nterms = tc.variant == 256 ? 2 : 3;
     x.zero(tc.beta_ref, size_t(M.Dp) * sizeof(float));
     logistic_tc_write_reference(tc, x.stream, nullptr);
     if (!beta_ref) return x.check(err);
-    if (!tc.aug) { err = "no spare K columns for the reference term (D + 3 > 128)"; return BNUTS_ERR_UNSUPPORTED; }
+    if (!tc.aug && tc.variant != 256) { err = "no spare K columns for the reference term (125 < D <= 128)"; return BNUTS_ERR_UNSUPPORTED; }
     std::vector<float> b(size_t(M.Dp), 0.f);
     std::vector<uint16_t> h(size_t(tc.Dt), 0), m(size_t(tc.Dt), 0), l(size_t(tc.Dt), 0);
     for (int d = 0; d < M.D; ++d) {
@@ -128,7 +129,7 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
       m[d] = bf16_bits(r1);
       l[d] = bf16_bits(r1 - bf16_val(m[d]));
     }
-    for (int k = 0; k < 3; ++k) h[M.D + k] = 0x3F80;
+    if (tc.aug) for (int k = 0; k < 3; ++k) h[M.D + k] = 0x3F80;
     x.h2d(M.stage_bh, h.data(), h.size() * 2); x.h2d(M.stage_bm, m.data(), m.size() * 2); x.h2d(M.stage_bl, l.data(), l.size() * 2);
     tc.run(x.stream, 1);
     const int ns = tc.last_nsplit;

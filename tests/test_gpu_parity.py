@@ -296,3 +296,37 @@ def test_row_sharded_machinery_single_rank(bn, cuda_lib, exchange):
     assert same > 0.9, same
     ok = (st0["steps"] == st1["steps"]).all(axis=1)
     assert np.max(_rel(ch1[ok, 0], ch0[ok, 0])) < 1e-4
+
+
+@pytest.mark.parametrize("N,D,C", [(3000, 256, 200), (700, 129, 5), (1500, 200, 130)])
+def test_tensor_wide_kernel_128_to_256(bn, oracle_lib, cuda_lib, N, D, C):
+    """k_logistic_tc256 (128 < D <= 256; BASELINE config 5 has D = 256): two-term operand around a reference point.
+    Without a reference the operand is a 16-bit beta (coarse: 2e-4); with the mode as reference the north-star
+    fp32 tolerance holds."""
+    X, y, beta = make_logistic(N, D)
+    rng = np.random.default_rng(21)
+    ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0, row_blocks=1)
+    b = beta.copy()
+    for _ in range(10):                               # Newton on the host: the posterior mode
+        s = 1 / (1 + np.exp(-(X @ b)))
+        H = (X * (s * (1 - s))[:, None]).T @ X + np.eye(D)
+        b = b + np.linalg.solve(H, X.T @ (y - s) - b)
+    sd = 1.0 / np.sqrt(np.diag(H))
+    q = _f32(b[None, :] + rng.normal(size=(C, D)) * sd[None, :] * np.linspace(0.3, 3.0, C)[:, None])
+    ref.set_positions(q); _, g0, l0 = ref.get_state()
+    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0)
+    tc.set_positions(q); _, gc, lc = tc.get_state()
+    nrm = np.linalg.norm(g0, axis=1)
+    floor = 3 * N * 6e-8
+    assert np.all(np.linalg.norm(gc - g0, axis=1) < np.maximum(3e-4 * np.sqrt(N * D) / 2, 3e-4 * nrm)), "coarse mode"
+    assert np.max(np.abs(lc - l0) / np.abs(l0)) < 1e-5
+    tc.logistic_set_reference(b)
+    tc.set_positions(q); _, g2, l2 = tc.get_state()
+    err = np.linalg.norm(g2 - g0, axis=1)
+    assert np.all(err < np.maximum(TOL32 * nrm, floor)), (np.max(err / np.maximum(TOL32 * nrm, floor)))
+    assert np.max(np.abs(l2 - l0) / np.abs(l0)) < TOL32       # the engine's log density is an fp32 number
+    p = _f32(rng.normal(size=(C, D)) * np.sqrt(N) * 0.3)
+    a = ref.leapfrog(p, 1e-3, 2); c = tc.leapfrog(p, 1e-3, 2)
+    assert np.max(_rel(c[0], a[0])) < TOL32
+    tc.set_stepsize(0.02); ch, st = tc.sample(2)
+    assert np.isfinite(ch).all() and (st["steps"] > 0).all()
