@@ -130,6 +130,7 @@ int32_t bnuts_set_nccl(bnuts_engine* e, const uint8_t* id, int32_t world, int32_
   std::string& err = ae->dtype == BNUTS_F64 ? ae->e64->err : ae->e32->err;
   int32_t rc = ae->dtype == BNUTS_F64 ? ae->e64->x.nccl_init(id, world, rank, err) : ae->e32->x.nccl_init(id, world, rank, err);
   if (rc) return rc;
+  if (ae->dtype == BNUTS_F64) ae->e64->red_world = world; else ae->e32->red_world = world;
   BN_DISPATCH(e, enable_reduce(nullptr, nullptr));
 }
 int32_t bnuts_p2p_export(bnuts_engine* e, uint8_t* handle) {

@@ -142,7 +142,7 @@ template <class T, class X> struct EngineCore {
     if (rc) return rc;
     rc = enable_reduce(nullptr, nullptr);
     if (rc) return rc;
-    p2p_on = true; p2p_seq = 0;
+    p2p_on = true; p2p_seq = 0; red_world = world;
     return 0;
   }
   // ≙ no reference counterpart (the reference has no collective).  After this call the engine
@@ -312,6 +312,35 @@ template <class T, class X> struct EngineCore {
     model.kind = MODEL_LOGISTIC; M.model_kind = MODEL_LOGISTIC;
     return x.check(err);
   }
+
+  // gradient of staged row 0 after a one-row gradient launch with `nb` partial blocks, folded on the host;
+  // in row-sharded mode the partials are first summed over the group (every rank must make the same call)
+  int32_t folded_row0(int nb, std::vector<double>& g) {
+    g.assign(size_t(M.Dp), 0.0);
+    if (reduce_on) {
+      M.stage_nb = nb; M.stage_rows = 1;
+      if (p2p_on) {
+        p2p_seq += 1;
+        x.fold_push(M, 1, p2p_seq);
+        x.wait_sum(M, 1, p2p_seq, red_g, red_l);
+      } else {
+        x.fold_partials(M, 1, red_g, red_l);
+        int32_t rc = x.allreduce(red_g, M.Dp, sizeof(T) == 4, red_l, 1, red_fn, red_ctx, err);
+        if (rc) return rc;
+      }
+      std::vector<T> r(size_t(M.Dp));
+      x.d2h(r.data(), red_g, r.size() * sizeof(T));
+      for (int d = 0; d < M.D; ++d) g[d] = double(r[d]);
+    } else {
+      std::vector<T> r(size_t(nb) * M.Dp);
+      x.d2h(r.data(), M.stage_g, r.size() * sizeof(T));
+      for (int d = 0; d < M.D; ++d)
+        for (int s = 0; s < nb; ++s) g[d] += double(r[size_t(s) * M.Dp + d]);
+    }
+    return x.check(err);
+  }
+  int reduce_world() const { return reduce_on ? red_world : 1; }
+  int red_world = 1;
 
   // reference point of the tensor-core logistic path (numerical device, see include/bnuts.h)
   int32_t logistic_set_reference(const double* beta_ref) {

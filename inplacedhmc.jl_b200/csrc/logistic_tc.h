@@ -132,19 +132,15 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
     if (tc.aug) for (int k = 0; k < 3; ++k) h[M.D + k] = 0x3F80;
     x.h2d(M.stage_bh, h.data(), h.size() * 2); x.h2d(M.stage_bm, m.data(), m.size() * 2); x.h2d(M.stage_bl, l.data(), l.size() * 2);
     tc.run(x.stream, 1);
-    const int ns = tc.last_nsplit;
-    std::vector<float> g(size_t(ns) * M.Dp);
-    x.d2h(g.data(), M.stage_g, g.size() * sizeof(float));
-    int32_t rc = x.check(err);
+    std::vector<double> g;
+    int32_t rc = eng.folded_row0(tc.last_nsplit, g);   // summed over the group when the rows are sharded
     if (rc) return rc;
     double n2 = 0.0;
     for (int d = 0; d < M.D; ++d) {
-      double acc = 0.0;
-      for (int s = 0; s < ns; ++s) acc += double(g[size_t(s) * M.Dp + d]);
-      acc -= double(M.tau) * double(b[d]);
+      const double acc = g[d] - double(M.tau) * double(b[d]);
       n2 += acc * acc;
     }
-    const double bound = 0.5 * std::sqrt(double(tc.N) * double(M.D));
+    const double bound = 0.5 * std::sqrt(double(tc.N) * double(eng.reduce_world()) * double(M.D));
     if (!(n2 <= bound * bound)) {
       err = "reference point rejected: |grad| = " + std::to_string(std::sqrt(n2)) + " exceeds sqrt(N D)/2 = " +
             std::to_string(bound) + " (not at the mode); exact three-term path kept";

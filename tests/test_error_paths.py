@@ -50,7 +50,7 @@ def test_invalid_arguments(bn, lib):
 
 
 def test_unsupported_requests_fail_loudly(bn, hostemu_lib):
-    """No silent fallbacks: the tensor path, its reference point and the NCCL / peer-memory exchanges are CUDA-only."""
+    """No silent fallbacks: the tensor path (D <= 256), its reference point and the NCCL / peer-memory exchanges are CUDA-only."""
     X, y, _ = make_logistic(50, 4)
     e = bn.Engine(2, 4, dtype=bn.F32, lib=hostemu_lib, gradient_path=bn.GRAD_TENSOR)
     with pytest.raises(bn.BnutsError) as ei:
