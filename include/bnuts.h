@@ -104,12 +104,28 @@ int32_t bnuts_model_gaussian(bnuts_engine* e, const double* precision /* [D][D] 
 int32_t bnuts_model_logistic(bnuts_engine* e, const void* X, int32_t x_dtype, const double* y,
                              int64_t N, double prior_precision, int32_t row_blocks);
 
+/* The same model on SYNTHETIC rows [row_offset, row_offset + N) of one conceptual design matrix; no reference
+ * counterpart (the reference ships no models or data; SURVEY.md §8d defines the benchmark inputs, and for the
+ * row-sharded configuration asks for rows generated where they are used).  Row i, column d is a pure function of
+ * (data_seed, i, d): x[i][0] = 1, x[i][d] = bf16(N(0,1)) from Philox4x32-10 keyed by the seed with counter
+ * (row, column quad), beta*[d] ~ N(0, 1/D), y[i] ~ Bernoulli(sigma(x[i]·beta*)) — so every sharding of the rows
+ * sees the same matrix.  The tensor path generates its shard on the device (only the seed crosses PCIe); the
+ * deterministic path generates it on the host and takes the upload route of bnuts_model_logistic. */
+int32_t bnuts_model_logistic_synthetic(bnuts_engine* e, uint64_t data_seed, int64_t row_offset, int64_t N,
+                                       double prior_precision, int32_t row_blocks);
+/* Host copy of the same rows (no engine needed): X [nrows][D] as bf16 bits, y [nrows] of 0/1, beta_true [D];
+ * any output may be NULL. */
+int32_t bnuts_synth_logistic_rows(uint64_t data_seed, int64_t row_offset, int64_t nrows, int32_t D, uint16_t* X_bf16,
+                                  double* y, double* beta_true);
+
 /* Tensor-core logistic path only; no reference counterpart (the reference's first warmup stage,
  * FindLocalOptimum src/warmup.jl:152-186, is what produces such a point).  beta_ref [D] near the
  * posterior mode lets the kernel evaluate X·beta as X·beta_ref (stored) + X·(beta − beta_ref) with
  * two instead of three bf16 terms for the fp32 position.  The point is checked: if the gradient
  * there exceeds sqrt(N·D)/2 the call fails with BNUTS_ERR_INVALID_ARGUMENT and the exact
- * three-term path stays in force.  beta_ref == NULL returns to the three-term path. */
+ * three-term path stays in force.  beta_ref == NULL returns to the three-term path.
+ * For tall problems (N >= 3.3e5 D over the whole row group) the residual is carried about the reference as well
+ * (one bf16 term of sigma(−eta) − sigma(−eta_ref) instead of two of sigma(−eta); BNUTS_TC_RREF=0/1 overrides). */
 int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double* beta_ref);
 
 /* ≙ initialize_warmup_state(q = …), src/warmup.jl:100-129: sets q and evaluates

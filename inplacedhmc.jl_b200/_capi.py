@@ -54,7 +54,8 @@ assert TREE_STATS_DTYPE.itemsize == 32
 
 EXPORTS = [
     "bnuts_create", "bnuts_destroy", "bnuts_last_error", "bnuts_model_iid_normal", "bnuts_model_funnel",
-    "bnuts_model_gaussian", "bnuts_model_logistic", "bnuts_logistic_set_reference", "bnuts_set_positions", "bnuts_get_state",
+    "bnuts_model_gaussian", "bnuts_model_logistic", "bnuts_model_logistic_synthetic", "bnuts_synth_logistic_rows",
+    "bnuts_logistic_set_reference", "bnuts_set_positions", "bnuts_get_state",
     "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_set_metric_dense", "bnuts_get_metric_dense", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed",
     "bnuts_inject", "bnuts_leapfrog", "bnuts_find_local_optimum", "bnuts_find_initial_stepsize", "bnuts_warmup_stage", "bnuts_sample",
     "bnuts_counters", "bnuts_profile", "bnuts_chain_status", "bnuts_set_allreduce", "bnuts_nccl_unique_id", "bnuts_set_nccl",
@@ -88,6 +89,8 @@ def load_library(path=None):
     lib.bnuts_model_gaussian.argtypes = [_P, _P]
     lib.bnuts_model_logistic.argtypes = [_P, _P, C.c_int32, _P, C.c_int64, C.c_double, C.c_int32]
     lib.bnuts_logistic_set_reference.argtypes = [_P, _P]
+    lib.bnuts_model_logistic_synthetic.argtypes = [_P, C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_int32]
+    lib.bnuts_synth_logistic_rows.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P]
     lib.bnuts_set_allreduce.argtypes = [_P, ALLREDUCE_FN, _P]
     lib.bnuts_nccl_unique_id.argtypes = [_P]
     lib.bnuts_set_nccl.argtypes = [_P, _P, C.c_int32, C.c_int32]
@@ -129,6 +132,17 @@ def nccl_unique_id(lib=None):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(_P)
+
+
+def synth_logistic_rows(data_seed, row_offset, nrows, dim, lib=None):
+    """Host copy of rows [row_offset, row_offset + nrows) of the synthetic design matrix (include/bnuts.h):
+    X as bf16 bits (uint16), y, beta_true."""
+    lib = lib or load_library()
+    X = np.empty((nrows, dim), dtype=np.uint16); y = np.empty(nrows); beta = np.empty(dim)
+    rc = lib.bnuts_synth_logistic_rows(data_seed, row_offset, nrows, dim, _ptr(X), _ptr(y), _ptr(beta))
+    if rc:
+        raise BnutsError(rc, "bnuts_synth_logistic_rows failed")
+    return X, y, beta
 
 
 def _f64(a, shape=None):
@@ -191,6 +205,11 @@ class Engine:
         y = _f64(y, (X.shape[0],))
         self._chk(self.lib.bnuts_model_logistic(self.h, _ptr(X), x_dtype, _ptr(y), X.shape[0], prior_precision,
                                                 row_blocks))
+
+    def model_logistic_synthetic(self, data_seed, row_offset, n_rows, prior_precision=1.0, row_blocks=1):
+        """Logistic model on the synthetic rows [row_offset, row_offset + n_rows) (generated on the device for the
+        tensor path)."""
+        self._chk(self.lib.bnuts_model_logistic_synthetic(self.h, data_seed, row_offset, n_rows, prior_precision, row_blocks))
 
     def logistic_set_reference(self, beta_ref=None):
         """Tensor-core logistic path: evaluate X·β as X·β_ref + X·(β − β_ref) (two bf16 terms instead of

@@ -50,6 +50,7 @@ template <class T> struct EngineMem {
   int32_t Dt;            // padded K of the tensor path
   const T* beta_ref;     // [Dp] reference point of the tensor path (staged operand is q − beta_ref), or null
   const double* lin_w;   // [Dp] tensor path: the kernel's log-density partials omit ½ Σ_d lin_w[d] q[d]
+  const double* grad0;   // [Dp] tensor path, single-term residual mode: the kernel's gradient partials omit X̃ᵀ·r0, or null
   T tau;                 // logistic prior precision
   // per-call outputs
   double* draws;         // [C][N][D]
@@ -418,6 +419,11 @@ template <class T, class LP> struct Backend {
             T pv[4];
             ld4(sg + b * bs + d0, pv);
             for (int e = 0; e < 4; ++e) acc[e] = acc[e] + pv[e];
+          }
+          if (M.grad0) {  // constant part of the gradient about the reference point (see k_logistic_tc)
+            double g0[4];
+            ld4(M.grad0 + d0, g0);
+            for (int e = 0; e < 4; ++e) acc[e] = T((double)acc[e] + g0[e]);
           }
           ld4(q + d0, qv);
           for (int e = 0; e < 4; ++e) gv[e] = fma_(-M.tau, qv[e], acc[e]);

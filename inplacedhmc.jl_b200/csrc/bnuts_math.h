@@ -361,4 +361,44 @@ BN_HD double init_position(uint64_t seed, uint32_t chain, uint32_t d) {
   return fma_(u01_half(w.x, w.y, 0.0), 4.0, -2.0);
 }
 
+
+// ---- synthetic logistic-regression data (config c5 generates its rows from Philox keyed by
+// (data seed, GLOBAL row index), so every sharding of the rows sees the same matrix and nothing crosses PCIe).
+// Pure functions of (seed, row, column), the same bits on host and device:
+//   x[row][0] = 1 (intercept); x[row][d] = bf16(z), z ~ N(0,1) from fp32 Box-Muller (one Philox call = 4 columns)
+//   beta*[d] = z / sqrt(D), z ~ N(0,1) in Float64
+//   y[row] = u < sigma(eta), eta = sum_d x[row][d] beta*[d] accumulated in Float64 with fma, d = 0, 1, ..., D-1
+enum : uint32_t { PURPOSE_DATA = 4 };
+BN_HD void synth_x4(uint64_t seed, uint64_t row, uint32_t quad, float* x) {
+  const u32x4 w = draw4(seed, (uint32_t)row, (uint32_t)(row >> 32), PURPOSE_DATA, quad);
+  box_muller(u01_open0(w.x, 0.f), u01_half(w.y, 0.f), &x[0], &x[1]);
+  box_muller(u01_open0(w.z, 0.f), u01_half(w.w, 0.f), &x[2], &x[3]);
+  for (int e = 0; e < 4; ++e) {   // round to nearest even on the bf16 grid
+    const uint32_t u = f2u(x[e]);
+    x[e] = u2f((u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u);
+  }
+  if (quad == 0) x[0] = 1.f;
+}
+BN_HD double synth_beta(uint64_t seed, uint32_t d, int32_t D) {
+  const u32x4 w = draw4(seed, d, 0u, PURPOSE_DATA | (1u << 8), 0u);
+  double z0, z1;
+  box_muller(u01_open0(w.x, w.y, 0.0), u01_half(w.z, w.w, 0.0), &z0, &z1);
+  return z0 / sqrt_((double)D);
+}
+BN_HD double synth_uniform(uint64_t seed, uint64_t row) {
+  const u32x4 w = draw4(seed, (uint32_t)row, (uint32_t)(row >> 32), PURPOSE_DATA | (2u << 8), 0u);
+  return u01_half(w.x, w.y, 0.0);
+}
+// label of one row given beta* (length D): the reference implementation of the definition above
+BN_HDN double synth_label(uint64_t seed, uint64_t row, int32_t D, const double* beta) {
+  double eta = 0.0;
+  for (int32_t q = 0; 4 * q < D; ++q) {
+    float x[4];
+    synth_x4(seed, row, (uint32_t)q, x);
+    for (int e = 0; e < 4 && 4 * q + e < D; ++e) eta = fma_((double)x[e], beta[4 * q + e], eta);
+  }
+  const double p = 1.0 / (1.0 + exp_(-eta));
+  return synth_uniform(seed, row) < p ? 1.0 : 0.0;
+}
+
 }  // namespace bn

@@ -69,6 +69,15 @@ int32_t bnuts_model_logistic(bnuts_engine* e, const void* X, int32_t xd, const d
                              int32_t rb) {
   BN_DISPATCH(e, model_logistic(X, xd, y, N, tau, rb));
 }
+int32_t bnuts_model_logistic_synthetic(bnuts_engine* e, uint64_t data_seed, int64_t row_offset, int64_t N, double tau, int32_t rb) {
+  BN_DISPATCH(e, model_logistic_synth(data_seed, row_offset, N, tau, rb));
+}
+int32_t bnuts_synth_logistic_rows(uint64_t data_seed, int64_t row_offset, int64_t nrows, int32_t D, uint16_t* X, double* y,
+                                  double* beta_true) {
+  if (nrows < 0 || row_offset < 0 || D <= 0) return BNUTS_ERR_INVALID_ARGUMENT;
+  bn::synth_rows_host(data_seed, row_offset, nrows, D, X, y, beta_true);
+  return 0;
+}
 int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double* beta_ref) { BN_DISPATCH(e, logistic_set_reference(beta_ref)); }
 int32_t bnuts_set_positions(bnuts_engine* e, const double* q) { BN_DISPATCH(e, set_positions(q)); }
 int32_t bnuts_get_state(bnuts_engine* e, double* q, double* g, double* l) { BN_DISPATCH(e, get_state(q, g, l)); }

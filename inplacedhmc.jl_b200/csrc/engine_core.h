@@ -53,6 +53,26 @@ struct DenseMetric {
   double* dL = nullptr; double* dLt = nullptr; double* dLinv = nullptr; double* dLinvt = nullptr;   // device
 };
 
+// host form of the synthetic-row definition (bnuts_math.h, synth_*): rows [row0, row0 + N) as bf16 bits + labels
+inline void synth_rows_host(uint64_t seed, int64_t row0, int64_t N, int32_t D, uint16_t* X, double* y, double* beta_out) {
+  std::vector<double> beta(static_cast<size_t>(D));
+  for (int32_t d = 0; d < D; ++d) beta[size_t(d)] = synth_beta(seed, uint32_t(d), D);
+  if (beta_out) for (int32_t d = 0; d < D; ++d) beta_out[d] = beta[size_t(d)];
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static)
+#endif
+  for (int64_t i = 0; i < N; ++i) {
+    const uint64_t row = uint64_t(row0 + i);
+    if (X)
+      for (int32_t q = 0; 4 * q < D; ++q) {
+        float x[4];
+        synth_x4(seed, row, uint32_t(q), x);
+        for (int e = 0; e < 4 && 4 * q + e < D; ++e) X[size_t(i) * D + 4 * q + e] = uint16_t(f2u(x[e]) >> 16);
+      }
+    if (y) y[i] = synth_label(seed, row, D, beta.data());
+  }
+}
+
 template <class T, class X> struct EngineCore {
   bnuts_config cfg{};
   X x;
@@ -171,7 +191,7 @@ template <class T, class X> struct EngineCore {
     EngineMem<T> V = M;
     V.stage_q = wide_q; V.stage_bh = wide_bh; V.stage_bm = wide_bm; V.stage_bl = wide_bl;
     V.stage_active = d_active;
-    V.stage_g = red_g; V.stage_ld = red_l; V.stage_nb = 1; V.stage_rows = (int32_t)rows; V.lin_w = nullptr;
+    V.stage_g = red_g; V.stage_ld = red_l; V.stage_nb = 1; V.stage_rows = (int32_t)rows; V.lin_w = nullptr; V.grad0 = nullptr;
     return V;
   }
 
@@ -184,7 +204,7 @@ template <class T, class X> struct EngineCore {
     model = ModelCtx<T>();
     user_model_kind = MODEL_NONE; h_P.clear();
     M.stage_nb = 0;
-    M.beta_ref = nullptr; M.lin_w = nullptr;
+    M.beta_ref = nullptr; M.lin_w = nullptr; M.grad0 = nullptr;
   }
   int32_t model_simple(int kind) {
     free_model();
@@ -306,6 +326,33 @@ template <class T, class X> struct EngineCore {
       model.row_blocks = rb;
       alloc_stage(rb);
     }
+    model.N = N;
+    M.tau = T(tau);
+    user_model_kind = MODEL_LOGISTIC;
+    model.kind = MODEL_LOGISTIC; M.model_kind = MODEL_LOGISTIC;
+    return x.check(err);
+  }
+
+  // ≙ SURVEY.md §8d (config c5): the shard's rows [row0, row0 + N) of the synthetic design matrix, generated from
+  // Philox keyed by (data seed, global row index) — on the device for the tensor path, by the same definition on the
+  // host (synth_rows_host) for the deterministic path, which then takes the ordinary upload route
+  int32_t model_logistic_synth(uint64_t seed, int64_t row0, int64_t N, double tau, int32_t rb) {
+    if (N <= 0 || row0 < 0 || rb <= 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad synthetic logistic arguments");
+    if (dm.on) return fail(BNUTS_ERR_UNSUPPORTED, "dense metric is implemented for the Gaussian and iid normal targets");
+    const bool want_tensor = cfg.gradient_path == BNUTS_GRAD_TENSOR ||
+                             (cfg.gradient_path == BNUTS_GRAD_AUTO && sizeof(T) == 4 && X::has_tensor_path);
+    if (!want_tensor) {
+      std::vector<uint16_t> xb(size_t(N) * M.D);
+      std::vector<double> y(static_cast<size_t>(N));
+      synth_rows_host(seed, row0, N, M.D, xb.data(), y.data(), nullptr);
+      return model_logistic(xb.data(), BNUTS_X_BF16, y.data(), N, tau, rb);
+    }
+    if (sizeof(T) != 4 || !X::has_tensor_path)
+      return fail(BNUTS_ERR_UNSUPPORTED, "tensor gradient path needs dtype F32 on the CUDA engine");
+    free_model();
+    int32_t rc = x.logistic_tensor_setup_synth(*this, seed, row0, N, err);
+    if (rc) return rc;
+    model.tensor = true;
     model.N = N;
     M.tau = T(tau);
     user_model_kind = MODEL_LOGISTIC;

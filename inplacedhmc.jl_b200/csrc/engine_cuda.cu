@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_fold_partials(EngineMem<T> M, i
     T acc = T(0);
     if (d < M.D) {
       for (int b = 0; b < M.stage_nb; ++b) acc = acc + sg[b * bs + d];
+      if (M.grad0) acc = T((double)acc + M.grad0[d]);
       if (M.lin_w) lin = fma(M.lin_w[d], (double)M.stage_q[(int64_t)row * M.Dp + d], lin);
     }
     red_g[(int64_t)row * M.Dp + d] = acc;
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_fold_push(EngineMem<T> M, int r
       T acc = T(0);
       if (d < M.D) {
         for (int b = 0; b < M.stage_nb; ++b) acc = acc + sg[b * bs + d];
+        if (M.grad0) acc = T((double)acc + M.grad0[d]);
         if (M.lin_w) lin = fma(M.lin_w[d], (double)M.stage_q[(int64_t)row * M.Dp + d], lin);
       }
       for (int r = 0; r < V.world; ++r)
@@ -457,6 +459,46 @@ __global__ void __launch_bounds__(32) k_grad_logistic(const T* __restrict__ X, c
   }
 }
 
+// ------------------------------------------------------------------ synthetic rows (bnuts_model_logistic_synthetic)
+// ≙ SURVEY.md §8d, config c5: rows generated on the device from Philox keyed by (data seed, global row index), the
+// definition in bnuts_math.h (synth_*).  This file is compiled without FMA contraction, so the bits are the host
+// generator's.  k_synth_labels: one thread per row (eta accumulated in the defined order).  k_synth_rows: one
+// thread per four columns, coalesced 8-byte stores of the sign-folded bf16 row (X~_i = (2 y_i - 1) X_i).
+__global__ void k_synth_labels(uint64_t seed, long long row0, long long N, int D, const double* __restrict__ beta, uint8_t* y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  y[i] = synth_label(seed, (uint64_t)(row0 + i), D, beta) != 0.0 ? 1 : 0;
+}
+__global__ void k_synth_beta(uint64_t seed, int D, double* beta) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) beta[d] = synth_beta(seed, (uint32_t)d, D);
+}
+__global__ void k_synth_rows(uint64_t seed, long long row0, long long N, int D, int Dt, const uint8_t* __restrict__ y, uint16_t* Xb) {
+  const int nq = (D + 3) >> 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t / nq;
+  const int q = (int)(t - i * nq);
+  if (i >= N) return;
+  float x[4];
+  synth_x4(seed, (uint64_t)(row0 + i), (uint32_t)q, x);
+  const uint16_t flip = y[i] ? 0 : 0x8000;
+  uint16_t h[4];
+  for (int e = 0; e < 4; ++e) h[e] = (4 * q + e < D) ? (uint16_t)((f2u(x[e]) >> 16) ^ flip) : (uint16_t)0;
+  // Dt is a multiple of 64: the four columns of a quad never straddle the row end and the store is 8-byte aligned
+  *reinterpret_cast<uint2*>(Xb + i * Dt + 4 * q) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+}
+void synth_fill_xb(cudaStream_t s, uint64_t seed, int64_t row0, int64_t N, int32_t D, int32_t Dt, uint16_t* Xb) {
+  double* beta = nullptr;
+  uint8_t* y = nullptr;
+  if (cudaMalloc(&beta, (size_t)D * 8) != cudaSuccess || cudaMalloc(&y, (size_t)N) != cudaSuccess) { cudaFree(beta); return; }
+  k_synth_beta<<<(D + 127) / 128, 128, 0, s>>>(seed, D, beta);
+  k_synth_labels<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(seed, (long long)row0, (long long)N, D, beta, y);
+  const long long nt = (long long)N * ((D + 3) >> 2);
+  k_synth_rows<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(seed, (long long)row0, (long long)N, D, Dt, y, Xb);
+  cudaStreamSynchronize(s);
+  cudaFree(beta); cudaFree(y);
+}
+
 // ------------------------------------------------------------------ execution policy
 struct CudaExec {
   static constexpr bool has_tensor_path = true;
@@ -688,6 +730,9 @@ struct CudaExec {
   }
   template <class E> int32_t logistic_tensor_setup(E& eng, const void* Xh, int32_t xd, const double* y, int64_t N, std::string& err) {
     return logistic_tc_setup(tc, eng, Xh, xd, y, N, err);
+  }
+  template <class E> int32_t logistic_tensor_setup_synth(E& eng, uint64_t seed, int64_t row0, int64_t N, std::string& err) {
+    return logistic_tc_setup_synth(tc, eng, seed, row0, N, &synth_fill_xb, err);
   }
   // ---- row-sharded mode
   static NcclApi& nccl() { static NcclApi api; return api; }

@@ -109,7 +109,8 @@ template <int DT> struct SmemPlan {
   static constexpr int NSB = 3;                      // S/R buffers in TMEM
   static constexpr int OFF_B = 0;                    // 3 terms
   static constexpr int OFF_X = 3 * B_BYTES;
-  static constexpr int OFF_BAR = OFF_X + NS * X_BYTES;
+  static constexpr int OFF_R = OFF_X + NS * X_BYTES;   // per-row offsets of the single-term residual mode: NS x 128 floats
+  static constexpr int OFF_BAR = OFF_R + NS * 128 * 4;
   static constexpr int NBAR = 1 + 2 * NS + 3 * NSB + 2;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
 };
@@ -117,12 +118,24 @@ template <int DT> struct SmemPlan {
 // NK = round16(D)/16: K steps of GEMM1; dk = 16 NK is also N of GEMM2 (columns >= dk of the
 // 64-wide smem chunks are never read).  NK is a template parameter so the single MMA-issuing
 // thread runs fully unrolled code with constant descriptor offsets (it is latency-critical).
-template <int DT, int NK>
+//
+// RR (single-term residual, only with a reference point): the residual is carried about the reference,
+// r_i = r0_i + δ_i with r0_i = σ(−η̃0_i); X̃ᵀ·r0 is a constant vector the consumer adds in Float64 (EngineMem::grad0)
+// and only δ goes through GEMM2, as ONE bf16 term: its rounding error, 2⁻⁹·|δ|, is relative to δ, not to r, and
+// averages over the rows, so the gradient error is ≈ 1.7e-3·√(D/N)·|∇ℓ| at any distance from the reference
+// (numerical experiment in DESIGN.md §6).  That is below the fp32 tolerance of the path only for tall problems:
+// the host enables the mode when N ≥ 3.3e5·D (config 5: N = 1e8, D = 256), not for config 3 (N/D = 1e4: 1.7e-5).
+// An fp16 δ would be 8× finer (enough for config 3), but tcgen05.mma kind::f16 with an fp16 A operand next to the
+// bf16 B operand X̃ is an illegal instruction on sm_100a (measured), and X̃ is not exact in fp16.
+// The kernel reads c_i = ½ − r0_i (fp32, one
+// 512-byte bulk copy per X̃ stage) and forms δ = c_i − copysign(1/d − ½, η̃) in the FMA that produced r before:
+// no extra arithmetic, no hi/lo split, half the TMEM stores and half the GEMM2 MMAs.
+template <int DT, int NK, bool RR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBm, const __grid_constant__ CUtensorMap tmBl,
-              float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total, int nsplit, int flush_every,
-              int nterms) {
+              const float* __restrict__ c0, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total, int nsplit,
+              int flush_every, int nterms) {
   using P = SmemPlan<DT>;
   constexpr int dk = NK * 16;
   constexpr int NS = P::NS;
@@ -131,6 +144,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   extern __shared__ __align__(1024) unsigned char smem[];   // SW128 tiles need 1024 B alignment (checked below)
   unsigned char* sB = smem + P::OFF_B;
   unsigned char* sX = smem + P::OFF_X;
+  float* sR = reinterpret_cast<float*>(smem + P::OFF_R);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
   uint64_t* bar_b = bars;               // β tiles landed
   uint64_t* x_full = bars + 1;          // [NS]
@@ -189,9 +203,10 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         TC_TRACE(0, i, 0);
         mbar_wait(&x_empty[st], ph ^ 1u);
         TC_TRACE(0, i, 1);
-        mbar_expect_tx(&x_full[st], P::X_BYTES);
+        mbar_expect_tx(&x_full[st], P::X_BYTES + (RR ? ROWS * 4 : 0));
         for (int kc = 0; kc < KC; ++kc)
           tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK_BYTES, &x_full[st], kc * 64, (b0 + i) * ROWS);
+        if (RR) bulk_load_1d(sR + st * ROWS, c0 + (size_t)(b0 + i) * ROWS, ROWS * 4, &x_full[st]);
       }
     }
   } else if (warp == 1) {
@@ -261,7 +276,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         const uint32_t a = tmem_S + (uint32_t)buf * 128u;
         const uint32_t acc0 = in_period > 0 ? 1u : 0u;
 #pragma unroll
-        for (int term = 0; term < 2; ++term)
+        for (int term = 0; term < (RR ? 1 : 2); ++term)
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {   // 64-row halves of the block
             if (TCDBG & 4) continue;
@@ -343,9 +358,11 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         if (warp == 2) TC_TRACE(2, i, 3);
         tmem_ld_wait();
         if (warp == 2) TC_TRACE(2, i, 4);
-        uint32_t hi[16], lo[16];
+        uint32_t hi[16], lo[RR ? 1 : 16];
         float2 prod = ONE2;
         float as0 = 0.f, as1 = 0.f;
+        if (RR && cc == 0) mbar_wait(&x_full[i % NS], (uint32_t)(i / NS) & 1u);   // c of this block is visible (long complete)
+        const float2* c2p = reinterpret_cast<const float2*>(sR + (i % NS) * ROWS + ch * 32);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           // eta = H~ (natural units); t = exp(-|eta|) in (0,1]; d = 1 + t in (1,2]
@@ -358,12 +375,17 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const float2 hm = __fadd2_rn((TCDBG & 8) ? d2 : rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
           const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
                                         __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
-          const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
-          const uint32_t hh = pack_bf16(r2.x, r2.y);
-          const float2 hv = make_float2(__uint_as_float(hh << 16), __uint_as_float(hh & 0xffff0000u));
-          const float2 l2 = __ffma2_rn(hv, MONE2, r2);
-          hi[j] = hh;
-          lo[j] = pack_bf16(l2.x, l2.y);
+          if constexpr (RR) {
+            const float2 dl = __ffma2_rn(cs, MONE2, c2p[j]);   // δ = (½ − r0) − copysign(..) = r − r0, one rounding
+            hi[j] = pack_bf16(dl.x, dl.y);
+          } else {
+            const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
+            const uint32_t hh = pack_bf16(r2.x, r2.y);
+            const float2 hv = make_float2(__uint_as_float(hh << 16), __uint_as_float(hh & 0xffff0000u));
+            const float2 l2 = __ffma2_rn(hv, MONE2, r2);
+            hi[j] = hh;
+            lo[j] = pack_bf16(l2.x, l2.y);
+          }
         }
         bsum += lg2_approx(prod.x * prod.y);
         asum += as0 + as1;
@@ -373,7 +395,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         if (cc + 1 < CPW) have_next = load_item(i, cc + 1, true);
         else if (i + NG < nb) have_next = load_item(i + NG, 0, false);
         tmem_st16(tS, hi);
-        tmem_st16(tS + 16u, lo);
+        if constexpr (!RR) tmem_st16(tS + 16u, lo);
       }
       if (warp == 2) TC_TRACE(2, i, 6);
       tmem_st_wait();
@@ -439,22 +461,26 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
 }
 
-template <int DT, int NK> void launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
+template <int DT, int NK, bool RR> void launch_rr(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
   using P = SmemPlan<DT>;
   // the attribute is per device: one bit per device ordinal (engines on several GPUs may live in one process)
   static unsigned long long attr_done = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!((attr_done >> (dev & 63)) & 1ull)) {
-    tc.last = cudaFuncSetAttribute(k_logistic_tc<DT, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    tc.last = cudaFuncSetAttribute(k_logistic_tc<DT, NK, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     attr_done |= 1ull << (dev & 63);
   }
   const int tiles = (nrows + CHAINS - 1) / CHAINS;
   dim3 grid(tiles, nsplit);
   CUtensorMap m[4];
   for (int i = 0; i < 4; ++i) std::memcpy(&m[i], tc.tmaps[i], sizeof(CUtensorMap));
-  k_logistic_tc<DT, NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
-                                                           (int)(tc.Npad / ROWS), nsplit, tc.flush_every, tc.nterms);
+  k_logistic_tc<DT, NK, RR><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.c0, tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
+                                                               (int)(tc.Npad / ROWS), nsplit, tc.flush_every, tc.nterms);
+}
+template <int DT, int NK> void launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
+  if (tc.rterms == 1) launch_rr<DT, NK, true>(tc, s, nrows, nsplit);
+  else launch_rr<DT, NK, false>(tc, s, nrows, nsplit);
 }
 
 
@@ -819,16 +845,17 @@ template <int KC> struct SmemPlan3 {
   static constexpr int OFF_B = 0;
   static constexpr int OFF_X = 2 * B_BYTES;
   static constexpr int OFF_E = OFF_X + NS * X_BYTES;     // eta0: NS x 64 floats
-  static constexpr int OFF_BAR = OFF_E + NS * ROWS2 * 4;
+  static constexpr int OFF_R = OFF_E + NS * ROWS2 * 4;   // ½ − r0 (single-term residual mode): NS x 64 floats
+  static constexpr int OFF_BAR = OFF_R + NS * ROWS2 * 4;
   static constexpr int NBAR = 1 + 2 * NS + 3 * 4 + 2;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
 };
 
-template <int NK>
+template <int NK, bool RR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
-                 const __grid_constant__ CUtensorMap tmBm, const float* __restrict__ eta0, float* G, double* Ld, int nrows, int Dp,
-                 long long N, int nblk_total, int nsplit, int flush_every) {
+                 const __grid_constant__ CUtensorMap tmBm, const float* __restrict__ eta0, const float* __restrict__ c0, float* G,
+                 double* Ld, int nrows, int Dp, long long N, int nblk_total, int nsplit, int flush_every) {
   constexpr int KC = (NK + 3) / 4;
   using P = SmemPlan3<KC>;
   constexpr int dk = NK * 16;
@@ -837,6 +864,7 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   unsigned char* sB = smem + P::OFF_B;
   unsigned char* sX = smem + P::OFF_X;
   float* sE = reinterpret_cast<float*>(smem + P::OFF_E);
+  float* sR = reinterpret_cast<float*>(smem + P::OFF_R);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
   uint64_t* bar_b = bars;
   uint64_t* x_full = bars + 1;
@@ -887,10 +915,11 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int st = i % NS;
         const uint32_t ph = (uint32_t)(i / NS) & 1u;
         mbar_wait(&x_empty[st], ph ^ 1u);
-        mbar_expect_tx(&x_full[st], P::X_BYTES + ROWS2 * 4);
+        mbar_expect_tx(&x_full[st], P::X_BYTES + ROWS2 * 4 * (RR ? 2 : 1));
         for (int kc = 0; kc < KC; ++kc)
           tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK2, &x_full[st], kc * 64, (b0 + i) * ROWS2);
         bulk_load_1d(sE + st * ROWS2, eta0 + (size_t)(b0 + i) * ROWS2, ROWS2 * 4, &x_full[st]);
+        if (RR) bulk_load_1d(sR + st * ROWS2, c0 + (size_t)(b0 + i) * ROWS2, ROWS2 * 4, &x_full[st]);
       }
     }
   } else if (warp == 1) {
@@ -941,7 +970,7 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t a = tmem_S + (uint32_t)buf * 64u;
         const uint32_t acc0 = in_period > 0 ? 1u : 0u;
 #pragma unroll
-        for (int term = 0; term < 2; ++term)
+        for (int term = 0; term < (RR ? 1 : 2); ++term)
           mma_ts_run4(tmem_G, a + (uint32_t)(term * 16), xm, mn_hi, IDESC2, term ? 1u : acc0);
         if (elect_one()) { tc_commit(&x_empty[st]); tc_commit(&sr_empty[buf]); }
         ++in_period;
@@ -993,9 +1022,10 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (!have_next) have_next = load_item(i, true);
         mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);     // eta0 of this block is visible (long complete)
         const float4* e4 = reinterpret_cast<const float4*>(sE + st * ROWS2 + h * 32);
+        const float2* c2p = reinterpret_cast<const float2*>(sR + st * ROWS2 + h * 32);
         const uint32_t tS = tmem_S + (uint32_t)buf * 64u + lane_sel + (uint32_t)h * 32u;
         tmem_ld_wait();
-        uint32_t hi[16], lo[16];
+        uint32_t hi[16], lo[RR ? 1 : 16];
         float2 prod = ONE2;
         float as0 = 0.f, as1 = 0.f;
 #pragma unroll
@@ -1013,12 +1043,17 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
             const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (__float_as_uint(e0) & 0x80000000u)),
                                           __uint_as_float(__float_as_uint(hm.y) | (__float_as_uint(e1) & 0x80000000u)));
-            const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
-            const uint32_t hh = pack_bf16(r2.x, r2.y);
-            const float2 hv = make_float2(__uint_as_float(hh << 16), __uint_as_float(hh & 0xffff0000u));
-            const float2 l2 = __ffma2_rn(hv, MONE2, r2);
-            hi[j] = hh;
-            lo[j] = pack_bf16(l2.x, l2.y);
+            if constexpr (RR) {
+              const float2 dl = __ffma2_rn(cs, MONE2, c2p[j]);   // δ = r − r0 (see k_logistic_tc)
+              hi[j] = pack_bf16(dl.x, dl.y);
+            } else {
+              const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
+              const uint32_t hh = pack_bf16(r2.x, r2.y);
+              const float2 hv = make_float2(__uint_as_float(hh << 16), __uint_as_float(hh & 0xffff0000u));
+              const float2 l2 = __ffma2_rn(hv, MONE2, r2);
+              hi[j] = hh;
+              lo[j] = pack_bf16(l2.x, l2.y);
+            }
           }
         }
         bsum = lg2_approx(prod.x * prod.y);
@@ -1026,7 +1061,7 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         have_next = false;
         if (i + 2 < nb) have_next = load_item(i + 2, false);
         tmem_st16(tS, hi);
-        tmem_st16(tS + 16u, lo);
+        if constexpr (!RR) tmem_st16(tS + 16u, lo);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -1087,13 +1122,13 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
 }
 
-template <int NK> void launch256(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
+template <int NK, bool RR> void launch256_rr(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
   using P = SmemPlan3<(NK + 3) / 4>;
   static unsigned long long attr_done = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!((attr_done >> (dev & 63)) & 1ull)) {
-    tc.last = cudaFuncSetAttribute(k_logistic_tc256<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    tc.last = cudaFuncSetAttribute(k_logistic_tc256<NK, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     attr_done |= 1ull << (dev & 63);
   }
   const int tiles = (nrows + CHAINS - 1) / CHAINS;
@@ -1102,8 +1137,12 @@ template <int NK> void launch256(LogisticTC& tc, cudaStream_t s, int nrows, int 
   std::memcpy(&m[0], tc.tmaps[4], sizeof(CUtensorMap));
   std::memcpy(&m[1], tc.tmaps[1], sizeof(CUtensorMap));
   std::memcpy(&m[2], tc.tmaps[2], sizeof(CUtensorMap));
-  k_logistic_tc256<NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], tc.eta0, tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
-                                                        (int)(tc.Npad / ROWS2), nsplit, tc.flush_every);
+  k_logistic_tc256<NK, RR><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], tc.eta0, tc.c0, tc.G, tc.Ld, nrows, tc.Dp,
+                                                            (long long)tc.N, (int)(tc.Npad / ROWS2), nsplit, tc.flush_every);
+}
+template <int NK> void launch256(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
+  if (tc.rterms == 1) launch256_rr<NK, true>(tc, s, nrows, nsplit);
+  else launch256_rr<NK, false>(tc, s, nrows, nsplit);
 }
 
 }  // namespace
@@ -1175,7 +1214,11 @@ void LogisticTC::destroy() {
   if (colsum) cudaFree(colsum);
   if (beta_ref) cudaFree(beta_ref);
   if (eta0) cudaFree(eta0);
-  Xb = nullptr; colsum = nullptr; beta_ref = nullptr; eta0 = nullptr; ready = false; nterms = 3; variant = 128;
+  if (c0) cudaFree(c0);
+  if (grad0) cudaFree(grad0);
+  if (grad0_part) cudaFree(grad0_part);
+  Xb = nullptr; colsum = nullptr; beta_ref = nullptr; eta0 = nullptr; c0 = nullptr; grad0 = nullptr; grad0_part = nullptr;
+  ready = false; nterms = 3; rterms = 2; variant = 128;
 }
 
 namespace {
@@ -1216,6 +1259,49 @@ __global__ void k_write_eta0(const uint16_t* __restrict__ Xb, const float* __res
   eta0[i] = (float)acc;
 }
 }  // namespace
+namespace {
+constexpr int G0_BLOCKS = 1024;
+// one thread per data row: c_i = ½ − σ(−η̃0_i) = ½·tanh(η̃0_i / 2) with η̃0_i = X̃_i·beta_ref in Float64, rounded once
+// to fp32.  Any fp32 value near it would do: what matters is that grad0 below is formed from the STORED values.
+__global__ void k_write_c0(const uint16_t* __restrict__ Xb, const float* __restrict__ beta_ref, float* c0, long long N, long long Npad,
+                           int D, int Dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  float c = 0.f;
+  if (i < N) {
+    const uint16_t* xr = Xb + i * Dt;
+    double acc = 0.0;
+    for (int d = 0; d < D; ++d) acc = fma((double)bf16_val(xr[d]), (double)beta_ref[d], acc);
+    c = (float)(0.5 * tanh(0.5 * acc));
+  }
+  c0[i] = c;
+}
+// grad0_d = Σ_i X̃_id (½ − c_i): block b sums its contiguous range of rows (thread = column), then one block
+// adds the G0_BLOCKS partials in order — the same bits on every run and every rank
+__global__ void k_grad0_partial(const uint16_t* __restrict__ Xb, const float* __restrict__ c0, double* part, long long N, int D,
+                                int Dt, int Dp) {
+  const long long r0 = N * blockIdx.x / gridDim.x, r1 = N * (blockIdx.x + 1) / gridDim.x;
+  for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
+    double acc = 0.0;
+    if (d < D)
+      for (long long i = r0; i < r1; ++i) acc = fma((double)bf16_val(Xb[i * Dt + d]), c0 ? 0.5 - (double)c0[i] : 1.0, acc);
+    part[(size_t)blockIdx.x * Dp + d] = acc;
+  }
+}
+__global__ void k_grad0_sum(const double* __restrict__ part, double* grad0, int nb, int Dp) {
+  for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
+    double acc = 0.0;
+    for (int b = 0; b < nb; ++b) acc += part[(size_t)b * Dp + d];
+    grad0[d] = acc;
+  }
+}
+}  // namespace
+void logistic_tc_write_residual_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev) {
+  k_write_c0<<<(unsigned)((tc.Npad + 255) / 256), 256, 0, s>>>(tc.Xb, beta_ref_dev, tc.c0, (long long)tc.N, (long long)tc.Npad, tc.D,
+                                                              tc.Dt);
+  k_grad0_partial<<<G0_BLOCKS, 128, 0, s>>>(tc.Xb, tc.c0, tc.grad0_part, (long long)tc.N, tc.D, tc.Dt, tc.Dp);
+  k_grad0_sum<<<1, 128, 0, s>>>(tc.grad0_part, tc.grad0, G0_BLOCKS, tc.Dp);
+}
 void logistic_tc_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev) {
   if (tc.variant == 256) {
     k_write_eta0<<<(unsigned)((tc.N + 255) / 256), 256, 0, s>>>(tc.Xb, beta_ref_dev, tc.eta0, (long long)tc.N, tc.D, tc.Dt);
@@ -1229,8 +1315,9 @@ void logistic_tc_init_stage(LogisticTC& tc, cudaStream_t s, uint16_t* bh) {
   k_init_stage<<<(tc.C + 127) / 128, 128, 0, s>>>(bh, tc.C, tc.D, tc.Dt);
 }
 
-int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, int64_t N, int32_t C, int32_t D, int32_t Dp,
-                          std::string& err) {
+namespace {
+// shape of the problem: K / N of the MMAs, tile width, kernel variant, padded row count, environment overrides
+void tc_shape(LogisticTC& tc, int64_t N, int32_t C, int32_t D, int32_t Dp) {
   tc.destroy();
   tc.C = C; tc.D = D; tc.Dp = Dp; tc.N = N;
   tc.aug = (D + 3 <= 128) ? 1 : 0;
@@ -1248,6 +1335,50 @@ int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, i
   if (fe) tc.flush_every = std::atoi(fe);
   const char* se = std::getenv("BNUTS_TC_NSPLIT");
   tc.force_nsplit = se ? std::atoi(se) : 0;
+}
+// device buffers (zeroed) and the split plan
+int32_t tc_alloc(LogisticTC& tc, std::string& err) {
+  const size_t xbytes = size_t(tc.Npad) * tc.Dt * 2;
+  if (cudaMalloc(&tc.Xb, xbytes) != cudaSuccess || cudaMalloc(&tc.colsum, size_t(tc.Dp) * 8) != cudaSuccess ||
+      cudaMalloc(&tc.beta_ref, size_t(tc.Dp) * 4) != cudaSuccess) {
+    err = "device allocation failed (tensor path X)";
+    return BNUTS_ERR_CUDA;
+  }
+  cudaMemset(tc.Xb, 0, xbytes);
+  cudaMemset(tc.colsum, 0, size_t(tc.Dp) * 8);
+  cudaMemset(tc.beta_ref, 0, size_t(tc.Dp) * 4);
+  if (cudaMalloc(&tc.c0, size_t(tc.Npad) * 4) != cudaSuccess || cudaMalloc(&tc.grad0, size_t(tc.Dp) * 8) != cudaSuccess ||
+      cudaMalloc(&tc.grad0_part, size_t(G0_BLOCKS) * tc.Dp * 8) != cudaSuccess) {
+    err = "device allocation failed (residual reference)";
+    return BNUTS_ERR_CUDA;
+  }
+  cudaMemset(tc.c0, 0, size_t(tc.Npad) * 4);
+  cudaMemset(tc.grad0, 0, size_t(tc.Dp) * 8);
+  if (tc.variant == 256) {
+    if (cudaMalloc(&tc.eta0, size_t(tc.Npad) * 4) != cudaSuccess) { err = "device allocation failed (eta0)"; return BNUTS_ERR_CUDA; }
+    cudaMemset(tc.eta0, 0, size_t(tc.Npad) * 4);
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&tc.sms, cudaDevAttrMultiProcessorCount, dev);
+  if (tc.sms <= 0) tc.sms = 148;
+  // staging rows needed for the partial outputs: max over nrows of nsplit(nrows) * nrows
+  tc.max_splits = 3 * tc.sms;
+  const int64_t nblk = tc.Npad / ROWS;
+  if (tc.max_splits > nblk) tc.max_splits = (int)nblk;
+  int64_t worst = tc.C;
+  for (int tiles = 1; tiles <= (tc.C + CHAINS - 1) / CHAINS; ++tiles) {
+    const int nr = std::min<int>(tc.C, tiles * CHAINS);
+    worst = std::max<int64_t>(worst, (int64_t)tc.plan_splits(nr) * nr);
+  }
+  tc.partial_rows = worst;
+  return 0;
+}
+}  // namespace
+
+int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, int64_t N, int32_t C, int32_t D, int32_t Dp,
+                          std::string& err) {
+  tc_shape(tc, N, C, D, Dp);
   // sign-folded design matrix: row i multiplied by (2 y_i - 1) (flip of the bf16 sign bit)
   std::vector<uint16_t> xp(size_t(tc.Npad) * tc.Dt, 0);
   std::vector<double> cs(size_t(Dp), 0.0);
@@ -1264,32 +1395,26 @@ int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xh, const double* y, i
       cs[d] += double(bf16_val(dst[d]));
     }
   }
-  if (cudaMalloc(&tc.Xb, xp.size() * 2) != cudaSuccess || cudaMalloc(&tc.colsum, cs.size() * 8) != cudaSuccess ||
-      cudaMalloc(&tc.beta_ref, size_t(Dp) * 4) != cudaSuccess) {
-    err = "device allocation failed (tensor path X)";
-    return BNUTS_ERR_CUDA;
-  }
+  const int32_t rc = tc_alloc(tc, err);
+  if (rc) return rc;
   cudaMemcpy(tc.Xb, xp.data(), xp.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(tc.colsum, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice);
-  cudaMemset(tc.beta_ref, 0, size_t(Dp) * 4);
-  if (tc.variant == 256) {
-    if (cudaMalloc(&tc.eta0, size_t(tc.Npad) * 4) != cudaSuccess) { err = "device allocation failed (eta0)"; return BNUTS_ERR_CUDA; }
-    cudaMemset(tc.eta0, 0, size_t(tc.Npad) * 4);
-  }
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&tc.sms, cudaDevAttrMultiProcessorCount, dev);
-  if (tc.sms <= 0) tc.sms = 148;
-  // staging rows needed for the partial outputs: max over nrows of nsplit(nrows) * nrows
-  tc.max_splits = 3 * tc.sms;
-  const int64_t nblk = tc.Npad / ROWS;
-  if (tc.max_splits > nblk) tc.max_splits = (int)nblk;
-  int64_t worst = C;
-  for (int tiles = 1; tiles <= (C + CHAINS - 1) / CHAINS; ++tiles) {
-    const int nr = std::min<int>(C, tiles * CHAINS);
-    worst = std::max<int64_t>(worst, (int64_t)tc.plan_splits(nr) * nr);
-  }
-  tc.partial_rows = worst;
+  return 0;
+}
+
+// ≙ SURVEY.md §8d, config c5: the rows of this shard are generated ON THE DEVICE from Philox keyed by (data seed, global
+// row index) (bnuts_math.h, synth_*), sign-folded on the way; nothing but the seed crosses PCIe.  `fill` is the
+// generator kernel pair of engine_cuda.cu (compiled without FMA contraction: the same bits as the host generator).
+int32_t logistic_tc_build_synth(LogisticTC& tc, uint64_t seed, int64_t row0, int64_t N, int32_t C, int32_t D, int32_t Dp,
+                                cudaStream_t s, SynthFillFn fill, std::string& err) {
+  tc_shape(tc, N, C, D, Dp);
+  const int32_t rc = tc_alloc(tc, err);
+  if (rc) return rc;
+  fill(s, seed, row0, N, D, tc.Dt, tc.Xb);
+  // column sums of X~ in Float64, fixed order (same two-pass reduction as grad0, weight 1)
+  k_grad0_partial<<<G0_BLOCKS, 128, 0, s>>>(tc.Xb, nullptr, tc.grad0_part, (long long)tc.N, tc.D, tc.Dt, tc.Dp);
+  k_grad0_sum<<<1, 128, 0, s>>>(tc.grad0_part, tc.colsum, G0_BLOCKS, tc.Dp);
+  if (cudaStreamSynchronize(s) != cudaSuccess) { err = "synthetic data generation failed"; return BNUTS_ERR_CUDA; }
   return 0;
 }
 

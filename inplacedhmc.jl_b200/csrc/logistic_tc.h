@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -27,6 +28,11 @@ struct LogisticTC {
   double* colsum = nullptr;  // [Dp] column sums of X~ (linear part of the log density)
   float* beta_ref = nullptr; // [Dp] reference point (zeros when none is set)
   float* eta0 = nullptr;     // [Npad] X~ beta_ref per row (k_logistic_tc256 only)
+  // single-term residual about the reference (see k_logistic_tc, template parameter RR)
+  float* c0 = nullptr;       // [Npad] ½ − r0_i, r0_i = σ(−η̃0_i) (zero in the padding rows)
+  double* grad0 = nullptr;   // [Dp] X̃ᵀ·r0 in Float64 from the stored fp32 values: added by the consumer (EngineMem::grad0)
+  double* grad0_part = nullptr;  // [G0_BLOCKS][Dp] scratch of its two-pass (deterministic) reduction
+  int32_t rterms = 2;        // terms of the residual operand: 2 (r = rh + rl, bf16) or 1 (δ = r − r0 in bf16, with a reference point and N ≥ 3.3e5·D)
   // borrowed from the engine
   const uint16_t* bh = nullptr; const uint16_t* bm = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
   float* G = nullptr;        // [nsplit][rows][Dp]
@@ -46,12 +52,22 @@ struct LogisticTC {
 int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xbf16_host /*[N][D]*/, const double* y, int64_t N,
                           int32_t C, int32_t D, int32_t Dp, std::string& err);
 
+// the same with the rows generated on the device (bnuts_model_logistic_synthetic); `fill` writes the sign-folded
+// bf16 rows [row0, row0 + N) of the synthetic matrix into Xb [Npad][Dt]
+typedef void (*SynthFillFn)(cudaStream_t s, uint64_t seed, int64_t row0, int64_t N, int32_t D, int32_t Dt, uint16_t* Xb);
+int32_t logistic_tc_build_synth(LogisticTC& tc, uint64_t seed, int64_t row0, int64_t N, int32_t C, int32_t D, int32_t Dp,
+                                cudaStream_t s, SynthFillFn fill, std::string& err);
+
 int32_t logistic_tc_maps(LogisticTC& tc, std::string& err);
 
 // write H~0 = X~·beta_ref (three bf16 terms) into the reserved columns (beta_ref == nullptr: clear them)
 void logistic_tc_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev);
+// c0_i = ½ − σ(−X̃_i·beta_ref) per row and grad0 = X̃ᵀ·(½ − c0) in Float64 (fixed summation order)
+void logistic_tc_write_residual_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev);
 // staging rows: 1.0 in the reserved columns of the high term
 void logistic_tc_init_stage(LogisticTC& tc, cudaStream_t s, uint16_t* bh);
+
+template <class E> int32_t logistic_tc_attach(LogisticTC& tc, E& eng, std::string& err);
 
 template <class E>
 int32_t logistic_tc_setup(LogisticTC& tc, E& eng, const void* Xh, int32_t xd, const double* y, int64_t N, std::string& err) {
@@ -77,24 +93,45 @@ int32_t logistic_tc_setup(LogisticTC& tc, E& eng, const void* Xh, int32_t xd, co
     }
     int32_t rc = logistic_tc_build(tc, xb.data(), y, N, M.C, M.D, M.Dp, err);
     if (rc) return rc;
-    // staging owned by the engine: bf16 hi/lo of q, partial outputs
-    M.Dt = tc.Dt;
-    const size_t nbt = size_t(M.C) * tc.Dt;
-    M.stage_bh = eng.x.template alloc<uint16_t>(nbt);
-    M.stage_bm = eng.x.template alloc<uint16_t>(nbt);
-    M.stage_bl = eng.x.template alloc<uint16_t>(nbt);
-    eng.x.zero(M.stage_bh, nbt * 2); eng.x.zero(M.stage_bm, nbt * 2); eng.x.zero(M.stage_bl, nbt * 2);
-    eng.alloc_stage(1, size_t(tc.partial_rows));
-    M.stage_ld = eng.x.template alloc<double>(size_t(tc.partial_rows));
-    eng.x.zero(M.stage_ld, size_t(tc.partial_rows) * sizeof(double));
-    tc.bh = M.stage_bh; tc.bm = M.stage_bm; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.Ld = M.stage_ld;
-    logistic_tc_init_stage(tc, eng.x.stream, M.stage_bh);
-    M.lin_w = tc.colsum;
-    M.beta_ref = tc.beta_ref;
-    rc = logistic_tc_maps(tc, err);
+    return logistic_tc_attach(tc, eng, err);
+  }
+}
+
+// engine-owned staging of the tensor path (bf16 terms of q, partial outputs), tensor maps
+template <class E>
+int32_t logistic_tc_attach(LogisticTC& tc, E& eng, std::string& err) {
+  auto& M = eng.M;
+  M.Dt = tc.Dt;
+  const size_t nbt = size_t(M.C) * tc.Dt;
+  M.stage_bh = eng.x.template alloc<uint16_t>(nbt);
+  M.stage_bm = eng.x.template alloc<uint16_t>(nbt);
+  M.stage_bl = eng.x.template alloc<uint16_t>(nbt);
+  eng.x.zero(M.stage_bh, nbt * 2); eng.x.zero(M.stage_bm, nbt * 2); eng.x.zero(M.stage_bl, nbt * 2);
+  eng.alloc_stage(1, size_t(tc.partial_rows));
+  M.stage_ld = eng.x.template alloc<double>(size_t(tc.partial_rows));
+  eng.x.zero(M.stage_ld, size_t(tc.partial_rows) * sizeof(double));
+  tc.bh = M.stage_bh; tc.bm = M.stage_bm; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.Ld = M.stage_ld;
+  logistic_tc_init_stage(tc, eng.x.stream, M.stage_bh);
+  M.lin_w = tc.colsum;
+  M.beta_ref = tc.beta_ref;
+  const int32_t rc = logistic_tc_maps(tc, err);
+  if (rc) return rc;
+  eng.model.Npad = tc.Npad;
+  return 0;
+}
+
+template <class E>
+int32_t logistic_tc_setup_synth(LogisticTC& tc, E& eng, uint64_t seed, int64_t row0, int64_t N, SynthFillFn fill, std::string& err) {
+  using T = typename std::remove_reference<decltype(*eng.M.zs)>::type;
+  if constexpr (!std::is_same<T, float>::value) {
+    err = "tensor gradient path needs dtype F32";
+    return BNUTS_ERR_UNSUPPORTED;
+  } else {
+    auto& M = eng.M;
+    if (M.D > 256) { err = "tensor gradient path supports D <= 256 in this build"; return BNUTS_ERR_UNSUPPORTED; }
+    const int32_t rc = logistic_tc_build_synth(tc, seed, row0, N, M.C, M.D, M.Dp, eng.x.stream, fill, err);
     if (rc) return rc;
-    eng.model.Npad = tc.Npad;
-    return 0;
+    return logistic_tc_attach(tc, eng, err);
   }
 }
 
@@ -115,6 +152,8 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
     if (!tc.ready) { err = "reference point needs the tensor gradient path"; return BNUTS_ERR_UNSUPPORTED; }
     // back to the exact path (D <= 128) / to the zero reference (D > 128: always two terms, see k_logistic_tc256)
     tc.nterms = tc.variant == 256 ? 2 : 3;
+    tc.rterms = 2;
+    M.grad0 = nullptr;
     x.zero(tc.beta_ref, size_t(M.Dp) * sizeof(float));
     logistic_tc_write_reference(tc, x.stream, nullptr);
     if (!beta_ref) return x.check(err);
@@ -149,6 +188,16 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
     x.h2d(tc.beta_ref, b.data(), size_t(M.Dp) * sizeof(float));
     logistic_tc_write_reference(tc, x.stream, tc.beta_ref);
     tc.nterms = 2;
+    // residual about the reference as well: ONE bf16 term of δ = r − r0 instead of r = rh + rl.  Its error is
+    // ≈ 1.7e-3·√(D/N)·|∇ℓ| (see k_logistic_tc), so the mode is taken when N ≥ 3.3e5·D (3e-6, a third of the fp32
+    // tolerance of the path; N counts the rows of the whole group); BNUTS_TC_RREF=0 / 1 forces it off / on.
+    const char* rr = std::getenv("BNUTS_TC_RREF");
+    const bool rr_auto = double(tc.N) * double(eng.reduce_world()) >= 3.3e5 * double(M.D);
+    if (tc.variant != 64 && (rr ? std::atoi(rr) != 0 : rr_auto)) {
+      logistic_tc_write_residual_reference(tc, x.stream, tc.beta_ref);
+      tc.rterms = 1;
+      M.grad0 = tc.grad0;
+    }
     return x.check(err);
   }
 }

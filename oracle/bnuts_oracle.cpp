@@ -876,6 +876,34 @@ int32_t bnuts_model_gaussian(bnuts_engine* e, const double* P) { DISPATCH(e, mod
 int32_t bnuts_model_logistic(bnuts_engine* e, const void* X, int32_t xd, const double* y, int64_t N, double tau, int32_t rb) {
   DISPATCH(e, model_logistic(E, X, xd, y, N, tau, rb), model_logistic(E, X, xd, y, N, tau, rb));
 }
+// synthetic rows (include/bnuts.h; definition in bnuts_math.h, synth_*): generated here row by row, then the ordinary model
+int32_t bnuts_synth_logistic_rows(uint64_t seed, int64_t row0, int64_t nrows, int32_t D, uint16_t* X, double* y, double* beta_true) {
+  if (nrows < 0 || row0 < 0 || D <= 0) return BNUTS_ERR_INVALID_ARGUMENT;
+  std::vector<double> beta(static_cast<size_t>(D));
+  for (int32_t d = 0; d < D; ++d) beta[size_t(d)] = bn::synth_beta(seed, uint32_t(d), D);
+  if (beta_true) std::copy(beta.begin(), beta.end(), beta_true);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nrows; ++i) {
+    const uint64_t row = uint64_t(row0 + i);
+    float x[4];
+    if (X)
+      for (int32_t q = 0; 4 * q < D; ++q) {
+        bn::synth_x4(seed, row, uint32_t(q), x);
+        for (int e = 0; e < 4 && 4 * q + e < D; ++e) X[size_t(i) * D + 4 * q + e] = uint16_t(bn::f2u(x[e]) >> 16);
+      }
+    if (y) y[i] = bn::synth_label(seed, row, D, beta.data());
+  }
+  return 0;
+}
+int32_t bnuts_model_logistic_synthetic(bnuts_engine* e, uint64_t seed, int64_t row0, int64_t N, double tau, int32_t rb) {
+  if (!e || N <= 0 || row0 < 0) return BNUTS_ERR_INVALID_ARGUMENT;
+  AnyEngine* ae = reinterpret_cast<AnyEngine*>(e);
+  const int32_t D = ae->dtype == BNUTS_F64 ? ae->e64->D : ae->e32->D;
+  std::vector<uint16_t> X(size_t(N) * D);
+  std::vector<double> y(static_cast<size_t>(N));
+  bnuts_synth_logistic_rows(seed, row0, N, D, X.data(), y.data(), nullptr);
+  return bnuts_model_logistic(e, X.data(), BNUTS_X_BF16, y.data(), N, tau, rb);
+}
 // numerical device of the CUDA tensor path; the oracle computes in plain arithmetic: accepted, no effect
 int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double*) { return e ? 0 : BNUTS_ERR_INVALID_ARGUMENT; }
 // row sharding is a property of the device engine's data layout; the oracle always sees all rows

@@ -87,7 +87,22 @@ def main():
         for dtype, nm in ((bn.F64, "f64"), (bn.F32, "f32")):
             arrs = run_protocol(bn, lib, kind, dtype)
             np.savez_compressed(os.path.join(HERE, f"protocol_{kind}_{nm}.npz"), **{f"a{i:02d}": np.asarray(a) for i, a in enumerate(arrs)})
+    synth_fixture(lib)
     print("golden fixtures written to", HERE)
+
+
+SYNTH = dict(seed=5, D=10, blocks=((0, 6), (4294967294, 4), (12500000 * 7 + 3, 3)))   # row ranges incl. one across 2^32
+
+
+def synth_fixture(lib):
+    """Frozen rows of the synthetic design matrix (include/bnuts.h, bnuts_model_logistic_synthetic) from the oracle's
+    host generator: pins the (seed, row, column) -> value map, including row indices beyond 32 bits."""
+    out = {}
+    for k, (r0, n) in enumerate(SYNTH["blocks"]):
+        X, y, beta = bn.synth_logistic_rows(SYNTH["seed"], r0, n, SYNTH["D"], lib=lib)
+        out.update({f"X{k}": X, f"y{k}": y})
+    out["beta"] = beta
+    np.savez_compressed(os.path.join(HERE, "synth_rows.npz"), **out)
 
 
 if __name__ == "__main__":

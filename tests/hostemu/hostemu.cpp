@@ -112,6 +112,10 @@ struct HostExec {
     err = "tensor path is CUDA-only";
     return BNUTS_ERR_UNSUPPORTED;
   }
+  template <class E> int32_t logistic_tensor_setup_synth(E&, uint64_t, int64_t, int64_t, std::string& err) {
+    err = "tensor path is CUDA-only";
+    return BNUTS_ERR_UNSUPPORTED;
+  }
   // ---- row-sharded mode (same semantics as the CUDA policy, serial loops)
   static int32_t nccl_unique_id(uint8_t*) { return BNUTS_ERR_UNSUPPORTED; }
   int32_t nccl_init(const uint8_t*, int, int, std::string& err) { err = "NCCL is CUDA-only"; return BNUTS_ERR_UNSUPPORTED; }
