@@ -171,6 +171,8 @@ template <class T, class X> struct EngineCore {
   // All engines of the group must hold all chains (same seed, chain_offset, positions).
   int32_t enable_reduce(bnuts_allreduce_fn fn, void* ctx) {
     if (model.kind != MODEL_LOGISTIC) return fail(BNUTS_ERR_NO_MODEL, "row sharding needs the logistic model (set it first)");
+    if (x.reference_mode() == 2)
+      return fail(BNUTS_ERR_UNSUPPORTED, "set the reference point after enabling row sharding (its single-GPU mode is in force)");
     free_reduce();
     const size_t CD = size_t(M.C) * M.Dp;
     red_g = x.template alloc<T>(CD); red_l = x.template alloc<double>(M.C);
@@ -536,7 +538,7 @@ template <class T, class X> struct EngineCore {
       if (np_known > 0) {
         M.stage_nb = x.gradient(*this, (int)np_known);
         M.stage_rows = (int32_t)np_known;
-        counters.kernel_launches += 1;
+        counters.kernel_launches += x.launches_per_gradient();
       }
       x.advance_async(M, rp, 1, (int)(step % X::RING), (int)(step & 1));
       counters.kernel_launches += 1;
@@ -569,7 +571,7 @@ template <class T, class X> struct EngineCore {
       if (np > 0 && batched) {
         M.stage_nb = x.gradient(*this, (int)np);
         M.stage_rows = (int32_t)np;
-        counters.kernel_launches += 1;
+        counters.kernel_launches += x.launches_per_gradient();
         counters.gradient_rows += np;
         if (reduce_on && p2p_on) {   // fold + push over NVLink in one kernel, wait + sum in rank order in another
           p2p_seq += 1;

@@ -827,6 +827,8 @@ struct CudaExec {
   template <class E> int32_t logistic_reference(E& eng, const double* beta_ref, std::string& err) {
     return logistic_tc_set_reference(tc, eng, beta_ref, err);
   }
+  int reference_mode() const { return tc.ready ? tc.rmode : 0; }
+  int launches_per_gradient() const { return reference_mode() == 2 ? 2 : 1; }   // k_lin_ref follows the tensor kernel
   template <class T> void metric_update(const EngineMem<T>& M, int N, double lambda) {
     k_metric<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, N, lambda);
   }

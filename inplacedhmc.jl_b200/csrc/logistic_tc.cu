@@ -130,11 +130,28 @@ template <int DT> struct SmemPlan {
 // The kernel reads c_i = ½ − r0_i (fp32, one
 // 512-byte bulk copy per X̃ stage) and forms δ = c_i − copysign(1/d − ½, η̃) in the FMA that produced r before:
 // no extra arithmetic, no hi/lo split, half the TMEM stores and half the GEMM2 MMAs.
-template <int DT, int NK, bool RR>
+//
+// RR == 2 (quadratic remainder; opt-in with BNUTS_TC_QREF=1, D <= 125, rows not sharded): the first-order part of δ is
+// taken out as well.  With w_i ≈ σ'(η̃0_i) stored per row, ρ_i = δ_i + w_i (η̃_i − η̃0_i) = O((η̃ − η̃0)²) is what goes
+// through GEMM2 as one bf16 term, and
+//     ∇ℓ = g0 − H0 (β − β0) + X̃ᵀρ − τβ,    H0 = X̃ᵀ diag(w) X̃  (D x D, Float64 from the stored fp32 w, kept as fp32),
+// where g0 − H0 (β − β0) is a D x D mat-vec per chain done by k_lin_ref after this kernel (it adds into the partial
+// of split 0).  The rounded quantity is now second order: its error is 1.7e-3·√(D/N)·|X̃ᵀρ|, about 0.2·|η̃ − η̃0| times
+// the figure of the δ mode, i.e. < 1e-6·|∇ℓ| within tens of posterior standard deviations of the reference at
+// N/D = 1e4; and because k_lin_ref uses the exact fp32 β − β0 while the kernel's η̃ uses its two-term bf16 split, the
+// truncation error of that split (2⁻¹⁷·|H (β − β0)| in the other modes) cancels to first order.  Far from the
+// reference (|η̃ − η̃0| ≳ 2) H0 (β − β0) outgrows the saturating gradient and the cancellation costs accuracy
+// (measured in tests/test_gpu_parity.py); the reference check of the host keeps β0 at the mode.
+// The kernel needs two constants per row, w and a = c − w η̃0 (ρ = fma(w, η̃, a) − copysign(..): two FMAs, the same count
+// as forming r), stored pairwise as (w0, w1, a0, a1) so one broadcast 16-byte shared-memory load serves two rows:
+// 1 024 B per X̃ stage, in the third β tile, which is unused with two terms.  (A first version with three constants per
+// row and 8-byte loads was slower than the two-term kernel: 48 instead of 16 shared-memory instructions per 32-row chunk
+// and warp saturated the shared-memory pipe.)
+template <int DT, int NK, int RR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBm, const __grid_constant__ CUtensorMap tmBl,
-              const float* __restrict__ c0, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total, int nsplit,
+              const float* __restrict__ c0, const float* __restrict__ aux, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total, int nsplit,
               int flush_every, int nterms) {
   using P = SmemPlan<DT>;
   constexpr int dk = NK * 16;
@@ -145,6 +162,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   unsigned char* sB = smem + P::OFF_B;
   unsigned char* sX = smem + P::OFF_X;
   float* sR = reinterpret_cast<float*>(smem + P::OFF_R);
+  float* sQ = reinterpret_cast<float*>(sB + 2 * P::B_BYTES);   // RR == 2: per-row constants (w, a) in the unused third β tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
   uint64_t* bar_b = bars;               // β tiles landed
   uint64_t* x_full = bars + 1;          // [NS]
@@ -186,11 +204,11 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0 && nb > 0) {
-      mbar_expect_tx(bar_b, 3 * P::B_BYTES);
+      mbar_expect_tx(bar_b, (RR == 2 ? 2 : 3) * P::B_BYTES);
       for (int kc = 0; kc < KC; ++kc) {
         tma_load_2d(&tmBh, sB + 0 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
         tma_load_2d(&tmBm, sB + 1 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
-        tma_load_2d(&tmBl, sB + 2 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+        if (RR != 2) tma_load_2d(&tmBl, sB + 2 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
       }
       constexpr int PF = BNUTS_TC_PREFETCH;   // L2 prefetch distance in row blocks (0: none)
       for (int i = 0; i < PF && i < nb; ++i)
@@ -203,10 +221,11 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         TC_TRACE(0, i, 0);
         mbar_wait(&x_empty[st], ph ^ 1u);
         TC_TRACE(0, i, 1);
-        mbar_expect_tx(&x_full[st], P::X_BYTES + (RR ? ROWS * 4 : 0));
+        mbar_expect_tx(&x_full[st], P::X_BYTES + (RR == 1 ? ROWS * 4 : RR == 2 ? 2 * ROWS * 4 : 0));
         for (int kc = 0; kc < KC; ++kc)
           tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK_BYTES, &x_full[st], kc * 64, (b0 + i) * ROWS);
-        if (RR) bulk_load_1d(sR + st * ROWS, c0 + (size_t)(b0 + i) * ROWS, ROWS * 4, &x_full[st]);
+        if (RR == 1) bulk_load_1d(sR + st * ROWS, c0 + (size_t)(b0 + i) * ROWS, ROWS * 4, &x_full[st]);
+        if (RR == 2) bulk_load_1d(sQ + st * 2 * ROWS, aux + (size_t)(b0 + i) * 2 * ROWS, 2 * ROWS * 4, &x_full[st]);
       }
     }
   } else if (warp == 1) {
@@ -363,6 +382,8 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         float as0 = 0.f, as1 = 0.f;
         if (RR && cc == 0) mbar_wait(&x_full[i % NS], (uint32_t)(i / NS) & 1u);   // c of this block is visible (long complete)
         const float2* c2p = reinterpret_cast<const float2*>(sR + (i % NS) * ROWS + ch * 32);
+        // RR == 2: one 16-byte record per PAIR of rows, (w0, w1, a0, a1) with a = c − w η̃0: one broadcast LDS.128 per pair
+        const float4* q4p = reinterpret_cast<const float4*>(sQ + (i % NS) * 2 * ROWS + ch * 64);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           // eta = H~ (natural units); t = exp(-|eta|) in (0,1]; d = 1 + t in (1,2]
@@ -375,9 +396,14 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const float2 hm = __fadd2_rn((TCDBG & 8) ? d2 : rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
           const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
                                         __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
-          if constexpr (RR) {
+          if constexpr (RR == 1) {
             const float2 dl = __ffma2_rn(cs, MONE2, c2p[j]);   // δ = (½ − r0) − copysign(..) = r − r0, one rounding
             hi[j] = pack_bf16(dl.x, dl.y);
+          } else if constexpr (RR == 2) {
+            const float4 k4 = q4p[j];
+            const float2 lin = __ffma2_rn(make_float2(k4.x, k4.y), make_float2(e0, e1), make_float2(k4.z, k4.w));   // c + w (η̃ − η̃0)
+            const float2 rho = __ffma2_rn(cs, MONE2, lin);                                                           // ρ = δ + w Δη̃ = O(Δη̃²)
+            hi[j] = pack_bf16(rho.x, rho.y);
           } else {
             const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
             const uint32_t hh = pack_bf16(r2.x, r2.y);
@@ -461,7 +487,320 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
 }
 
-template <int DT, int NK, bool RR> void launch_rr(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
+// =====================================================================================================
+// k_logistic_tcq — the quadratic-remainder mode (RR == 2 above) on a DECOUPLED pipeline.
+//
+// Measured (ncu launch list, profiles/): halving the GEMM2 work in k_logistic_tc<.., 2> did not shorten that kernel at all —
+// its period is set by the loop S -> elementwise -> R -> GEMM2 -> buffer free -> GEMM1 over three in-place S/R buffers,
+// not by a pipe.  A single-term residual is 64 TMEM columns instead of 128, so here R gets buffers of its own:
+//     TMEM = G [0, 128) | S_0, S_1 [128, 384) | R_0, R_1 [384, 512)
+// and an S buffer goes back to GEMM1 as soon as the elementwise warps hold its values in registers (s_empty), not
+// after GEMM2.  The two elementwise groups own one (S, R) pair each (block i -> group i & 1), so a group's chain is
+//     GEMM1(i+2) runs while the group finishes block i;  GEMM2(i) runs while it starts block i+2.
+// Same arithmetic as k_logistic_tc<.., 2>, same split / flush / epilogue conventions, same outputs.
+__device__ __forceinline__ void mma_ts_run4c(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t acc_first) {
+  // four K steps of one 64-row half block, A compact in TMEM (8 columns per K step), B advances 2048 B = 128 units
+  asm volatile("{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 rb;\n\t.reg .b32 ta, bl;\n\t"
+               "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+               "mov.b32 ta, %1;\n\tmov.b32 bl, %2;\n\t" BN_MMA_TS("pa")
+               "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 128;\n\t" BN_MMA_TS("pt")
+               "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 128;\n\t" BN_MMA_TS("pt")
+               "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 128;\n\t" BN_MMA_TS("pt") "}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory");
+}
+template <int DT, int NK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_logistic_tcq(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
+               const __grid_constant__ CUtensorMap tmBm, const float* __restrict__ aux, float* G, double* Ld, int nrows, int Dp,
+               long long N, int nblk_total, int nsplit, int flush_every) {
+  using P = SmemPlan<DT>;
+  constexpr int dk = NK * 16;
+  constexpr int NS = P::NS;
+  constexpr int KC = P::KC;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sB = smem + P::OFF_B;
+  unsigned char* sX = smem + P::OFF_X;
+  float* sQ = reinterpret_cast<float*>(sB + 2 * P::B_BYTES);   // per-row constants (w0, w1, a0, a1), NS x 1024 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
+  uint64_t* bar_b = bars;
+  uint64_t* x_full = bars + 1;          // [NS]
+  uint64_t* x_empty = x_full + NS;      // [NS]
+  uint64_t* s_full = x_empty + NS;      // [2] GEMM1 done
+  uint64_t* s_empty = s_full + 2;       // [2] S is in the registers of the group's warps
+  uint64_t* r_full = s_empty + 2;       // [2] residual written
+  uint64_t* r_empty = r_full + 2;       // [2] GEMM2 done with the residual
+  uint64_t* g_full = r_empty + 2;
+  uint64_t* g_empty = g_full + 1;
+  static_assert(1 + 2 * NS + 8 + 2 <= P::NBAR, "barrier slots");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int b0 = (int)(((long long)nblk_total * split) / nsplit);
+  const int b1 = (int)(((long long)nblk_total * (split + 1)) / nsplit);
+  const int nb = b1 - b0;
+  const int fe = flush_every > 0 ? flush_every : 0x7fffffff;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) asm volatile("trap;");
+    mbar_init(bar_b, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); mbar_init(&r_full[i], 256); mbar_init(&r_empty[i], 1); }
+    mbar_init(g_full, 1);
+    mbar_init(g_empty, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_G = tmem;
+  const uint32_t tmem_S = tmem + 128u;     // 2 x 128 columns
+  const uint32_t tmem_R = tmem + 384u;     // 2 x 64 columns
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0 && nb > 0) {
+      mbar_expect_tx(bar_b, 2 * P::B_BYTES);
+      for (int kc = 0; kc < KC; ++kc) {
+        tma_load_2d(&tmBh, sB + 0 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+        tma_load_2d(&tmBm, sB + 1 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+      }
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS;
+        const uint32_t ph = (uint32_t)(i / NS) & 1u;
+        mbar_wait(&x_empty[st], ph ^ 1u);
+        mbar_expect_tx(&x_full[st], P::X_BYTES + 2 * ROWS * 4);
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK_BYTES, &x_full[st], kc * 64, (b0 + i) * ROWS);
+        bulk_load_1d(sQ + st * 2 * ROWS, aux + (size_t)(b0 + i) * 2 * ROWS, 2 * ROWS * 4, &x_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== GEMM1 issuer: S_g = (β − β0 | 1) · X̃_iᵀ, two bf16 terms
+    if (nb > 0) {
+      constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t aX = smem_u32(sX);
+      const uint64_t dKM = desc_kmajor(0, 0);
+      const uint32_t km_hi = (uint32_t)(dKM >> 32), km_lo0 = (uint32_t)dKM;
+      uint32_t bB[2];
+#pragma unroll
+      for (int term = 0; term < 2; ++term) bB[term] = km_lo0 + ((smem_u32(sB) + (uint32_t)term * P::B_BYTES) >> 4);
+      mbar_wait(bar_b, 0);
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS, g = i & 1, u = i >> 1;
+        mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
+        if (u >= 1) mbar_wait(&s_empty[g], (uint32_t)(u - 1) & 1u);
+        tc_fence_after();
+        const uint32_t xlo = km_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
+        const uint32_t d = tmem_S + (uint32_t)g * 128u;
+#pragma unroll
+        for (int term = 0; term < 2; ++term) {
+#pragma unroll
+          for (int c = 0; c < (NK + 3) / 4; ++c) {
+            constexpr int LAST = NK - ((NK + 3) / 4 - 1) * 4;
+            const uint32_t off = (uint32_t)(c * (CHUNK_BYTES >> 4));
+            const uint32_t acc = (term | c) ? 1u : 0u;
+            if (c + 1 < (NK + 3) / 4) mma_ss_run<4>(d, bB[term] + off, km_hi, xlo + off, km_hi, IDESC1, acc);
+            else mma_ss_run<LAST>(d, bB[term] + off, km_hi, xlo + off, km_hi, IDESC1, acc);
+          }
+        }
+        if (elect_one()) tc_commit(&s_full[g]);
+        __syncwarp();
+      }
+    }
+  } else if (warp == G2_WARP) {
+    // ===================================================== GEMM2 issuer: G += R_g (TMEM, compact) · X̃_i (smem, MN-major)
+    if (nb > 0) {
+      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
+      const uint32_t aX = smem_u32(sX);
+      const uint64_t dMN = desc_mnmajor(0, 0);
+      const uint32_t mn_hi = (uint32_t)(dMN >> 32), mn_lo0 = (uint32_t)dMN;
+      int period = 0, in_period = 0;
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS, g = i & 1, u = i >> 1;
+        mbar_wait(&r_full[g], (uint32_t)u & 1u);
+        if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
+        tc_fence_after();
+        const uint32_t xm = mn_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
+        const uint32_t a = tmem_R + (uint32_t)g * 64u;
+        const uint32_t acc0 = in_period > 0 ? 1u : 0u;
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb)   // 64-row halves of the block
+          mma_ts_run4c(tmem_G, a + (uint32_t)(hb * 32), xm + (uint32_t)(hb * 4 * 128), mn_hi, IDESC2, hb ? 1u : acc0);
+        if (elect_one()) { tc_commit(&x_empty[st]); tc_commit(&r_empty[g]); }
+        ++in_period;
+        if (i + 1 == nb || in_period == fe) {
+          if (elect_one()) tc_commit(g_full);
+          ++period;
+          in_period = 0;
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================== elementwise + epilogue: two groups of eight warps, group = block parity
+    const int ew = warp - 2;
+    const int grp = ew >> 3;
+    const int h = (ew >> 2) & 1;             // column half of the group's blocks: chunks 2h, 2h + 1
+    const int q = warp & 3;                  // TMEM lane group (hardware rule)
+    const int row = tile * CHAINS + q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool live = (tile * CHAINS + q * 32) < nrows;
+    double lsum = 0.0;
+    const float2 L2E2 = make_float2(1.4426950408889634f, 1.4426950408889634f);
+    const float2 ONE2 = make_float2(1.0f, 1.0f), MHALF2 = make_float2(-0.5f, -0.5f), MONE2 = make_float2(-1.0f, -1.0f);
+    const float LN2 = 0.6931471805599453f;
+    float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
+    int fpos = grp, fper = 0;
+    while (fpos >= fe) { fpos -= fe; ++fper; }
+    const uint32_t tS = tmem_S + (uint32_t)grp * 128u + lane_sel;
+    const uint32_t tR = tmem_R + (uint32_t)grp * 64u + lane_sel;
+    uint32_t v[32];
+    // S chunk of (block i, chunk cc) -> registers; cc == 0 first waits for (blocking) or tests (non-blocking) GEMM1 of the block
+    auto load_item = [&](int i, int cc, bool blocking) -> bool {
+      if (cc == 0) {
+        const uint32_t par = (uint32_t)(i >> 1) & 1u;
+        if (!blocking) {
+          if (!mbar_test(&s_full[grp], par)) return false;
+        } else {
+          mbar_wait(&s_full[grp], par);
+        }
+        tc_fence_after();
+      }
+      tmem_ld32(tS + (uint32_t)(2 * h + cc) * 32u, v);
+      return true;
+    };
+    bool have_next = false;
+    if (grp < nb && live) have_next = load_item(grp, 0, true);
+    for (int i = grp; i < nb; i += 2) {
+      const int u = i >> 1, st = i % NS;
+      float bsum = 0.f, asum = 0.f;
+      if (!live) {
+        // no staged chains in this lane group: keep the barrier protocol going, no elementwise work
+        // (the r_empty wait keeps this thread's arrivals one phase apart: GEMM1(i + 2) no longer depends on r_full(i), so
+        // without it idle warps could arrive twice on r_full before a working warp has arrived once)
+        mbar_wait(&s_full[grp], (uint32_t)u & 1u);
+        mbar_arrive(&s_empty[grp]);
+        if (u >= 1) mbar_wait(&r_empty[grp], (uint32_t)(u - 1) & 1u);
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ch = 2 * h + cc;
+          if (!have_next) have_next = load_item(i, cc, true);
+          tmem_ld_wait();
+          if (cc == 1) { tc_fence_before(); mbar_arrive(&s_empty[grp]); }   // S of this block is in registers: GEMM1(i + 2) may overwrite it
+          if (cc == 0) mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);     // the constants of this block are visible (long complete)
+          const float4* q4p = reinterpret_cast<const float4*>(sQ + st * 2 * ROWS + ch * 64);
+          uint32_t hi[16];
+          float2 prod = ONE2;
+          float as0 = 0.f, as1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float e0 = __uint_as_float(v[2 * j]), e1 = __uint_as_float(v[2 * j + 1]);
+            const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
+            const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
+            prod = __fmul2_rn(prod, d2);
+            as0 += fabsf(e0); as1 += fabsf(e1);
+            const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
+            const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
+                                          __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
+            const float4 k4 = q4p[j];
+            const float2 lin = __ffma2_rn(make_float2(k4.x, k4.y), make_float2(e0, e1), make_float2(k4.z, k4.w));   // c + w (η̃ − η̃0)
+            const float2 rho = __ffma2_rn(cs, MONE2, lin);                                                           // ρ = δ + w Δη̃
+            hi[j] = pack_bf16(rho.x, rho.y);
+          }
+          bsum += lg2_approx(prod.x * prod.y);
+          asum += as0 + as1;
+          // next S chunk -> registers (v is dead now): within the block always, the group's next block only if it is ready
+          have_next = false;
+          if (cc == 0) have_next = load_item(i, 1, true);
+          else if (i + 2 < nb) have_next = load_item(i + 2, 0, false);
+          if (cc == 0 && u >= 1) { mbar_wait(&r_empty[grp], (uint32_t)(u - 1) & 1u); tc_fence_after(); }   // GEMM2(i − 2) has read R
+          tmem_st16(tR + (uint32_t)ch * 16u, hi);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&r_full[grp]);
+      lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);
+      const bool closes = (i + 1 == nb) || (fpos == fe - 1);
+      const int period = fper;
+      fpos += 2;
+      while (fpos >= fe) { fpos -= fe; ++fper; }
+      if (closes) {
+        mbar_wait(g_full, (uint32_t)period & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ch = 2 * h + cc;
+          if (ch * 32 < dk && live) {
+            uint32_t w[32];
+            tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, w);
+            tmem_ld_wait();
+            if (row < nrows) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const int d = ch * 32 + j;
+                if (d < dk && d < Dp) {
+                  float4 a = make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]), __uint_as_float(w[j + 2]),
+                                         __uint_as_float(w[j + 3]));
+                  float4* gp = reinterpret_cast<float4*>(gout + d);
+                  if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+                  *gp = a;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(g_empty);
+      }
+    }
+    // rows >= N of the last block are zero padding: eta = 0 -> each contributed -log 2
+    if (h == 0 && nb > 0 && grp == ((nb - 1) & 1) && b1 == nblk_total)
+      lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
+    double* lp = reinterpret_cast<double*>(sX);   // X stages are dead by now
+    const int part = grp * 2 + h;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (part > 0) lp[(part - 1) * 128 + q * 32 + lane] = lsum;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (part == 0 && row < nrows) {
+      if (nb == 0) for (int d = 0; d < Dp; ++d) gout[d] = 0.f;
+      const int k = q * 32 + lane;
+      Ld[(size_t)split * nrows + row] = ((lsum + lp[k]) + lp[128 + k]) + lp[256 + k];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+template <int DT, int NK> void launch_q(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
+  using P = SmemPlan<DT>;
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
+    tc.last = cudaFuncSetAttribute(k_logistic_tcq<DT, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    attr_done |= 1ull << (dev & 63);
+  }
+  const int tiles = (nrows + CHAINS - 1) / CHAINS;
+  dim3 grid(tiles, nsplit);
+  CUtensorMap m[3];
+  for (int i = 0; i < 3; ++i) std::memcpy(&m[i], tc.tmaps[i], sizeof(CUtensorMap));
+  k_logistic_tcq<DT, NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], tc.aux, tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
+                                                            (int)(tc.Npad / ROWS), nsplit, tc.flush_every);
+}
+
+template <int DT, int NK, int RR> void launch_rr(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
   using P = SmemPlan<DT>;
   // the attribute is per device: one bit per device ordinal (engines on several GPUs may live in one process)
   static unsigned long long attr_done = 0;
@@ -475,12 +814,83 @@ template <int DT, int NK, bool RR> void launch_rr(LogisticTC& tc, cudaStream_t s
   dim3 grid(tiles, nsplit);
   CUtensorMap m[4];
   for (int i = 0; i < 4; ++i) std::memcpy(&m[i], tc.tmaps[i], sizeof(CUtensorMap));
-  k_logistic_tc<DT, NK, RR><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.c0, tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
-                                                               (int)(tc.Npad / ROWS), nsplit, tc.flush_every, tc.nterms);
+  k_logistic_tc<DT, NK, RR><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.c0, tc.aux, tc.G, tc.Ld, nrows, tc.Dp,
+                                                               (long long)tc.N, (int)(tc.Npad / ROWS), nsplit, tc.flush_every, tc.nterms);
+}
+// linear part of the quadratic-remainder mode: G[split 0][row][:] += g0 − H0 (q_row − β0).  A block of 8 warps takes
+// LR_ROWS staged rows: H0 (D x Dp floats, <= 64 KB) is copied to shared memory with all loads of a thread in flight at once
+// (it has usually been evicted from L2 by the X̃ stream of the tensor kernel: one HBM round trip, not one per row of
+// H0 — a first version that read H0 through L1 inside the k loop, behind warp shuffles, took 45 us), then a warp does
+// one row at a time: lane l owns coordinates 4l..4l+3, row k of the symmetric H0 is one conflict-free 16-byte
+// shared-memory load per lane and (q − β0)_k a broadcast load.
+constexpr int LR_ROWS = 32;
+__global__ void __launch_bounds__(256) k_lin_ref(float* __restrict__ G, const float* __restrict__ q, const float* __restrict__ beta_ref,
+                                                 const float* __restrict__ H0, const double* __restrict__ g0, int nrows, int D, int Dp) {
+  extern __shared__ __align__(16) float lr_smem[];
+  float* sH = lr_smem;                   // [D][Dp]
+  float* sD = lr_smem + (size_t)D * Dp;  // [8 warps][128]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int n4 = D * Dp / 4;
+    const float4* src = reinterpret_cast<const float4*>(H0);
+    float4 t[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { const int idx = threadIdx.x + u * 256; if (idx < n4) t[u] = __ldg(src + idx); }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { const int idx = threadIdx.x + u * 256; if (idx < n4) reinterpret_cast<float4*>(sH)[idx] = t[u]; }
+  }
+  __syncthreads();
+  const int d0 = 4 * lane;
+  const bool own = d0 < Dp;
+  float* db = sD + warp * 128;
+  for (int r = warp; r < LR_ROWS; r += 8) {
+    const int row = blockIdx.x * LR_ROWS + r;
+    if (row >= nrows) break;
+    float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (own) {
+      const float4 qv = *reinterpret_cast<const float4*>(q + (size_t)row * Dp + d0);
+      const float4 bv = *reinterpret_cast<const float4*>(beta_ref + d0);
+      dv = make_float4(qv.x - bv.x, qv.y - bv.y, qv.z - bv.z, qv.w - bv.w);
+    }
+    __syncwarp();
+    *reinterpret_cast<float4*>(db + d0) = dv;
+    __syncwarp();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (own) {
+#pragma unroll 4
+      for (int k = 0; k < D; ++k) {
+        const float dk = db[k];
+        const float4 h = *reinterpret_cast<const float4*>(sH + (size_t)k * Dp + d0);
+        acc[0] = fmaf(h.x, dk, acc[0]); acc[1] = fmaf(h.y, dk, acc[1]); acc[2] = fmaf(h.z, dk, acc[2]); acc[3] = fmaf(h.w, dk, acc[3]);
+      }
+    }
+    if (d0 < D) {
+      float4* gp = reinterpret_cast<float4*>(G + (size_t)row * Dp + d0);
+      float4 g = *gp;
+      g.x += (float)(g0[d0] - (double)acc[0]); g.y += (float)(g0[d0 + 1] - (double)acc[1]);
+      g.z += (float)(g0[d0 + 2] - (double)acc[2]); g.w += (float)(g0[d0 + 3] - (double)acc[3]);
+      *gp = g;
+    }
+  }
+}
+void launch_lin_ref(LogisticTC& tc, cudaStream_t s, int nrows) {
+  const size_t smem = ((size_t)tc.D * tc.Dp + 8 * 128) * sizeof(float);
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
+    tc.last = cudaFuncSetAttribute(k_lin_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    attr_done |= 1ull << (dev & 63);
+  }
+  k_lin_ref<<<(nrows + LR_ROWS - 1) / LR_ROWS, 256, smem, s>>>(tc.G, tc.q, tc.beta_ref, tc.H0, tc.grad0, nrows, tc.D, tc.Dp);
 }
 template <int DT, int NK> void launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
-  if (tc.rterms == 1) launch_rr<DT, NK, true>(tc, s, nrows, nsplit);
-  else launch_rr<DT, NK, false>(tc, s, nrows, nsplit);
+  if (tc.rmode == 2) {
+    if (tc.qpipe) launch_q<DT, NK>(tc, s, nrows, nsplit);
+    else launch_rr<DT, NK, 2>(tc, s, nrows, nsplit);
+    launch_lin_ref(tc, s, nrows);
+  } else if (tc.rmode == 1) launch_rr<DT, NK, 1>(tc, s, nrows, nsplit);
+  else launch_rr<DT, NK, 0>(tc, s, nrows, nsplit);
 }
 
 
@@ -1141,7 +1551,7 @@ template <int NK, bool RR> void launch256_rr(LogisticTC& tc, cudaStream_t s, int
                                                             (long long)tc.N, (int)(tc.Npad / ROWS2), nsplit, tc.flush_every);
 }
 template <int NK> void launch256(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
-  if (tc.rterms == 1) launch256_rr<NK, true>(tc, s, nrows, nsplit);
+  if (tc.rmode == 1) launch256_rr<NK, true>(tc, s, nrows, nsplit);
   else launch256_rr<NK, false>(tc, s, nrows, nsplit);
 }
 
@@ -1217,8 +1627,13 @@ void LogisticTC::destroy() {
   if (c0) cudaFree(c0);
   if (grad0) cudaFree(grad0);
   if (grad0_part) cudaFree(grad0_part);
+  if (aux) cudaFree(aux);
+  if (cw) cudaFree(cw);
+  if (H0) cudaFree(H0);
+  if (H0_part) cudaFree(H0_part);
   Xb = nullptr; colsum = nullptr; beta_ref = nullptr; eta0 = nullptr; c0 = nullptr; grad0 = nullptr; grad0_part = nullptr;
-  ready = false; nterms = 3; rterms = 2; variant = 128;
+  aux = nullptr; cw = nullptr; H0 = nullptr; H0_part = nullptr;
+  ready = false; nterms = 3; rmode = 0; variant = 128;
 }
 
 namespace {
@@ -1288,6 +1703,17 @@ __global__ void k_grad0_partial(const uint16_t* __restrict__ Xb, const float* __
     part[(size_t)blockIdx.x * Dp + d] = acc;
   }
 }
+// the same with c read from the interleaved records of the quadratic-remainder mode
+__global__ void k_grad0_partial_aux(const uint16_t* __restrict__ Xb, const float* __restrict__ cw, double* part, long long N, int D,
+                                    int Dt, int Dp) {
+  const long long r0 = N * blockIdx.x / gridDim.x, r1 = N * (blockIdx.x + 1) / gridDim.x;
+  for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
+    double acc = 0.0;
+    if (d < D)
+      for (long long i = r0; i < r1; ++i) acc = fma((double)bf16_val(Xb[i * Dt + d]), 0.5 - (double)cw[2 * i], acc);
+    part[(size_t)blockIdx.x * Dp + d] = acc;
+  }
+}
 __global__ void k_grad0_sum(const double* __restrict__ part, double* grad0, int nb, int Dp) {
   for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
     double acc = 0.0;
@@ -1296,6 +1722,93 @@ __global__ void k_grad0_sum(const double* __restrict__ part, double* grad0, int 
   }
 }
 }  // namespace
+namespace {
+constexpr int H0_BLOCKS = 148, H0_THREADS = 512, H0_ACC = 32;   // D x D <= 128 x 128 = 512 x 32 accumulators per block
+// one thread per data row: the constants of the quadratic-remainder mode.  aux [Npad / 2] records (w0, w1, a0, a1) of
+// row pairs (what the kernel loads), cw [Npad][2] = (c, w) (what g0 and H0 are formed from); η̃0 is the fp32 value whose
+// three bf16 terms sit in the spare K columns (k_write_reference); a = c − w η̃0 rounded once.
+__global__ void k_write_aux(const uint16_t* __restrict__ Xb, const float* __restrict__ beta_ref, float* aux, float* cw, long long N,
+                            long long Npad, int D, int Dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  float c = 0.f, w = 0.f, a = 0.f;
+  if (i < N) {
+    const uint16_t* xr = Xb + i * Dt;
+    double acc = 0.0;
+    for (int d = 0; d < D; ++d) acc = fma((double)bf16_val(xr[d]), (double)beta_ref[d], acc);
+    const float e = (float)acc;                       // what the MMA adds through the spare columns
+    const double t = tanh(0.5 * (double)e);
+    w = (float)(0.25 * (1.0 - t * t));                // σ'(η̃0)
+    a = (float)(0.5 * t - (double)w * (double)e);     // c − w η̃0 with c = ½ − σ(−η̃0)
+    c = (float)((double)a + (double)w * (double)e);   // the c the kernel's arithmetic implies: fma(w, η̃0, a)
+  }
+  float* rec = aux + (i >> 1) * 4 + (i & 1);
+  rec[0] = w; rec[2] = a;
+  cw[2 * i] = c; cw[2 * i + 1] = w;
+}
+// H0 = X̃ᵀ diag(w) X̃ in Float64 from the stored fp32 w: each block sums a contiguous range of rows into D x D
+// register accumulators (pair p = a D + b -> thread p % 512, slot p / 512), then one pass adds the blocks in order
+__global__ void __launch_bounds__(H0_THREADS) k_hess0_partial(const uint16_t* __restrict__ Xb, const float* __restrict__ cw,
+                                                              double* part, long long N, int D, int Dt) {
+  __shared__ float xs[8][128];
+  __shared__ float ws[8];
+  const long long r0 = N * blockIdx.x / gridDim.x, r1 = N * (blockIdx.x + 1) / gridDim.x;
+  double acc[H0_ACC];
+  int pa[H0_ACC], pb[H0_ACC];
+#pragma unroll
+  for (int m = 0; m < H0_ACC; ++m) {
+    acc[m] = 0.0;
+    const int p = threadIdx.x + m * H0_THREADS;
+    pa[m] = p < D * D ? p / D : -1;
+    pb[m] = p < D * D ? p % D : 0;
+  }
+  for (long long it = r0; it < r1; it += 8) {
+    const int nr = (int)((r1 - it < 8) ? (r1 - it) : 8);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nr * 128; idx += H0_THREADS) {
+      const int r = idx >> 7, d = idx & 127;
+      xs[r][d] = d < D ? bf16_val(Xb[(it + r) * Dt + d]) : 0.f;
+    }
+    if (threadIdx.x < nr) ws[threadIdx.x] = cw[2 * (it + threadIdx.x) + 1];
+    __syncthreads();
+    for (int r = 0; r < nr; ++r) {
+      const double w = (double)ws[r];
+#pragma unroll
+      for (int m = 0; m < H0_ACC; ++m)
+        if (pa[m] >= 0) acc[m] = fma((double)(xs[r][pa[m]] * xs[r][pb[m]]), w, acc[m]);   // bf16 x bf16 is exact in fp32
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < H0_ACC; ++m) {
+    const int p = threadIdx.x + m * H0_THREADS;
+    if (p < D * D) part[(size_t)blockIdx.x * D * D + p] = acc[m];
+  }
+}
+__global__ void k_hess0_sum(const double* __restrict__ part, float* H0, int nb, int D, int Dp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= D * D) return;
+  double acc = 0.0;
+  for (int b = 0; b < nb; ++b) acc += part[(size_t)b * D * D + p];
+  H0[(size_t)(p / D) * Dp + (p % D)] = (float)acc;
+}
+}  // namespace
+// quadratic-remainder mode (k_logistic_tc, RR == 2): per-row records, g0 = X̃ᵀ r0 and H0 = X̃ᵀ diag(w) X̃
+int32_t logistic_tc_write_quadratic_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev, std::string& err) {
+  if (!tc.aux && (cudaMalloc(&tc.aux, size_t(tc.Npad) * 2 * 4) != cudaSuccess || cudaMalloc(&tc.cw, size_t(tc.Npad) * 2 * 4) != cudaSuccess)) {
+    err = "device allocation failed (aux)";
+    return BNUTS_ERR_CUDA;
+  }
+  if (!tc.H0 && cudaMalloc(&tc.H0, size_t(tc.Dp) * tc.Dp * 4) != cudaSuccess) { err = "device allocation failed (H0)"; return BNUTS_ERR_CUDA; }
+  if (!tc.H0_part && cudaMalloc(&tc.H0_part, size_t(H0_BLOCKS) * tc.D * tc.D * 8) != cudaSuccess) { err = "device allocation failed (H0 partials)"; return BNUTS_ERR_CUDA; }
+  cudaMemsetAsync(tc.H0, 0, size_t(tc.Dp) * tc.Dp * 4, s);
+  k_write_aux<<<(unsigned)((tc.Npad + 255) / 256), 256, 0, s>>>(tc.Xb, beta_ref_dev, tc.aux, tc.cw, (long long)tc.N, (long long)tc.Npad, tc.D, tc.Dt);
+  // g0 from the c of the records: the same two-pass reduction as the δ mode
+  k_grad0_partial_aux<<<G0_BLOCKS, 128, 0, s>>>(tc.Xb, tc.cw, tc.grad0_part, (long long)tc.N, tc.D, tc.Dt, tc.Dp);
+  k_grad0_sum<<<1, 128, 0, s>>>(tc.grad0_part, tc.grad0, G0_BLOCKS, tc.Dp);
+  k_hess0_partial<<<H0_BLOCKS, H0_THREADS, 0, s>>>(tc.Xb, tc.cw, tc.H0_part, (long long)tc.N, tc.D, tc.Dt);
+  k_hess0_sum<<<(tc.D * tc.D + 255) / 256, 256, 0, s>>>(tc.H0_part, tc.H0, H0_BLOCKS, tc.D, tc.Dp);
+  return 0;
+}
 void logistic_tc_write_residual_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev) {
   k_write_c0<<<(unsigned)((tc.Npad + 255) / 256), 256, 0, s>>>(tc.Xb, beta_ref_dev, tc.c0, (long long)tc.N, (long long)tc.Npad, tc.D,
                                                               tc.Dt);

@@ -112,6 +112,8 @@ struct HostExec {
     err = "tensor path is CUDA-only";
     return BNUTS_ERR_UNSUPPORTED;
   }
+  int reference_mode() const { return 0; }
+  int launches_per_gradient() const { return 1; }
   template <class E> int32_t logistic_tensor_setup_synth(E&, uint64_t, int64_t, int64_t, std::string& err) {
     err = "tensor path is CUDA-only";
     return BNUTS_ERR_UNSUPPORTED;

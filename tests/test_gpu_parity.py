@@ -392,39 +392,108 @@ def test_tensor_single_term_residual_forced(bn, oracle_lib, cuda_lib, monkeypatc
 
 def test_tensor_reference_modes_full_size(bn, cuda_lib, monkeypatch):
     """BASELINE config 3 shape (N = 1e6, D = 100) around the optimum found on the device: gradients in the posterior bulk
-    against numpy Float64.  Two-term residual (what the engine takes at N / D = 1e4): north-star fp32 tolerance, or the
-    fp32 conditioning floor N * eps32 where |grad| -> 0; slot / tile invariance bit for bit.  Single-term residual
-    forced on: within three times its error model (1.7e-5 |grad| here, which is why it is not taken by itself)."""
+    and its tails against numpy Float64 for the three residual modes of the reference-point path.  Two bf16 terms of r
+    (what the engine takes here) and the quadratic remainder (opt-in): north-star fp32 tolerance, or the fp32 conditioning floor N * eps32 where
+    |grad| -> 0; slot / tile invariance bit for bit.  One term of delta forced on: within three times its error model
+    (1.7e-5 |grad| at this N / D, which is why it is not taken by itself here)."""
     N, D, C = 1_000_000, 100, 256
     X, y, beta = make_logistic(N, D)
     rng = np.random.default_rng(4)
-    monkeypatch.delenv("BNUTS_TC_RREF", raising=False)
+    for v in ("BNUTS_TC_RREF", "BNUTS_TC_QREF"):
+        monkeypatch.delenv(v, raising=False)
     tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0)
     tc.set_positions(np.repeat(_f32(beta)[None, :], C, axis=0))
     tc.find_local_optimum(1e-4, 50)
     b = tc.get_state()[0].mean(axis=0)
     q = np.repeat(_f32(b)[None, :], C, axis=0)
-    for k, w in enumerate((0.0002, 0.002, 0.006, 0.02)):     # posterior sd is ~ 2 / sqrt(N) = 0.002 per coordinate
+    widths = (0.0002, 0.002, 0.006, 0.02, 0.06)             # posterior sd is ~ 2 / sqrt(N) = 0.002 per coordinate
+    nw = len(widths)
+    for k, w in enumerate(widths):
         q[1 + k] = _f32(b + rng.normal(size=D) * w)
-    q[5:] = q[1 + (np.arange(C - 5) % 4)]
-    eta = X @ q[1:5].T
-    gref = ((y[:, None] - 1 / (1 + np.exp(-eta))).T @ X) - q[1:5]
+    q[1 + nw:] = q[1 + (np.arange(C - 1 - nw) % nw)]
+    eta = X @ q[1:1 + nw].T
+    gref = ((y[:, None] - 1 / (1 + np.exp(-eta))).T @ X) - q[1:1 + nw]
     nrm = np.linalg.norm(gref, axis=1)
     out = {}
-    for mode in (None, "1"):
-        if mode is None:
-            monkeypatch.delenv("BNUTS_TC_RREF", raising=False)
-        else:
-            monkeypatch.setenv("BNUTS_TC_RREF", mode)
+    for mode, env in (("two", {}), ("quad", {"BNUTS_TC_QREF": "1"}), ("delta", {"BNUTS_TC_RREF": "1"})):
+        for v in ("BNUTS_TC_RREF", "BNUTS_TC_QREF"):
+            monkeypatch.delenv(v, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         tc.logistic_set_reference(b); tc.set_positions(q); _, g, l = tc.get_state()
-        err = np.linalg.norm(g[1:5] - gref, axis=1)
-        tol = TOL32 if mode is None else 3 * RR_MODEL * np.sqrt(D / N)
+        err = np.linalg.norm(g[1:1 + nw] - gref, axis=1)
+        tol = 3 * RR_MODEL * np.sqrt(D / N) if mode == "delta" else TOL32
         assert np.all(err < np.maximum(tol * nrm, 3 * N * 6e-8)), (mode, err, nrm)
-        for k in range(5, C):
-            assert g[k].tobytes() == g[1 + (k - 5) % 4].tobytes() and l[k] == l[1 + (k - 5) % 4]
+        for k in range(1 + nw, C):
+            assert g[k].tobytes() == g[1 + (k - 1 - nw) % nw].tobytes() and l[k] == l[1 + (k - 1 - nw) % nw]
         out[mode] = (g, l, err)
-    assert out[None][0].tobytes() != out["1"][0].tobytes() and out[None][1].tobytes() == out["1"][1].tobytes()
-    print("N=1e6 D=100: |grad|", nrm, "err two bf16 terms", out[None][2], "err one bf16 term", out["1"][2])
+        print("N=1e6 D=100 mode", mode, "|grad|", nrm, "err", err, "rel", err / nrm)
+    assert out["two"][0].tobytes() != out["quad"][0].tobytes() != out["delta"][0].tobytes()
+    assert out["two"][1].tobytes() == out["quad"][1].tobytes() == out["delta"][1].tobytes()      # the log density is untouched
+    assert np.all(out["quad"][2][1:] < out["two"][2][1:])     # the quadratic remainder is the more accurate one in the bulk
+
+
+QR_MODEL = 7.6e-4   # gradient error of the quadratic-remainder mode: QR_MODEL * k * (D / N) * |grad| at k posterior sd
+
+
+@pytest.mark.parametrize("N,D,C,pipe", [(20000, 100, 256, "0"), (5000, 61, 40, "1"), (9000, 125, 150, "0"), (3000, 17, 5, "1"),
+                                        (300000, 100, 64, "0"), (300000, 100, 160, "1")])
+def test_tensor_quadratic_remainder_mode(bn, oracle_lib, cuda_lib, monkeypatch, N, D, C, pipe):
+    """Quadratic-remainder mode of the reference-point path (opt-in, BNUTS_TC_QREF=1; k_logistic_tc with RR = 2 or, with
+    BNUTS_TC_QPIPE=1, the decoupled-buffer kernel k_logistic_tcq, + k_lin_ref): the residual operand is
+    rho = r - r0 + w (eta - eta0), one bf16 term, and g0 - H0 (beta - beta0) is added per chain.  Error model
+    7.6e-4 k (D / N) |grad| at k posterior sd from the reference: north-star tolerance out to 10 sd when N >= 2500 D (last
+    two cases), three times the model at the small sizes.  Far tails (10..60 sd): bounded loss.  Leaving the mode restores
+    the exact path."""
+    force = N < 2500 * D
+    monkeypatch.setenv("BNUTS_TC_QPIPE", pipe)
+    for v in ("BNUTS_TC_RREF", "BNUTS_TC_QREF"):
+        monkeypatch.delenv(v, raising=False)
+    X, y, beta = make_logistic(N, D)
+    rng = np.random.default_rng(11)
+    b, sd = _newton_mode(X, y, beta)
+    scale = np.concatenate([np.linspace(0.02, 10.0, C - C // 4), np.linspace(10.0, 60.0, C // 4)])
+    q = _f32(b[None, :] + rng.normal(size=(C, D)) * sd[None, :] * scale[:, None])
+    ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0, row_blocks=1)
+    ref.set_positions(q); _, g0, l0 = ref.get_state()
+    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0)
+    tc.set_positions(q); _, g3, l3 = tc.get_state()                                   # exact three-term path
+    monkeypatch.setenv("BNUTS_TC_QREF", "0")
+    tc.logistic_set_reference(b); tc.set_positions(q); _, g2, l2 = tc.get_state()      # two-term operand, r = rh + rl
+    monkeypatch.setenv("BNUTS_TC_QREF", "1")
+    tc.logistic_set_reference(b); tc.set_positions(q); _, gq, lq = tc.get_state()      # quadratic remainder
+    assert gq.tobytes() != g2.tobytes() and lq.tobytes() == l2.tobytes()
+    nrm = np.linalg.norm(g0, axis=1)
+    floor = 3 * N * 6e-8
+    eq = np.linalg.norm(gq - g0, axis=1); e2 = np.linalg.norm(g2 - g0, axis=1)
+    near = scale <= 10.0
+    tol = np.maximum(TOL32, 3 * QR_MODEL * scale * D / N) if force else np.full(C, TOL32)
+    assert np.all(eq[near] < np.maximum(tol[near] * nrm[near], floor)), np.max(eq[near] / np.maximum(tol[near] * nrm[near], floor))
+    far = scale > 10.0 if np.any(scale > 10.0) else near
+    assert np.all(eq[far] < np.maximum(5e-3 * nrm[far], floor)), np.max(eq[far] / nrm[far])   # far tails: bounded loss
+    print("quadratic remainder N=%d D=%d: max rel err near %.2e (two-term %.2e), far %.2e (two-term %.2e)" % (
+        N, D, np.max(eq[near] / nrm[near]), np.max(e2[near] / nrm[near]), np.max(eq[far] / nrm[far]), np.max(e2[far] / nrm[far])))
+    assert np.max(np.abs(lq - l0) / np.abs(l0)) < TOL32
+    # a chain AT the reference: rho = 0 in every row, the gradient is the stored Float64 constant
+    at = np.repeat(_f32(b)[None, :], C, axis=0)
+    tc.set_positions(at); _, gb, _ = tc.get_state()
+    ref.set_positions(at); _, gb0, _ = ref.get_state()
+    assert np.max(np.linalg.norm(gb - gb0, axis=1)) < floor
+    # per-leapfrog parity (chains within 3 sd), a free run with ragged launches (compacted rows), slot invariance
+    qn = _f32(b[None, :] + rng.normal(size=(C, D)) * sd[None, :] * np.linspace(0.05, 3.0, C)[:, None])
+    ref.set_positions(qn); tc.set_positions(qn)
+    p = _f32(rng.normal(size=(C, D)) * np.sqrt(N) * 0.3)
+    a = ref.leapfrog(p, 1e-3, 3); c = tc.leapfrog(p, 1e-3, 3)
+    assert np.max(_rel(c[0], a[0])) < TOL32
+    tc.set_positions(q[:1].repeat(C, axis=0)); _, gs, ls = tc.get_state()
+    assert all(gs[k].tobytes() == gs[0].tobytes() for k in range(C)) and np.all(ls == ls[0])
+    tc.set_positions(qn); tc.set_stepsize(0.5 / np.sqrt(N)); ch, st = tc.sample(3)
+    assert np.isfinite(ch).all() and (st["steps"] > 0).all()
+    # row sharding cannot be switched on under the mode; leaving it restores the exact path bit for bit
+    with pytest.raises(bn.BnutsError):
+        tc.set_allreduce(lambda buf, count, dtype: None)
+    tc.logistic_set_reference(None); tc.set_positions(q); _, g3b, _ = tc.get_state()
+    assert g3b.tobytes() == g3.tobytes()
 
 
 def test_synthetic_rows_on_device(bn, oracle_lib, cuda_lib):
