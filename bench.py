@@ -280,7 +280,11 @@ def main():
                      "traffic": 306.9e6 if (N == 1_000_000 and D == 100) else None, "traffic_unit": "bytes per launch (ncu, full 4096-row launch)",
                      "kernel": "k_logistic_tc",
                      "launches": int(grad_n), "avg_launch_ms": grad_ms / max(grad_n, 1), "avg_rows_per_launch": rows / max(grad_n, 1), "peak_source": peak_src,
-                     "kernel_share_of_step": grad_ms / ms},
+                     "kernel_share_of_step": grad_ms / ms,
+                     # what the tensor pipe executes for those algorithmic flops: K and N padded to 16 (D + 3 reference
+                     # columns -> dk), the position operand in `terms` bf16 terms and the residual in two
+                     "executed_over_algorithmic": (terms + 2) * (-(-(D + 3) // 16) * 16) / (2.0 * D),
+                     "executed": (ach * (terms + 2) * (-(-(D + 3) // 16) * 16) / (2.0 * D)) if ach else None},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(qh.nbytes), "d2h_bytes_per_step": int(chain.nbytes + stats.nbytes)},
         "clocks": clk,
         "min_ess": {"value": min_ess, "per_s": min_ess / dt, "unit": "min over coordinates of multi-chain bulk ESS (/s: e2e wall clock)",

@@ -75,6 +75,11 @@ check(e, rc) = rc == 0 ? nothing :
 attach!(e, ::IIDNormal) = check(e, ccall((:bnuts_model_iid_normal, libbnuts), Int32, (Ptr{Cvoid},), e))
 attach!(e, ::Funnel) = check(e, ccall((:bnuts_model_funnel, libbnuts), Int32, (Ptr{Cvoid},), e))
 attach!(e, ℓ::GaussianTarget) = check(e, ccall((:bnuts_model_gaussian, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, ℓ.P))
+# synthetic rows [row_offset, row_offset + N) of the benchmark design matrix, generated on the device (include/bnuts.h)
+struct SyntheticLogisticTarget; D::Int; data_seed::UInt64; row_offset::Int64; N::Int64; prior_precision::Float64; end
+dimension(ℓ::SyntheticLogisticTarget) = ℓ.D
+attach!(e, ℓ::SyntheticLogisticTarget) = check(e, ccall((:bnuts_model_logistic_synthetic, libbnuts), Int32,
+    (Ptr{Cvoid}, UInt64, Int64, Int64, Float64, Int32), e, ℓ.data_seed, ℓ.row_offset, ℓ.N, ℓ.prior_precision, 1))
 attach!(e, ℓ::LogisticTarget) = check(e, ccall((:bnuts_model_logistic, libbnuts), Int32,
     (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Float64, Int32), e, ℓ.X, 1, ℓ.y, length(ℓ.y), ℓ.prior_precision, 1))
 

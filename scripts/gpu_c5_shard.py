@@ -23,25 +23,28 @@ e.set_positions(np.repeat(beta[None, :], C, axis=0))
 t0 = time.perf_counter(); e.find_local_optimum(1e-4, int(os.environ.get("OPT_ITERS", 30))); t_opt = time.perf_counter() - t0
 b = e.get_state()[0].mean(axis=0)
 sd = 2.0 / np.sqrt(N)
+q = b[None, :] + rng.normal(size=(C, D)) * sd
+p = rng.normal(size=(C, D)) * np.sqrt(N) * 0.3
+res = {}
 for mode in ("0", "1"):
     os.environ["BNUTS_TC_RREF"] = mode
     e.logistic_set_reference(b)
-    q = b[None, :] + rng.normal(size=(C, D)) * sd
     e.set_positions(q)
-    p = rng.normal(size=(C, D)) * np.sqrt(N) * 0.3
+    res[mode] = e.get_state()[1]
     e.leapfrog(p, 1e-4, 2)
+    walls = []
     e.profile(True)
-    torch.cuda.synchronize(); t = time.perf_counter(); e.leapfrog(p, 1e-4, 8); torch.cuda.synchronize(); dt = time.perf_counter() - t
+    for _ in range(3):
+        torch.cuda.synchronize(); t = time.perf_counter(); e.leapfrog(p, 1e-4, 4); torch.cuda.synchronize()
+        walls.append((time.perf_counter() - t) / 4)
     ms, n = e.profile(False)
     fl = 4.0 * N * D * C
-    g = e.get_state()[1]
     print(json.dumps({"config": "c5 shard: rows [%d, %d) of N=1e8, D=%d, %d chains, 1 GPU" % (ROW0, ROW0 + N, D, C),
                       "residual_terms": 2 if mode == "0" else 1, "generate_s": t_gen, "find_local_optimum_s": t_opt,
                       "grad_kernel_ms": ms / n, "alg_TFLOPs": fl / (ms / n * 1e-3) / 1e12,
                       "frac_of_sustained_bf16_peak_1390": fl / (ms / n * 1e-3) / 1e12 / 1390.3,
-                      "lockstep_step_ms": dt / 8 * 1e3, "chain_leapfrogs_per_s": C * 8 / dt,
-                      "grad_norm_mean": float(np.linalg.norm(g, axis=1).mean())}), flush=True)
-    if mode == "0":
-        g2 = g
-    else:
-        print(json.dumps({"single_vs_two_term_rel_diff_max": float(np.max(np.linalg.norm(g - g2, axis=1) / np.linalg.norm(g2, axis=1)))}))
+                      "lockstep_step_ms_min_of_3_calls": min(walls) * 1e3, "lockstep_step_ms_all": [w * 1e3 for w in walls],
+                      "chain_leapfrogs_per_s": C / min(walls),
+                      "grad_norm_mean": float(np.linalg.norm(res[mode], axis=1).mean())}), flush=True)
+print(json.dumps({"single_vs_two_term_rel_diff_max": float(np.max(np.linalg.norm(res["1"] - res["0"], axis=1) / np.linalg.norm(res["0"], axis=1))),
+                  "note": "same positions (about one posterior sd from the reference); the single-term error model is 1.7e-3 sqrt(D/N_total)"}))
