@@ -379,7 +379,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         if (warp == 2) TC_TRACE(2, i, 4);
         uint32_t hi[16], lo[RR ? 1 : 16];
         float2 prod = ONE2;
-        float as0 = 0.f, as1 = 0.f;
+        float2 as2 = make_float2(0.f, 0.f);   // Σ|η̃| of the even / odd columns: one FADD2 with |.| operand modifiers per pair
         if (RR && cc == 0) mbar_wait(&x_full[i % NS], (uint32_t)(i / NS) & 1u);   // c of this block is visible (long complete)
         const float2* c2p = reinterpret_cast<const float2*>(sR + (i % NS) * ROWS + ch * 32);
         // RR == 2: one 16-byte record per PAIR of rows, (w0, w1, a0, a1) with a = c − w η̃0: one broadcast LDS.128 per pair
@@ -391,7 +391,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
           const float2 d2 = (TCDBG & 16) ? __fadd2_rn(u2, ONE2) : __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
           prod = __fmul2_rn(prod, d2);                       // 32 factors in (1,2]: no overflow
-          as0 += fabsf(e0); as1 += fabsf(e1);
+          as2 = __fadd2_rn(as2, make_float2(fabsf(e0), fabsf(e1)));
           // rc = 1/d = sigma(|eta|) in [1/2,1);  sigma(-eta) = 1/2 - copysign(rc - 1/2, eta)
           const float2 hm = __fadd2_rn((TCDBG & 8) ? d2 : rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
           const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
@@ -414,7 +414,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           }
         }
         bsum += lg2_approx(prod.x * prod.y);
-        asum += as0 + as1;
+        asum += as2.x + as2.y;
         if (warp == 2) TC_TRACE(2, i, 5);
         // next item's S -> registers (v is dead now): always within the block, across blocks only if it is ready
         have_next = false;
@@ -699,14 +699,14 @@ k_logistic_tcq(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const float4* q4p = reinterpret_cast<const float4*>(sQ + st * 2 * ROWS + ch * 64);
           uint32_t hi[16];
           float2 prod = ONE2;
-          float as0 = 0.f, as1 = 0.f;
+          float2 as2 = make_float2(0.f, 0.f);   // Σ|η̃| of the even / odd columns: one FADD2 with |.| operand modifiers per pair
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float e0 = __uint_as_float(v[2 * j]), e1 = __uint_as_float(v[2 * j + 1]);
             const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
             const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
             prod = __fmul2_rn(prod, d2);
-            as0 += fabsf(e0); as1 += fabsf(e1);
+            as2 = __fadd2_rn(as2, make_float2(fabsf(e0), fabsf(e1)));
             const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
             const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
                                           __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
@@ -716,7 +716,7 @@ k_logistic_tcq(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             hi[j] = pack_bf16(rho.x, rho.y);
           }
           bsum += lg2_approx(prod.x * prod.y);
-          asum += as0 + as1;
+          asum += as2.x + as2.y;
           // next S chunk -> registers (v is dead now): within the block always, the group's next block only if it is ready
           have_next = false;
           if (cc == 0) have_next = load_item(i, 1, true);
@@ -1134,14 +1134,14 @@ k_logistic_tc64(const __grid_constant__ CUtensorMap tmX, const uint16_t* __restr
         tmem_ld_wait();
         uint32_t hi[16], lo[16];
         float2 prod = ONE2;
-        float as0 = 0.f, as1 = 0.f;
+        float2 as2 = make_float2(0.f, 0.f);   // Σ|η̃| of the even / odd columns: one FADD2 with |.| operand modifiers per pair
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float e0 = __uint_as_float(v[2 * j]), e1 = __uint_as_float(v[2 * j + 1]);
           const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
           const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
           prod = __fmul2_rn(prod, d2);
-          as0 += fabsf(e0); as1 += fabsf(e1);
+          as2 = __fadd2_rn(as2, make_float2(fabsf(e0), fabsf(e1)));
           const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
           const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
                                         __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
@@ -1153,7 +1153,7 @@ k_logistic_tc64(const __grid_constant__ CUtensorMap tmX, const uint16_t* __restr
           lo[j] = pack_bf16(l2.x, l2.y);
         }
         bsum = lg2_approx(prod.x * prod.y);
-        asum = as0 + as1;
+        asum = as2.x + as2.y;
         have_next = false;
         if (i + 2 < nb) have_next = load_item(i + 2, false);
         tmem_st16(tS, hi);
@@ -1437,7 +1437,7 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tmem_ld_wait();
         uint32_t hi[16], lo[RR ? 1 : 16];
         float2 prod = ONE2;
-        float as0 = 0.f, as1 = 0.f;
+        float2 as2 = make_float2(0.f, 0.f);   // Σ|η̃| of the even / odd columns: one FADD2 with |.| operand modifiers per pair
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 eo = e4[j4];
@@ -1449,7 +1449,7 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
             const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
             prod = __fmul2_rn(prod, d2);
-            as0 += fabsf(e0); as1 += fabsf(e1);
+            as2 = __fadd2_rn(as2, make_float2(fabsf(e0), fabsf(e1)));
             const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
             const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (__float_as_uint(e0) & 0x80000000u)),
                                           __uint_as_float(__float_as_uint(hm.y) | (__float_as_uint(e1) & 0x80000000u)));
@@ -1467,7 +1467,7 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
         bsum = lg2_approx(prod.x * prod.y);
-        asum = as0 + as1;
+        asum = as2.x + as2.y;
         have_next = false;
         if (i + 2 < nb) have_next = load_item(i + 2, false);
         tmem_st16(tS, hi);
