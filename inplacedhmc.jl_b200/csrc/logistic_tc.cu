@@ -36,6 +36,10 @@
 // ping-pong over the row blocks, a warp owns two 32-row chunks of its group's blocks.
 // A second kernel in this file, k_logistic_tc64, keeps the position operand in TMEM and works on 64-row
 // blocks (BNUTS_TC_VARIANT=64): same results, measured slower, kept as a documented variant.
+// Further kernels here: k_logistic_tc256 (128 < D <= 256, config 5's shape), k_logistic_tcq + k_lin_ref (quadratic-
+// remainder residual on decoupled S / R buffers: validated, opt-in, no faster — DESIGN.md section 6 has the
+// measurements), the set-up kernels of the reference-point modes (k_write_reference / _eta0 / _c0 / _aux, g0 and H0
+// reductions in a fixed order).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>

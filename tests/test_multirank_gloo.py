@@ -103,3 +103,44 @@ def test_row_sharded_replicas_agree_and_match_one_engine(tmp_path, bn):
     assert same[:, :3].all() and same.mean() > 0.8, same.mean()
     ok = same.all(axis=1)
     np.testing.assert_allclose(r0["ch"][ok], ch[ok], rtol=1e-8, atol=1e-8)
+
+
+# ---------------------------------------------------------------- config c5's data flow: every rank GENERATES its shard
+def _synth_row_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import inplacedhmc_jl_b200 as bn
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, D, C, seed = 600, 10, 5, 5
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    e = bn.Engine(C, D, max_depth=6, lib=HOSTEMU_SO, seed=9)
+    e.model_logistic_synthetic(seed, lo, hi - lo, 1.0, row_blocks=2)   # rows [lo, hi) of the one conceptual matrix
+    e.set_allreduce(_gloo_allreduce)
+    _, _, beta = bn.synth_logistic_rows(seed, 0, 0, D, lib=bn.load_library(HOSTEMU_SO))
+    rng = np.random.default_rng(6)
+    e.set_positions(beta[None, :] + rng.normal(size=(C, D)) * 0.3)
+    q, g, l = e.get_state()
+    e.set_stepsize(0.05)
+    ch, st = e.sample(10)
+    np.savez(os.path.join(out, f"synth{rank}.npz"), g=g, l=l, ch=ch, st=st)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_synthetic_rows(tmp_path, bn):
+    """Rows generated where they are used (bnuts_model_logistic_synthetic with a row offset per rank) add up to the
+    model of a single engine that generates all rows: the sharding does not change the matrix."""
+    build_hostemu()
+    world = 2
+    mp.spawn(_synth_row_worker, args=(world, 29523, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "synth0.npz"), np.load(tmp_path / "synth1.npz")
+    for k in ("g", "l", "ch", "st"):
+        assert r0[k].tobytes() == r1[k].tobytes(), k
+    N, D, C, seed = 600, 10, 5, 5
+    e = bn.Engine(C, D, max_depth=6, lib=HOSTEMU_SO, seed=9)
+    e.model_logistic_synthetic(seed, 0, N, 1.0, row_blocks=2)
+    _, _, beta = bn.synth_logistic_rows(seed, 0, 0, D, lib=bn.load_library(HOSTEMU_SO))
+    rng = np.random.default_rng(6)
+    e.set_positions(beta[None, :] + rng.normal(size=(C, D)) * 0.3)
+    q, g, l = e.get_state()
+    np.testing.assert_allclose(r0["g"], g, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(r0["l"], l, rtol=1e-13)
