@@ -487,16 +487,20 @@ __global__ void k_synth_rows(uint64_t seed, long long row0, long long N, int D, 
   // Dt is a multiple of 64: the four columns of a quad never straddle the row end and the store is 8-byte aligned
   *reinterpret_cast<uint2*>(Xb + i * Dt + 4 * q) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
 }
-void synth_fill_xb(cudaStream_t s, uint64_t seed, int64_t row0, int64_t N, int32_t D, int32_t Dt, uint16_t* Xb) {
+int synth_fill_xb(cudaStream_t s, uint64_t seed, int64_t row0, int64_t N, int32_t D, int32_t Dt, uint16_t* Xb) {
   double* beta = nullptr;
   uint8_t* y = nullptr;
-  if (cudaMalloc(&beta, (size_t)D * 8) != cudaSuccess || cudaMalloc(&y, (size_t)N) != cudaSuccess) { cudaFree(beta); return; }
+  if (cudaMalloc(&beta, (size_t)D * 8) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
+  if (cudaMalloc(&y, (size_t)N) != cudaSuccess) { cudaFree(beta); return (int)cudaErrorMemoryAllocation; }
   k_synth_beta<<<(D + 127) / 128, 128, 0, s>>>(seed, D, beta);
   k_synth_labels<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(seed, (long long)row0, (long long)N, D, beta, y);
   const long long nt = (long long)N * ((D + 3) >> 2);
   k_synth_rows<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(seed, (long long)row0, (long long)N, D, Dt, y, Xb);
-  cudaStreamSynchronize(s);
+  cudaError_t e = cudaGetLastError();
+  const cudaError_t e2 = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = e2;
   cudaFree(beta); cudaFree(y);
+  return (int)e;
 }
 
 // ------------------------------------------------------------------ execution policy

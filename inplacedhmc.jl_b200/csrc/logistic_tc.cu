@@ -1927,7 +1927,8 @@ int32_t logistic_tc_build_synth(LogisticTC& tc, uint64_t seed, int64_t row0, int
   tc_shape(tc, N, C, D, Dp);
   const int32_t rc = tc_alloc(tc, err);
   if (rc) return rc;
-  fill(s, seed, row0, N, D, tc.Dt, tc.Xb);
+  const int frc = fill(s, seed, row0, N, D, tc.Dt, tc.Xb);
+  if (frc != 0) { err = std::string("synthetic data generation failed: ") + cudaGetErrorString((cudaError_t)frc); return BNUTS_ERR_CUDA; }
   // column sums of X~ in Float64, fixed order (same two-pass reduction as grad0, weight 1)
   k_grad0_partial<<<G0_BLOCKS, 128, 0, s>>>(tc.Xb, nullptr, tc.grad0_part, (long long)tc.N, tc.D, tc.Dt, tc.Dp);
   k_grad0_sum<<<1, 128, 0, s>>>(tc.grad0_part, tc.colsum, G0_BLOCKS, tc.Dp);

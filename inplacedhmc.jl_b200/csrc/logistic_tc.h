@@ -61,7 +61,7 @@ int32_t logistic_tc_build(LogisticTC& tc, const uint16_t* Xbf16_host /*[N][D]*/,
 
 // the same with the rows generated on the device (bnuts_model_logistic_synthetic); `fill` writes the sign-folded
 // bf16 rows [row0, row0 + N) of the synthetic matrix into Xb [Npad][Dt]
-typedef void (*SynthFillFn)(cudaStream_t s, uint64_t seed, int64_t row0, int64_t N, int32_t D, int32_t Dt, uint16_t* Xb);
+typedef int (*SynthFillFn)(cudaStream_t s, uint64_t seed, int64_t row0, int64_t N, int32_t D, int32_t Dt, uint16_t* Xb);   // 0 or a cudaError_t
 int32_t logistic_tc_build_synth(LogisticTC& tc, uint64_t seed, int64_t row0, int64_t N, int32_t C, int32_t D, int32_t Dp,
                                 cudaStream_t s, SynthFillFn fill, std::string& err);
 
