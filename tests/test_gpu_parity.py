@@ -534,3 +534,24 @@ def test_synthetic_rows_on_device(bn, oracle_lib, cuda_lib):
     qw = _f32(bw[None, :] + rng.normal(size=(8, 256)) * 0.05)
     w.set_positions(qw); wh.set_positions(qw)
     assert w.get_state()[1].tobytes() == wh.get_state()[1].tobytes()
+
+
+@pytest.mark.parametrize("C,D,max_depth,eps,kind", [
+    (1, 1, 3, 0.4, "iid"), (2, 1, 1, 0.9, "funnel"), (3, 32, 2, 0.2, "gauss"), (3, 33, 4, 0.2, "gauss"),
+    (2, 128, 3, 0.05, "logit"), (2, 129, 3, 0.05, "logit"), (4, 5, 20, 1e-3, "iid"), (4, 7, 6, 50.0, "funnel"),
+    (5, 6, 5, 1e-7, "iid")])
+def test_cuda_edge_shapes_and_regimes_bitwise(bn, oracle_lib, cuda_lib, C, D, max_depth, eps, kind):
+    """The edge cases of tests/test_machine_vs_oracle.py (one chain / one coordinate, max_depth 1 and 20, lane-row
+    boundaries, every-leaf-diverges and never-turns regimes) on the CUDA engine, deterministic gradient path, fp64:
+    draws, statistics, selected indices and final state bit for bit against the oracle."""
+    outs = []
+    n = 6 if max_depth >= 20 else 25
+    for lib, kw in ((oracle_lib, {}), (cuda_lib, {"gradient_path": DET})):
+        e = bn.Engine(C, D, dtype=F64, max_depth=max_depth, lib=lib, seed=13, **kw)
+        set_model(e, kind, D, N=120)
+        e.set_positions(None)
+        e.set_stepsize(eps)
+        ch, st, sel = e.sample(n, want_index=True)
+        one = e.sample(1)
+        outs.append([ch, st, sel, one[0], one[1], e.get_state()[0], e.get_state()[1]])
+    assert_bitwise(outs[0], outs[1])

@@ -73,3 +73,41 @@ def test_chain_offset_makes_sharding_invisible(bn, hostemu_lib):
     a, b = run(3, 0), run(3, 3)
     assert np.concatenate([a[0], b[0]]).tobytes() == full[0].tobytes()
     assert np.concatenate([a[1], b[1]]).tobytes() == full[1].tobytes()
+
+
+@pytest.mark.parametrize("C,D,max_depth,eps,kind", [
+    (1, 1, 3, 0.4, "iid"),          # one chain, one coordinate
+    (2, 1, 1, 0.9, "funnel"),       # max_depth 1: every tree is a single doubling; funnel with D = 1 is N(0, 9)
+    (3, 32, 2, 0.2, "gauss"),       # D exactly one lane row
+    (3, 33, 4, 0.2, "gauss"),       # one element into the next group of 32
+    (2, 128, 3, 0.05, "logit"),     # D = 128: four full lane rows
+    (2, 129, 3, 0.05, "logit"),
+    (4, 5, 20, 1e-3, "iid"),        # max_depth at the engine's limit, tiny step: deep trees (capped by the draw count)
+    (4, 7, 6, 50.0, "funnel"),      # absurd step: every first leaf diverges
+    (5, 6, 5, 1e-7, "iid"),         # near-zero step: every tree hits max depth without turning
+])
+def test_edge_shapes_and_regimes_bitwise(bn, oracle_lib, hostemu_lib, C, D, max_depth, eps, kind):
+    """Extreme shapes and integrator regimes, the host build of the product state machine against the oracle:
+    draws, statistics, selected indices and final state bit for bit; the regime each case is meant to reach is
+    asserted so the test cannot pass vacuously."""
+    outs = []
+    n = 6 if max_depth >= 20 else 25
+    for lib in (oracle_lib, hostemu_lib):
+        e = bn.Engine(C, D, max_depth=max_depth, lib=lib, seed=13)
+        set_model(e, kind, D, N=120)
+        e.set_positions(None)
+        e.set_stepsize(eps)
+        ch, st, sel = e.sample(n, want_index=True)
+        one = e.sample(1)                                      # a single-draw call
+        outs.append([ch, st, sel, one[0], one[1], e.get_state()[0], e.get_state()[1]])
+    assert_bitwise(outs[0], outs[1])
+    st = outs[0][1]
+    assert (st["depth"] <= max_depth).all() and (st["steps"] >= 1).all()
+    if eps >= 50.0:
+        assert (st["term_left"] == st["term_right"]).mean() > 0.9          # divergence at a leaf: InvalidTree(i, i)
+        assert (outs[0][0][:, 0] == outs[0][0][:, -1]).all()               # nothing is ever accepted: chains stay put
+    if eps <= 1e-7:
+        assert ((st["term_left"] == 1) & (st["term_right"] == 0)).all()    # REACHED_MAX_DEPTH every time
+        assert (st["steps"] == 2 ** max_depth - 1).all()
+    if max_depth == 1:
+        assert (st["steps"] == 1).all()
