@@ -145,6 +145,11 @@ int32_t bnuts_get_metric_diag(bnuts_engine* e, double* minv /* [C][D] */);
  * symmetric positive definite M⁻¹ [D][D] shared by all chains; kinetic energy ½pᵀM⁻¹p, p♯ = M⁻¹p, drift
  * q + εM⁻¹p, momenta p = L⁻ᵀz with M⁻¹ = LLᵀ.  Implemented by whitening (see engine_core.h); Gaussian and iid
  * normal targets.  minv == NULL returns to the per-chain diagonal metric.  Existing positions are kept. */
+/* ≙ GaussianKineticEnergy(M⁻¹, W), src/hamiltonian.jl:33-38, holds BOTH fields.  The metric update forms W from the
+ * Float64 variance before M⁻¹ is rounded to the engine's type (src/hamiltonian.jl:153-162), so in an fp32 engine W is
+ * not a function of the stored M⁻¹: a checkpoint carries the pair. */
+int32_t bnuts_get_metric_diag_w(bnuts_engine* e, double* w /* [C][D] */);
+int32_t bnuts_set_metric_diag_pair(bnuts_engine* e, const double* minv /* [C][D] */, const double* w /* [C][D] */);
 int32_t bnuts_set_metric_dense(bnuts_engine* e, const double* minv /* [D][D] */);
 int32_t bnuts_get_metric_dense(bnuts_engine* e, double* minv /* [D][D] */);
 
@@ -153,6 +158,12 @@ int32_t bnuts_get_stepsize(bnuts_engine* e, double* eps /* [C] */);
 
 /* Philox key and the transition counter the next transition will use. */
 int32_t bnuts_seed(bnuts_engine* e, uint64_t seed, uint32_t next_transition);
+
+/* ≙ WarmupState (src/warmup.jl:47-51) is (z, κ, ϵ); the engine's counterpart of the rng argument every reference entry
+ * point takes is (seed, next transition index).  bnuts_get_state / bnuts_get_metric_diag / bnuts_get_stepsize /
+ * bnuts_get_rng read everything a run needs to continue; the matching setters restore it in a fresh engine, and the
+ * continued run is bit-identical to an uninterrupted one (checkpoint / resume; tests/test_checkpoint_resume.py). */
+int32_t bnuts_get_rng(bnuts_engine* e, uint64_t* seed, uint32_t* next_transition);
 
 /* ≙ sample_tree(...; p = …, directions = …) src/NUTS.jl:251-258: the next T
  * transitions of every chain use these directions and momenta instead of Philox.

@@ -56,7 +56,7 @@ EXPORTS = [
     "bnuts_create", "bnuts_destroy", "bnuts_last_error", "bnuts_model_iid_normal", "bnuts_model_funnel",
     "bnuts_model_gaussian", "bnuts_model_logistic", "bnuts_model_logistic_synthetic", "bnuts_synth_logistic_rows",
     "bnuts_logistic_set_reference", "bnuts_set_positions", "bnuts_get_state",
-    "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_set_metric_dense", "bnuts_get_metric_dense", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed",
+    "bnuts_set_metric_diag", "bnuts_get_metric_diag", "bnuts_get_metric_diag_w", "bnuts_set_metric_diag_pair", "bnuts_set_metric_dense", "bnuts_get_metric_dense", "bnuts_set_stepsize", "bnuts_get_stepsize", "bnuts_seed", "bnuts_get_rng",
     "bnuts_inject", "bnuts_leapfrog", "bnuts_find_local_optimum", "bnuts_find_initial_stepsize", "bnuts_warmup_stage", "bnuts_sample",
     "bnuts_counters", "bnuts_profile", "bnuts_chain_status", "bnuts_set_allreduce", "bnuts_nccl_unique_id", "bnuts_set_nccl",
     "bnuts_p2p_export", "bnuts_p2p_connect",
@@ -100,11 +100,14 @@ def load_library(path=None):
     lib.bnuts_get_state.argtypes = [_P, _P, _P, _P]
     lib.bnuts_set_metric_diag.argtypes = [_P, _P]
     lib.bnuts_get_metric_diag.argtypes = [_P, _P]
+    lib.bnuts_get_metric_diag_w.argtypes = [_P, _P]
+    lib.bnuts_set_metric_diag_pair.argtypes = [_P, _P, _P]
     lib.bnuts_set_metric_dense.argtypes = [_P, _P]
     lib.bnuts_get_metric_dense.argtypes = [_P, _P]
     lib.bnuts_set_stepsize.argtypes = [_P, _P]
     lib.bnuts_get_stepsize.argtypes = [_P, _P]
     lib.bnuts_seed.argtypes = [_P, C.c_uint64, C.c_uint32]
+    lib.bnuts_get_rng.argtypes = [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     lib.bnuts_inject.argtypes = [_P, C.c_int32, _P, _P]
     lib.bnuts_leapfrog.argtypes = [_P, _P, _P, C.c_int32, _P, _P, _P, _P]
     lib.bnuts_find_local_optimum.argtypes = [_P, C.c_double, C.c_int32]
@@ -268,6 +271,15 @@ class Engine:
         self._chk(self.lib.bnuts_get_metric_diag(self.h, _ptr(m)))
         return m
 
+    def get_metric_diag_w(self):
+        w = np.empty((self.C, self.D))
+        self._chk(self.lib.bnuts_get_metric_diag_w(self.h, _ptr(w)))
+        return w
+
+    def set_metric_diag_pair(self, minv, w):
+        m = _f64(minv, (self.C, self.D)); w = _f64(w, (self.C, self.D))
+        self._chk(self.lib.bnuts_set_metric_diag_pair(self.h, _ptr(m), _ptr(w)))
+
     def set_metric_dense(self, minv=None):
         """One dense SPD M⁻¹ [D, D] shared by all chains (None: back to the per-chain diagonal metric)."""
         m = _f64(minv, (self.D, self.D))
@@ -289,6 +301,29 @@ class Engine:
 
     def seed(self, seed, next_transition=0):
         self._chk(self.lib.bnuts_seed(self.h, seed, next_transition))
+
+    def rng(self):
+        """(seed, next transition index): the position of the counter-based generator."""
+        s, t = C.c_uint64(0), C.c_uint32(0)
+        self._chk(self.lib.bnuts_get_rng(self.h, C.byref(s), C.byref(t)))
+        return int(s.value), int(t.value)
+
+    # ---- ≙ WarmupState (z, κ, ϵ), src/warmup.jl:47-51, plus the generator position: checkpoint / resume
+    def warmup_state(self):
+        seed, t = self.rng()
+        return {"q": self.get_state()[0], "κ": self.get_metric_diag(), "W": self.get_metric_diag_w(), "ϵ": self.get_stepsize(),
+                "seed": seed, "next_transition": t}
+
+    def restore(self, state):
+        """Continue from a `warmup_state()` of another engine with the same model, dtype and chain ids: the continued
+        run is bit-identical to an uninterrupted one (ℓ and ∇ℓ are re-evaluated at q, deterministically)."""
+        if state.get("W") is not None:
+            self.set_metric_diag_pair(state["κ"], state["W"])      # ≙ GaussianKineticEnergy(M⁻¹, W): both fields
+        else:
+            self.set_metric_diag(state["κ"])
+        self.set_stepsize(state["ϵ"])
+        self.seed(state["seed"], state["next_transition"])
+        self.set_positions(state["q"])
 
     def inject(self, T, dirs=None, p=None):
         if dirs is not None:

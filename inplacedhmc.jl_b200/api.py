@@ -191,6 +191,52 @@ def threaded_mcmc(ℓ, N, δ=0.8, initialization=None, warmup_stages=None, algor
     return chains, stats
 
 
+def mcmc_keep_warmup(ℓ, N, δ=0.8, initialization=None, warmup_stages=None, algorithm=None, nchains=4096, dtype=capi.F64,
+                     seed=20261018, device=0, chain_offset=0, gradient_path=capi.GRAD_AUTO, lib=None):
+    """≙ mcmc_keep_warmup (documented, not exported, in the reference: src/mcmc.jl:23-50): MCMC with NUTS keeping the
+    warmup results.  Returns a dict with
+      initial_warmup_state, final_warmup_state : warmup states (q, κ, ϵ, generator position; ≙ WarmupState, src/warmup.jl:47-51)
+      warmup    : list of dicts (stage, results = (chain, tree_statistics, ϵs) or None, warmup_state after the stage)
+      inference : (chain [nchains, N, D], tree_statistics [nchains, N])
+    Every warmup_state can be handed to `Engine.restore` / `initialization={"state": ...}` to continue from that point."""
+    algorithm = algorithm or NUTS()
+    initialization = initialization or {}
+    if warmup_stages is None:
+        warmup_stages = default_warmup_stages(stepsize_adaptation=DualAveraging(δ=δ))
+    e = capi.Engine(nchains, ℓ.dim, dtype=dtype, max_depth=algorithm.max_depth, min_delta=algorithm.min_Δ, seed=seed,
+                    chain_offset=chain_offset, device=device, gradient_path=gradient_path, lib=lib)
+    ℓ.attach(e)
+    if initialization.get("state") is not None:
+        e.restore(initialization["state"])
+    else:
+        κ = initialization.get("κ")
+        if κ is not None:
+            e.set_metric_diag(np.broadcast_to(np.asarray(κ.M_inv, dtype=np.float64), (nchains, ℓ.dim)))
+        e.set_positions(initialization.get("q"))
+        if initialization.get("ϵ") is not None:
+            e.set_stepsize(initialization["ϵ"])
+    out = {"initial_warmup_state": e.warmup_state(), "warmup": []}
+    for st in warmup_stages:
+        if st is None:
+            continue
+        results = None
+        if isinstance(st, FindLocalOptimum):
+            e.find_local_optimum(st.magnitude_penalty, st.iterations)
+        elif isinstance(st, InitialStepsizeSearch):
+            e.find_initial_stepsize(st.a_min, st.a_max, st.ϵ0, st.C, st.maxiter_crossing, st.maxiter_bisect)
+        elif isinstance(st, TuningNUTS):
+            da = st.stepsize_adaptation
+            results = e.warmup_stage(st.N, capi.METRIC_DIAG if st.M else capi.METRIC_NONE, da.δ, da.γ, da.κ, da.t0,
+                                     -1.0 if st.λ is None else st.λ)
+        else:
+            raise TypeError(f"unknown warmup stage {st!r}")
+        out["warmup"].append({"stage": st, "results": results, "warmup_state": e.warmup_state()})
+    out["final_warmup_state"] = e.warmup_state()
+    out["inference"] = e.sample(N)
+    e.close()
+    return out
+
+
 def mcmc_with_warmup(ℓ, N, **kw):
     """≙ mcmc_with_warmup(ℓ, N; ...), src/mcmc.jl:109-128: one chain; returns (chain [N, D], tree_statistics [N])."""
     kw.setdefault("nchains", 1)

@@ -86,6 +86,11 @@ int32_t bnuts_get_metric_diag(bnuts_engine* e, double* m) {
   if (!m) return BNUTS_ERR_INVALID_ARGUMENT;
   BN_DISPATCH(e, get_metric(m));
 }
+int32_t bnuts_get_metric_diag_w(bnuts_engine* e, double* w) {
+  if (!w) return BNUTS_ERR_INVALID_ARGUMENT;
+  BN_DISPATCH(e, get_metric_w(w));
+}
+int32_t bnuts_set_metric_diag_pair(bnuts_engine* e, const double* m, const double* w) { BN_DISPATCH(e, set_metric_pair(m, w)); }
 int32_t bnuts_set_metric_dense(bnuts_engine* e, const double* m) { BN_DISPATCH(e, set_metric_dense(m)); }
 int32_t bnuts_get_metric_dense(bnuts_engine* e, double* m) {
   if (!m) return BNUTS_ERR_INVALID_ARGUMENT;
@@ -104,6 +109,13 @@ int32_t bnuts_seed(bnuts_engine* e, uint64_t seed, uint32_t next_t) {
   AnyEngine* ae = reinterpret_cast<AnyEngine*>(e);
   if (ae->dtype == BNUTS_F64) { ae->e64->rp.seed = seed; ae->e64->next_t = next_t; }
   else { ae->e32->rp.seed = seed; ae->e32->next_t = next_t; }
+  return 0;
+}
+int32_t bnuts_get_rng(bnuts_engine* e, uint64_t* seed, uint32_t* next_t) {
+  if (!e || !seed || !next_t) return BNUTS_ERR_INVALID_ARGUMENT;
+  AnyEngine* ae = reinterpret_cast<AnyEngine*>(e);
+  if (ae->dtype == BNUTS_F64) { *seed = ae->e64->rp.seed; *next_t = ae->e64->next_t; }
+  else { *seed = ae->e32->rp.seed; *next_t = ae->e32->next_t; }
   return 0;
 }
 int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const double* p) { BN_DISPATCH(e, inject(T, dirs, p)); }

@@ -411,6 +411,28 @@ template <class T, class X> struct EngineCore {
     x.h2d(M.W, hw.data(), hw.size() * sizeof(T));
     return x.check(err);
   }
+  // ≙ GaussianKineticEnergy(M⁻¹, W), src/hamiltonian.jl:33-38: the reference type holds BOTH fields.  The metric update
+  // forms W from the Float64 variance before M⁻¹ is rounded to T (k_metric / metric_update), so in an fp32 engine W is not
+  // a function of the stored M⁻¹: a checkpoint has to carry it (bnuts_get_metric_diag_w / bnuts_set_metric_diag_pair).
+  int32_t set_metric_pair(const double* minv, const double* w) {
+    if (!minv || !w) return fail(BNUTS_ERR_INVALID_ARGUMENT, "minv and w required");
+    std::vector<T> hm(size_t(M.C) * M.Dp, T(1)), hw(size_t(M.C) * M.Dp, T(1));
+    for (int c = 0; c < M.C; ++c)
+      for (int d = 0; d < M.D; ++d) {
+        hm[size_t(c) * M.Dp + d] = T(minv[size_t(c) * M.D + d]);
+        hw[size_t(c) * M.Dp + d] = T(w[size_t(c) * M.D + d]);
+      }
+    x.h2d(M.Minv, hm.data(), hm.size() * sizeof(T));
+    x.h2d(M.W, hw.data(), hw.size() * sizeof(T));
+    return x.check(err);
+  }
+  int32_t get_metric_w(double* out) {
+    std::vector<T> hw(size_t(M.C) * M.Dp);
+    x.d2h(hw.data(), M.W, hw.size() * sizeof(T));
+    for (int c = 0; c < M.C; ++c)
+      for (int d = 0; d < M.D; ++d) out[size_t(c) * M.D + d] = double(hw[size_t(c) * M.Dp + d]);
+    return x.check(err);
+  }
   // ---------------------------------------------------------------- dense metric (see DenseMetric above)
   void free_dense() {
     void** ps[] = {(void**)&dm.dL, (void**)&dm.dLt, (void**)&dm.dLinv, (void**)&dm.dLinvt};

@@ -147,6 +147,26 @@ join_row_shards!(e, id::Vector{UInt8}, world::Integer, rank::Integer) =
 set_reference!(e, β₀::Vector{Float64}) =
     check(e, ccall((:bnuts_logistic_set_reference, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, β₀))
 
+"""≙ WarmupState (z, κ, ϵ), src/warmup.jl:47-51, plus the position of the counter-based generator: everything a run needs
+to continue.  `restore!` in a fresh engine (same model, dtype, chain ids) continues bit-identically (tests/test_checkpoint_resume.py)."""
+struct WarmupState; q::Matrix{Float64}; M⁻¹::Matrix{Float64}; W::Matrix{Float64}; ϵ::Vector{Float64}; seed::UInt64; next_transition::UInt32; end
+function warmup_state(e, D, nchains)
+    q = Matrix{Float64}(undef, D, nchains); Mi = similar(q); W = similar(q); ϵ = Vector{Float64}(undef, nchains)
+    seed = Ref{UInt64}(0); t = Ref{UInt32}(0)
+    check(e, ccall((:bnuts_get_state, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), e, q, C_NULL, C_NULL))
+    check(e, ccall((:bnuts_get_metric_diag, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, Mi))
+    check(e, ccall((:bnuts_get_metric_diag_w, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, W))
+    check(e, ccall((:bnuts_get_stepsize, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, ϵ))
+    check(e, ccall((:bnuts_get_rng, libbnuts), Int32, (Ptr{Cvoid}, Ref{UInt64}, Ref{UInt32}), e, seed, t))
+    WarmupState(q, Mi, W, ϵ, seed[], t[])
+end
+function restore!(e, s::WarmupState)
+    check(e, ccall((:bnuts_set_metric_diag_pair, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), e, s.M⁻¹, s.W))
+    check(e, ccall((:bnuts_set_stepsize, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, s.ϵ))
+    check(e, ccall((:bnuts_seed, libbnuts), Int32, (Ptr{Cvoid}, UInt64, UInt32), e, s.seed, s.next_transition))
+    check(e, ccall((:bnuts_set_positions, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, s.q))
+end
+
 "≙ mcmc_with_warmup(ℓ, N; ...), src/mcmc.jl:109-128 (one chain)."
 function mcmc_with_warmup(ℓ, N; kw...)
     chains, stats = threaded_mcmc(ℓ, N; nchains = 1, kw...)

@@ -915,6 +915,20 @@ int32_t bnuts_set_nccl(bnuts_engine*, const uint8_t*, int32_t, int32_t) { return
 int32_t bnuts_set_positions(bnuts_engine* e, const double* q) { DISPATCH(e, set_positions(E, q), set_positions(E, q)); }
 int32_t bnuts_get_state(bnuts_engine* e, double* q, double* g, double* l) { DISPATCH(e, get_state(E, q, g, l), get_state(E, q, g, l)); }
 int32_t bnuts_set_metric_diag(bnuts_engine* e, const double* m) { DISPATCH(e, set_metric(E, m), set_metric(E, m)); }
+int32_t bnuts_get_metric_diag_w(bnuts_engine* e, double* w) {
+  if (!w) return BNUTS_ERR_INVALID_ARGUMENT;
+  DISPATCH(e, ([&] { for (size_t i = 0; i < E.W.size(); ++i) w[i] = double(E.W[i]); return 0; })(),
+              ([&] { for (size_t i = 0; i < E.W.size(); ++i) w[i] = double(E.W[i]); return 0; })());
+}
+int32_t bnuts_set_metric_diag_pair(bnuts_engine* e, const double* m, const double* w) {
+  if (!m || !w) return BNUTS_ERR_INVALID_ARGUMENT;
+  auto set = [&](auto& E) {
+    using T = typename std::remove_reference<decltype(E.W[0])>::type;
+    for (size_t i = 0; i < E.W.size(); ++i) { E.Minv[i] = T(m[i]); E.W[i] = T(w[i]); }
+    return 0;
+  };
+  DISPATCH(e, set(E), set(E));
+}
 int32_t bnuts_set_metric_dense(bnuts_engine* e, const double* m) { DISPATCH(e, set_metric_dense(E, m), set_metric_dense(E, m)); }
 int32_t bnuts_get_metric_dense(bnuts_engine* e, double* m) {
   if (!m) return BNUTS_ERR_INVALID_ARGUMENT;
@@ -941,6 +955,10 @@ int32_t bnuts_get_stepsize(bnuts_engine* e, double* eps) {
 }
 int32_t bnuts_seed(bnuts_engine* e, uint64_t seed, uint32_t next_t) {
   DISPATCH(e, ([&] { E.seed = seed; E.next_t = next_t; return 0; })(), ([&] { E.seed = seed; E.next_t = next_t; return 0; })());
+}
+int32_t bnuts_get_rng(bnuts_engine* e, uint64_t* seed, uint32_t* next_t) {
+  if (!seed || !next_t) return BNUTS_ERR_INVALID_ARGUMENT;
+  DISPATCH(e, ([&] { *seed = E.seed; *next_t = E.next_t; return 0; })(), ([&] { *seed = E.seed; *next_t = E.next_t; return 0; })());
 }
 int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const double* p) { DISPATCH(e, inject(E, T, dirs, p), inject(E, T, dirs, p)); }
 int32_t bnuts_leapfrog(bnuts_engine* e, const double* p_in, const double* eps, int32_t nsteps, double* q_out,
