@@ -111,3 +111,23 @@ def test_edge_shapes_and_regimes_bitwise(bn, oracle_lib, hostemu_lib, C, D, max_
         assert (st["steps"] == 2 ** max_depth - 1).all()
     if max_depth == 1:
         assert (st["steps"] == 1).all()
+
+
+def test_config_c1_full_run_bitwise_and_moments(bn, oracle_lib, hostemu_lib):
+    """BASELINE config 1 exactly as stated (100-dim iid standard normal, diagonal metric, max depth 10, 1000 warmup
+    (75 | 25..400 | 150) + 1000 draws, one chain): the host build of the product against the oracle bit for bit over
+    the whole run, and the draws against N(0, I) within Monte-Carlo error."""
+    stages = bn.default_warmup_stages(local_optimization=None, terminating_steps=150)
+    runs = [bn.mcmc_keep_warmup(bn.IIDNormal(100), 1000, warmup_stages=stages, nchains=1, lib=lib, seed=1)
+            for lib in (oracle_lib, hostemu_lib)]
+    a, b = runs
+    assert sum(w["stage"].N for w in a["warmup"] if hasattr(w["stage"], "N")) == 1000
+    for wa, wb in zip(a["warmup"], b["warmup"]):
+        for k in ("q", "κ", "W", "ϵ"):
+            assert wa["warmup_state"][k].tobytes() == wb["warmup_state"][k].tobytes()
+    assert a["inference"][0].tobytes() == b["inference"][0].tobytes() and a["inference"][1].tobytes() == b["inference"][1].tobytes()
+    ch, st = a["inference"]
+    ess = np.array([bn.diagnostics.ess(ch[:, :, d], rank_normalise=False) for d in range(100)])   # one chain per coordinate
+    ess2 = np.array([bn.diagnostics.ess(ch[:, :, d] ** 2, rank_normalise=False) for d in range(100)])   # of the second moment
+    assert np.all(np.abs(ch[0].mean(0)) < 5 / np.sqrt(ess)) and np.all(np.abs((ch[0] ** 2).mean(0) - 1) < 5 * np.sqrt(2 / ess2))
+    assert (st["depth"] <= 10).all() and (st["term_left"] != st["term_right"]).all()      # no divergences on N(0, I)
