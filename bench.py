@@ -114,7 +114,8 @@ def run_reference(a, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "c3: Bayesian logistic regression N=%d D=%d (bounded sample per step)" % (a.rows, a.dim)},
+        "config": {"workload": "c3: Bayesian logistic regression N=%d D=%d, 4096 chains total, max_depth 10" % (a.rows, a.dim),
+                   "sample": "bounded sample of the workload per step: bare leapfrogs (integrator + gradient) of one chain per host thread"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
