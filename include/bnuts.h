@@ -191,6 +191,7 @@ int32_t bnuts_find_initial_stepsize(bnuts_engine* e, const bnuts_stepsize_search
  * averaging restarted from the current eps (src/stepsize.jl:208-212), then (metric_kind
  * == DIAG) the regularised variance update (src/hamiltonian.jl:117-189) and
  * eps <- final_ϵ (src/stepsize.jl:241).  lambda < 0 means the default 5/N.
+ * da == NULL ≙ FixedStepsize (src/stepsize.jl:251-255; fixed_stepsize_warmup_stages, src/warmup.jl:383-389): ϵ is kept.
  * Optional outputs: chain_out/stats_out as bnuts_sample; eps_out [C][N]. */
 int32_t bnuts_warmup_stage(bnuts_engine* e, int32_t N, int32_t metric_kind,
                            const bnuts_dual_averaging* da, double lambda,

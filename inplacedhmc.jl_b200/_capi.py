@@ -351,12 +351,14 @@ class Engine:
                          allow=(-4, -5) if allow_fail else ())
 
     def warmup_stage(self, N, metric_kind=METRIC_NONE, delta=0.8, gamma=0.05, kappa=0.75, t0=10, lam=-1.0,
-                     keep=True, allow_fail=False):
+                     keep=True, allow_fail=False, fixed_stepsize=False):
+        """≙ warmup!(…, TuningNUTS{M}, …), src/warmup.jl:269-314.  fixed_stepsize=True ≙ FixedStepsize (src/stepsize.jl:251-255):
+        ϵ is kept, only the metric is tuned."""
         da = DualAveragingParams(delta, gamma, kappa, t0, 0)
         chain = np.empty((self.C, N, self.D)) if keep else None
         stats = np.zeros((self.C, N), dtype=TREE_STATS_DTYPE) if keep else None
         eps = np.empty((self.C, N)) if keep else None
-        self._chk(self.lib.bnuts_warmup_stage(self.h, N, metric_kind, C.byref(da), lam, _ptr(chain), self.D,
+        self._chk(self.lib.bnuts_warmup_stage(self.h, N, metric_kind, None if fixed_stepsize else C.byref(da), lam, _ptr(chain), self.D,
                                               N * self.D, _ptr(stats), N, _ptr(eps)),
                   allow=(-6,) if allow_fail else ())
         return chain, stats, eps

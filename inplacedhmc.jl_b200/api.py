@@ -82,6 +82,10 @@ class DualAveraging:
 
 
 @dataclass
+class FixedStepsize:
+    """≙ FixedStepsize, src/stepsize.jl:251-255: a warmup stage with this adaptation keeps ϵ."""
+
+
 class InitialStepsizeSearch:
     """≙ src/stepsize.jl:16-38"""
     a_min: float = 0.25
@@ -144,6 +148,12 @@ def default_warmup_stages(local_optimization=FindLocalOptimum(), stepsize_search
         (TuningNUTS(terminating_steps, da, None),)
 
 
+def fixed_stepsize_warmup_stages(local_optimization=FindLocalOptimum(), M="Diagonal", middle_steps=25, doubling_stages=5):
+    """≙ fixed_stepsize_warmup_stages, src/warmup.jl:383-389: local optimisation, then the doubling metric windows with the
+    step size fixed at the ϵ given in `initialization` (no step-size search, no dual averaging)."""
+    return (local_optimization,) + tuple(TuningNUTS(middle_steps << d, FixedStepsize(), M) for d in range(doubling_stages))
+
+
 def _run_warmup(e, stages):
     for st in stages:
         if st is None:
@@ -154,8 +164,10 @@ def _run_warmup(e, stages):
             e.find_initial_stepsize(st.a_min, st.a_max, st.ϵ0, st.C, st.maxiter_crossing, st.maxiter_bisect)
         elif isinstance(st, TuningNUTS):
             da = st.stepsize_adaptation
+            fixed = isinstance(da, FixedStepsize)
+            da = DualAveraging() if fixed else da
             e.warmup_stage(st.N, capi.METRIC_DIAG if st.M else capi.METRIC_NONE, da.δ, da.γ, da.κ, da.t0,
-                           -1.0 if st.λ is None else st.λ, keep=False)
+                           -1.0 if st.λ is None else st.λ, keep=False, fixed_stepsize=fixed)
         else:
             raise TypeError(f"unknown warmup stage {st!r}")
 
@@ -226,8 +238,10 @@ def mcmc_keep_warmup(ℓ, N, δ=0.8, initialization=None, warmup_stages=None, al
             e.find_initial_stepsize(st.a_min, st.a_max, st.ϵ0, st.C, st.maxiter_crossing, st.maxiter_bisect)
         elif isinstance(st, TuningNUTS):
             da = st.stepsize_adaptation
+            fixed = isinstance(da, FixedStepsize)
+            da = DualAveraging() if fixed else da
             results = e.warmup_stage(st.N, capi.METRIC_DIAG if st.M else capi.METRIC_NONE, da.δ, da.γ, da.κ, da.t0,
-                                     -1.0 if st.λ is None else st.λ)
+                                     -1.0 if st.λ is None else st.λ, fixed_stepsize=fixed)
         else:
             raise TypeError(f"unknown warmup stage {st!r}")
         out["warmup"].append({"stage": st, "results": results, "warmup_state": e.warmup_state()})

@@ -44,10 +44,13 @@ Base.@kwdef struct InitialStepsizeSearch                                        
     maxiter_crossing::Int = 400; maxiter_bisect::Int = 400
 end
 Base.@kwdef struct FindLocalOptimum; magnitude_penalty::Float64 = 1e-4; iterations::Int = 50; end # src/warmup.jl:137-150
+struct FixedStepsize end                                                                           # src/stepsize.jl:251-255
 struct TuningNUTS{M}                                                                               # src/warmup.jl:217-234
-    N::Int; stepsize_adaptation::DualAveraging; λ::Float64
+    N::Int; stepsize_adaptation::Union{DualAveraging,FixedStepsize}; λ::Float64
 end
-TuningNUTS{M}(N::Integer, da::DualAveraging, λ = 5.0 / N) where {M} = TuningNUTS{M}(Int(N), da, Float64(λ))
+TuningNUTS{M}(N::Integer, da::Union{DualAveraging,FixedStepsize}, λ = 5.0 / N) where {M} = TuningNUTS{M}(Int(N), da, Float64(λ))
+fixed_stepsize_warmup_stages(; local_optimization = FindLocalOptimum(), M = :Diagonal, middle_steps = 25, doubling_stages = 5) =
+    (local_optimization, ntuple(d -> TuningNUTS{M}(middle_steps << (d - 1), FixedStepsize()), doubling_stages)...)   # src/warmup.jl:383-389
 Base.length(t::TuningNUTS) = t.N
 struct GaussianKineticEnergy; M⁻¹::Matrix{Float64}; end     # [D, nchains] diagonals, src/hamiltonian.jl:33-38
 struct NoProgressReport end
@@ -92,6 +95,11 @@ function warmup!(e, s::InitialStepsizeSearch)                                   
 end
 function warmup!(e, t::TuningNUTS{M}) where {M}                                                   # ≙ src/warmup.jl:269-314
     da = t.stepsize_adaptation
+    if da isa FixedStepsize                                                                      # ≙ src/stepsize.jl:251-255: NULL keeps ϵ
+        return check(e, ccall((:bnuts_warmup_stage, libbnuts), Int32,
+            (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}, Float64, Ptr{Float64}, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Float64}),
+            e, t.N, M === Nothing ? 0 : 1, C_NULL, t.λ, C_NULL, 0, 0, C_NULL, 0, C_NULL))
+    end
     p = Ref(bnuts_dual_averaging(da.δ, da.γ, da.κ, da.t₀, 0))
     check(e, ccall((:bnuts_warmup_stage, libbnuts), Int32,
         (Ptr{Cvoid}, Int32, Int32, Ref{bnuts_dual_averaging}, Float64, Ptr{Float64}, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Float64}),

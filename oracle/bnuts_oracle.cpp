@@ -976,7 +976,7 @@ int32_t bnuts_find_initial_stepsize(bnuts_engine* e, const bnuts_stepsize_search
 int32_t bnuts_warmup_stage(bnuts_engine* e, int32_t N, int32_t metric_kind, const bnuts_dual_averaging* da,
                            double lambda, double* chain_out, int64_t sd, int64_t sc, bnuts_tree_stats* stats_out,
                            int64_t ssc, double* eps_out) {
-  if (!da) return BNUTS_ERR_INVALID_ARGUMENT;
+  // da == NULL ≙ FixedStepsize (src/stepsize.jl:251-255): the stage keeps ϵ and only tunes the metric
   DISPATCH(e, run_transitions(E, N, da, metric_kind, lambda, chain_out, sd, sc, stats_out, ssc, nullptr, eps_out),
            run_transitions(E, N, da, metric_kind, lambda, chain_out, sd, sc, stats_out, ssc, nullptr, eps_out));
 }

@@ -51,3 +51,27 @@ def test_ess_known_cases(bn):
     want = 8 * 4000 * (1 - rho) / (1 + rho)
     assert 0.7 * want < bn.diagnostics.ess(x) < 1.4 * want
     assert bn.diagnostics.min_ess(np.stack([iid, x[:, :2000]], axis=2)) < 0.2 * 16000
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_fixed_stepsize_warmup_stages(bn, oracle_lib, hostemu_lib, dtype):
+    """≙ fixed_stepsize_warmup_stages (src/warmup.jl:383-389) with FixedStepsize (src/stepsize.jl:251-255): the doubling
+    metric windows run at the ϵ given in `initialization`; the step size never changes, the metric does; the host
+    build of the product agrees with the oracle bit for bit."""
+    stages = bn.fixed_stepsize_warmup_stages(local_optimization=None, middle_steps=10, doubling_stages=3)
+    assert [s.N for s in stages[1:]] == [10, 20, 40] and all(isinstance(s.stepsize_adaptation, bn.FixedStepsize) for s in stages[1:])
+    eps0 = np.array([0.11, 0.23, 0.35])
+    outs = []
+    for lib in (oracle_lib, hostemu_lib):
+        r = bn.mcmc_keep_warmup(bn.Funnel(7), 12, warmup_stages=stages, nchains=3, lib=lib, seed=4, dtype=dtype,
+                                initialization={"ϵ": eps0})
+        for w in r["warmup"]:
+            assert np.array_equal(w["warmup_state"]["ϵ"], r["initial_warmup_state"]["ϵ"])       # ϵ is kept ...
+            assert np.all(w["results"][2] == r["initial_warmup_state"]["ϵ"][:, None])             # ... in every transition
+        assert not np.array_equal(r["final_warmup_state"]["κ"], r["initial_warmup_state"]["κ"])   # the metric is tuned
+        outs.append(r)
+    a, b = outs
+    for wa, wb in zip(a["warmup"], b["warmup"]):
+        for x, y in zip(wa["results"], wb["results"]):
+            assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+    assert a["inference"][0].tobytes() == b["inference"][0].tobytes() and a["inference"][1].tobytes() == b["inference"][1].tobytes()
