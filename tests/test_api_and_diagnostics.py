@@ -75,3 +75,18 @@ def test_fixed_stepsize_warmup_stages(bn, oracle_lib, hostemu_lib, dtype):
         for x, y in zip(wa["results"], wb["results"]):
             assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
     assert a["inference"][0].tobytes() == b["inference"][0].tobytes() and a["inference"][1].tobytes() == b["inference"][1].tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_cuda_fixed_stepsize_warmup_bitwise(bn, oracle_lib, cuda_lib, dtype):
+    """The FixedStepsize stage on the CUDA engine (deterministic gradient path) against the oracle, bit for bit."""
+    stages = bn.fixed_stepsize_warmup_stages(local_optimization=None, middle_steps=10, doubling_stages=3)
+    runs = [bn.mcmc_keep_warmup(bn.Funnel(7), 12, warmup_stages=stages, nchains=3, lib=lib, seed=4, dtype=dtype,
+                                initialization={"ϵ": np.array([0.11, 0.23, 0.35])}, **kw)
+            for lib, kw in ((oracle_lib, {}), (cuda_lib, {"gradient_path": 1}))]
+    a, b = runs
+    for wa, wb in zip(a["warmup"], b["warmup"]):
+        for x, y in zip(wa["results"], wb["results"]):
+            assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+    assert a["inference"][0].tobytes() == b["inference"][0].tobytes() and a["inference"][1].tobytes() == b["inference"][1].tobytes()
