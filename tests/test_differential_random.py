@@ -7,7 +7,7 @@ from hypothesis import given, settings, strategies as st, HealthCheck
 from conftest import set_model
 
 
-@settings(max_examples=250, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@settings(max_examples=1000, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
 @given(C=st.integers(1, 5), D=st.integers(1, 70), depth=st.integers(1, 8), kind=st.sampled_from(["iid", "funnel", "gauss", "logit"]),
        eps=st.floats(1e-3, 3.0), min_delta=st.sampled_from([-1000.0, -5.0, -0.5]), seed=st.integers(0, 2 ** 40),
        dtype=st.sampled_from([0, 1]), adapt=st.booleans())
