@@ -159,3 +159,37 @@ def test_divergence_keeps_last_completed_tree(bn, oracle_lib):
     assert s["term_left"] == s["term_right"] == 1 and s["depth"] == 0 and s["steps"] == 1
     assert sel[0, 0] == 0
     np.testing.assert_array_equal(ch[0, 0], q0[0])
+
+
+from hypothesis import given, settings, strategies as hst, HealthCheck  # noqa: E402
+
+
+@settings(max_examples=120, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(D=hst.integers(1, 9), max_depth=hst.integers(1, 6), eps=hst.floats(0.02, 2.5), min_delta=hst.sampled_from([-1000.0, -2.0, -0.2]),
+       seed=hst.integers(0, 2 ** 31), rs=hst.integers(0, 2 ** 31))
+def test_oracle_matches_transcription_on_random_configurations(bn, oracle_lib, D, max_depth, eps, min_delta, seed, rs):
+    """The oracle against the independent literal Python transcription of the reference recursion (class Ref above)
+    on random shapes, step sizes, depth caps, divergence thresholds, injected momenta and directions: termination
+    code, depth, steps and the selected index exact; the draw to 1e-12."""
+    Cn, T = 2, 3
+    rng = np.random.default_rng(rs)
+    q0 = rng.normal(size=(Cn, D))
+    p = rng.normal(size=(T, Cn, D))
+    dirs = rng.integers(0, 2 ** 32, size=(T, Cn), dtype=np.uint64).astype(np.uint32)
+    e = bn.Engine(Cn, D, max_depth=max_depth, min_delta=min_delta, lib=oracle_lib, seed=seed)
+    e.model_iid_normal()
+    e.set_positions(q0)
+    e.set_stepsize(eps)
+    e.inject(T, dirs, p)
+    ch, st, sel = e.sample(T, want_index=True)
+    for c in range(Cn):
+        q = q0[c]
+        for t in range(T):
+            r = Ref(oracle_lib, seed, c, t, eps, max_depth)
+            r.min_delta = min_delta
+            zeta, pi, acc, term, depth, steps = r.sample(q, p[t, c], int(dirs[t, c]))
+            s = st[c, t]
+            assert (s["term_left"], s["term_right"], s["depth"], s["steps"]) == (term[0], term[1], depth, steps)
+            assert sel[c, t] == zeta[1]
+            np.testing.assert_allclose(ch[c, t], zeta[0][0], atol=1e-12)
+            q = ch[c, t]
