@@ -1798,10 +1798,8 @@ __global__ void k_hess0_sum(const double* __restrict__ part, float* H0, int nb, 
 }  // namespace
 // quadratic-remainder mode (k_logistic_tc, RR == 2): per-row records, g0 = X̃ᵀ r0 and H0 = X̃ᵀ diag(w) X̃
 int32_t logistic_tc_write_quadratic_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev, std::string& err) {
-  if (!tc.aux && (cudaMalloc(&tc.aux, size_t(tc.Npad) * 2 * 4) != cudaSuccess || cudaMalloc(&tc.cw, size_t(tc.Npad) * 2 * 4) != cudaSuccess)) {
-    err = "device allocation failed (aux)";
-    return BNUTS_ERR_CUDA;
-  }
+  if (!tc.aux && cudaMalloc(&tc.aux, size_t(tc.Npad) * 2 * 4) != cudaSuccess) { tc.aux = nullptr; err = "device allocation failed (aux)"; return BNUTS_ERR_CUDA; }
+  if (!tc.cw && cudaMalloc(&tc.cw, size_t(tc.Npad) * 2 * 4) != cudaSuccess) { tc.cw = nullptr; err = "device allocation failed (aux)"; return BNUTS_ERR_CUDA; }
   if (!tc.H0 && cudaMalloc(&tc.H0, size_t(tc.Dp) * tc.Dp * 4) != cudaSuccess) { err = "device allocation failed (H0)"; return BNUTS_ERR_CUDA; }
   if (!tc.H0_part && cudaMalloc(&tc.H0_part, size_t(H0_BLOCKS) * tc.D * tc.D * 8) != cudaSuccess) { err = "device allocation failed (H0 partials)"; return BNUTS_ERR_CUDA; }
   cudaMemsetAsync(tc.H0, 0, size_t(tc.Dp) * tc.Dp * 4, s);
