@@ -665,6 +665,9 @@ template <class T, class X> struct EngineCore {
       return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad metric_kind");
     if (metric_kind == BNUTS_METRIC_DIAG && dm.on)
       return fail(BNUTS_ERR_UNSUPPORTED, "diagonal adaptation on top of a dense metric is not supported");
+    // the invariants the reference records as (commented-out) @argcheck's, src/stepsize.jl:183-186
+    if (da && !(da->delta > 0.0 && da->delta < 1.0 && da->gamma > 0.0 && da->kappa > 0.5 && da->kappa <= 1.0 && da->t0 >= 0))
+      return fail(BNUTS_ERR_INVALID_ARGUMENT, "dual averaging needs 0 < delta < 1, gamma > 0, 0.5 < kappa <= 1, t0 >= 0");
     const bool want_draws = chain_out != nullptr || metric_kind == BNUTS_METRIC_DIAG;
     ensure_out(N, want_draws);
     double* keep_draws = M.draws;
@@ -757,6 +760,9 @@ template <class T, class X> struct EngineCore {
   }
   int32_t find_initial_stepsize(const bnuts_stepsize_search& P) {
     if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
+    // ≙ the (commented-out) @argcheck's of InitialStepsizeSearch, src/stepsize.jl:31-35
+    if (!(P.a_min > 0.0 && P.a_min < P.a_max && P.a_max < 1.0 && P.C > 1.0 && P.eps0 > 0.0 && P.maxiter_crossing > 0 && P.maxiter_bisect > 0))
+      return fail(BNUTS_ERR_INVALID_ARGUMENT, "step size search needs 0 < a_min < a_max < 1, C > 1, eps0 > 0, positive iteration caps");
     rp.search.a_min = P.a_min; rp.search.a_max = P.a_max; rp.search.eps0 = P.eps0; rp.search.C = P.C;
     rp.search.maxiter_crossing = P.maxiter_crossing; rp.search.maxiter_bisect = P.maxiter_bisect;
     rp.da_on = 0;

@@ -574,6 +574,9 @@ int32_t run_transitions(Engine<T>& E, int N, const bnuts_dual_averaging* da, int
   if (N <= 0) return fail(E, BNUTS_ERR_INVALID_ARGUMENT, "N must be positive");
   if (metric_kind == BNUTS_METRIC_DIAG && E.dense)
     return fail(E, BNUTS_ERR_UNSUPPORTED, "diagonal adaptation on top of a dense metric is not supported");
+  // the invariants the reference records as (commented-out) @argcheck's, src/stepsize.jl:183-186
+  if (da && !(da->delta > 0.0 && da->delta < 1.0 && da->gamma > 0.0 && da->kappa > 0.5 && da->kappa <= 1.0 && da->t0 >= 0))
+    return fail(E, BNUTS_ERR_INVALID_ARGUMENT, "dual averaging needs 0 < delta < 1, gamma > 0, 0.5 < kappa <= 1, t0 >= 0");
   ensure_ctx(E);
   const int C = E.C, D = E.D;
   const uint32_t t0 = E.next_t;
@@ -618,6 +621,9 @@ int32_t run_transitions(Engine<T>& E, int N, const bnuts_dual_averaging* da, int
 
 template <class T> int32_t initial_stepsize(Engine<T>& E, const bnuts_stepsize_search& P) {
   if (E.model.kind == bn::MODEL_NONE) return fail(E, BNUTS_ERR_NO_MODEL, "no model set");
+  // ≙ the (commented-out) @argcheck's of InitialStepsizeSearch, src/stepsize.jl:31-35
+  if (!(P.a_min > 0.0 && P.a_min < P.a_max && P.a_max < 1.0 && P.C > 1.0 && P.eps0 > 0.0 && P.maxiter_crossing > 0 && P.maxiter_bisect > 0))
+    return fail(E, BNUTS_ERR_INVALID_ARGUMENT, "step size search needs 0 < a_min < a_max < 1, C > 1, eps0 > 0, positive iteration caps");
   ensure_ctx(E);
   const int C = E.C, D = E.D;
   const uint32_t t = E.next_t;

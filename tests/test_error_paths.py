@@ -45,6 +45,19 @@ def test_invalid_arguments(bn, lib):
     with pytest.raises(bn.BnutsError) as ei:
         e.set_metric_dense(bad)
     assert ei.value.code == -1
+    # the invariants the reference records as commented-out @argcheck's (src/stepsize.jl:31-35,183-186)
+    for kw in (dict(delta=0.0), dict(delta=1.0), dict(gamma=0.0), dict(kappa=0.5), dict(kappa=1.5), dict(t0=-1)):
+        with pytest.raises(bn.BnutsError) as ei:
+            e.warmup_stage(5, 0, **kw)
+        assert ei.value.code == -1, kw
+    for args in ((0.0, 0.75), (0.8, 0.75), (0.25, 1.0)):
+        with pytest.raises(bn.BnutsError) as ei:
+            e.find_initial_stepsize(*args)
+        assert ei.value.code == -1, args
+    with pytest.raises(bn.BnutsError) as ei:
+        e.find_initial_stepsize(0.25, 0.75, 1.0, 1.0)            # C must exceed 1
+    assert ei.value.code == -1
+    e.set_stepsize(0.3); e.warmup_stage(5, 0, fixed_stepsize=True)   # FixedStepsize needs no adaptation parameters
     assert e.chain_status().tolist() == [0, 0, 0]
     e.close()
 
