@@ -203,7 +203,10 @@ int32_t bnuts_warmup_stage(bnuts_engine* e, int32_t N, int32_t metric_kind,
  * (src/mcmc.jl:140-152): draw n of chain c is written at
  * chain_out[c*stride_chain + n*stride_draw + d] (strides in elements), its
  * statistics at stats_out[c*stats_stride_chain + n].  selected_index (may be
- * NULL) receives the trajectory position of the selected draw, [C][N]. */
+ * NULL) receives the trajectory position of the selected draw, [C][N].
+ * Chains whose bnuts_chain_status is non-zero (non-finite start, failed step size search, collapsed step size) do not
+ * move: their output rows are zero-filled and the call still returns 0 unless the failure happened inside it
+ * (BNUTS_ERR_STEPSIZE_COLLAPSE); callers mask rows with bnuts_chain_status. */
 int32_t bnuts_sample(bnuts_engine* e, int32_t N,
                      double* chain_out, int64_t stride_draw, int64_t stride_chain,
                      bnuts_tree_stats* stats_out, int64_t stats_stride_chain,

@@ -86,8 +86,9 @@ class FixedStepsize:
     """≙ FixedStepsize, src/stepsize.jl:251-255: a warmup stage with this adaptation keeps ϵ."""
 
 
+@dataclass
 class InitialStepsizeSearch:
-    """≙ src/stepsize.jl:16-38"""
+    """≙ InitialStepsizeSearch(; a_min, a_max, ϵ₀, C, maxiter_crossing, maxiter_bisect), src/stepsize.jl:16-38"""
     a_min: float = 0.25
     a_max: float = 0.75
     ϵ0: float = 1.0
@@ -179,6 +180,8 @@ def threaded_mcmc(ℓ, N, δ=0.8, initialization=None, warmup_stages=None, algor
 
     Returns (chains [nchains, N, D] Float64, tree_statistics [nchains, N] of TreeStatisticsNUTS records).
     `initialization` may carry q [nchains, D], κ (GaussianKineticEnergy with per-chain or shared diagonal) and ϵ.
+    Deviation from the reference: a given ϵ REPLACES the InitialStepsizeSearch stage (the reference, whose argument check
+    is commented out, would still run the search and overwrite the value, src/warmup.jl:188-200); julia/BNuts.jl does the same.
     """
     algorithm = algorithm or NUTS()
     initialization = initialization or {}

@@ -45,7 +45,12 @@ int32_t bnuts_create(const bnuts_config* cfg, bnuts_engine** out) {
     if (cfg->dtype == BNUTS_F64) { ae->e64 = new bn::EngineCore<double, BNUTS_EXEC>(); rc = ae->e64->init(*cfg); if (rc) g_create_error = ae->e64->err; }
     else { ae->e32 = new bn::EngineCore<float, BNUTS_EXEC>(); rc = ae->e32->init(*cfg); if (rc) g_create_error = ae->e32->err; }
   } catch (const std::exception& ex) { g_create_error = ex.what(); rc = BNUTS_ERR_INTERNAL; }
-  if (rc) { delete ae->e64; delete ae->e32; delete ae; return rc; }
+  if (rc) {   // release whatever init() had allocated before it failed (destroy() skips null pointers)
+    if (ae->e64) { ae->e64->destroy(); delete ae->e64; }
+    if (ae->e32) { ae->e32->destroy(); delete ae->e32; }
+    delete ae;
+    return rc;
+  }
   *out = reinterpret_cast<bnuts_engine*>(ae);
   return 0;
 }

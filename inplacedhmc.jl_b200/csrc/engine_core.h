@@ -122,7 +122,11 @@ template <class T, class X> struct EngineCore {
     M.cs = x.template alloc<ChainState<T>>(M.C);
     d_tmp_cd = x.template alloc<double>(size_t(M.C) * M.D * 4 + M.C);
     d_tmp_c = x.template alloc<double>(M.C);
-    if (!M.zs || !M.st_rho || !M.st_psf || !M.cs || !d_tmp_cd) return fail(BNUTS_ERR_CUDA, "device allocation failed");
+    {
+      const void* need[] = {M.zs, M.zlq, M.st_rho, M.st_psf, M.m_rho, M.m_psm, M.m_psp, M.ps_cur, M.Minv, M.W, M.cs, d_tmp_cd, d_tmp_c};
+      for (const void* p : need) if (!p) return fail(BNUTS_ERR_CUDA, "device allocation failed");
+      if (x.check(err)) return BNUTS_ERR_CUDA;
+    }
     x.zero(M.zs, CD * M.S * 3 * sizeof(T));
     x.zero(M.zlq, size_t(M.C) * M.S * sizeof(T));
     x.zero(M.cs, size_t(M.C) * sizeof(ChainState<T>));
@@ -399,7 +403,15 @@ template <class T, class X> struct EngineCore {
   }
 
   // ---------------------------------------------------------------- state setters
+  // ≙ GaussianKineticEnergy(M⁻¹): W = 1/sqrt(M⁻¹) (src/hamiltonian.jl:53-55) needs positive, finite entries
+  int32_t check_metric_values(const double* v, const char* what) {
+    const size_t n = size_t(M.C) * M.D;
+    for (size_t i = 0; i < n; ++i)
+      if (!(v[i] > 0.0) || !(v[i] < 1.7e308)) return fail(BNUTS_ERR_INVALID_ARGUMENT, std::string(what) + " must be positive and finite");
+    return 0;
+  }
   int32_t set_metric(const double* minv) {
+    if (minv) { const int32_t rc = check_metric_values(minv, "M^-1"); if (rc) return rc; }
     std::vector<T> hm(size_t(M.C) * M.Dp, T(1)), hw(size_t(M.C) * M.Dp, T(1));
     for (int c = 0; c < M.C; ++c)
       for (int d = 0; d < M.D; ++d) {
@@ -416,6 +428,7 @@ template <class T, class X> struct EngineCore {
   // a function of the stored M⁻¹: a checkpoint has to carry it (bnuts_get_metric_diag_w / bnuts_set_metric_diag_pair).
   int32_t set_metric_pair(const double* minv, const double* w) {
     if (!minv || !w) return fail(BNUTS_ERR_INVALID_ARGUMENT, "minv and w required");
+    { int32_t rc = check_metric_values(minv, "M^-1"); if (!rc) rc = check_metric_values(w, "W"); if (rc) return rc; }
     std::vector<T> hm(size_t(M.C) * M.Dp, T(1)), hw(size_t(M.C) * M.Dp, T(1));
     for (int c = 0; c < M.C; ++c)
       for (int d = 0; d < M.D; ++d) {
@@ -628,6 +641,8 @@ template <class T, class X> struct EngineCore {
       M.draws = x.template alloc<double>(nd);
       cap_draws = nd;
     }
+    // chains with a sticky non-zero status (bnuts_chain_status) write no rows: hand back zeros, never stale memory
+    if (want_draws) x.zero(M.draws, nd * sizeof(double));
     if (ns > cap_stats) {
       if (d_stats) { x.free(d_stats); x.free(d_sel); x.free(d_eps_hist); }
       d_stats = x.template alloc<TreeStats>(ns);
@@ -635,6 +650,7 @@ template <class T, class X> struct EngineCore {
       d_eps_hist = x.template alloc<double>(ns);
       cap_stats = ns;
     }
+    x.zero(d_stats, ns * sizeof(TreeStats)); x.zero(d_sel, ns * sizeof(int32_t)); x.zero(d_eps_hist, ns * sizeof(double));
   }
   void copy_out(int N, double* chain_out, int64_t sd, int64_t sc, bnuts_tree_stats* stats_out, int64_t ssc,
                 int32_t* sel, double* eps_out) {
@@ -668,6 +684,13 @@ template <class T, class X> struct EngineCore {
     // the invariants the reference records as (commented-out) @argcheck's, src/stepsize.jl:183-186
     if (da && !(da->delta > 0.0 && da->delta < 1.0 && da->gamma > 0.0 && da->kappa > 0.5 && da->kappa <= 1.0 && da->t0 >= 0))
       return fail(BNUTS_ERR_INVALID_ARGUMENT, "dual averaging needs 0 < delta < 1, gamma > 0, 0.5 < kappa <= 1, t0 >= 0");
+    // ≙ the (commented-out) @argcheck's of TuningNUTS, src/warmup.jl:230-231 (N ≥ 20, λ ≥ 0).  Enforced: the variance of
+    // src/hamiltonian.jl:153-162 needs two draws (N = 1 gives mulreg = inf, a NaN metric), and λ must be ≥ 0 or the
+    // default sentinel (any negative value used to be read as 5/N; only −1 is, now)
+    if (metric_kind == BNUTS_METRIC_DIAG && N < 2)
+      return fail(BNUTS_ERR_INVALID_ARGUMENT, "a metric-adapting stage needs N >= 2 (the reference records N >= 20)");
+    if (metric_kind == BNUTS_METRIC_DIAG && !(lambda >= 0.0 || lambda == -1.0))
+      return fail(BNUTS_ERR_INVALID_ARGUMENT, "lambda must be >= 0 (or -1 for the default 5/N)");
     const bool want_draws = chain_out != nullptr || metric_kind == BNUTS_METRIC_DIAG;
     ensure_out(N, want_draws);
     double* keep_draws = M.draws;
@@ -679,7 +702,7 @@ template <class T, class X> struct EngineCore {
     x.prepare(M, rp, a);
     int32_t rc = run(false);
     if (rc) { M.draws = keep_draws; return rc; }
-    if (metric_kind == BNUTS_METRIC_DIAG) x.metric_update(M, N, lambda < 0 ? 5.0 / N : lambda);  // ≙ src/warmup.jl:308-309
+    if (metric_kind == BNUTS_METRIC_DIAG) x.metric_update(M, N, lambda == -1.0 ? 5.0 / N : lambda);  // ≙ src/warmup.jl:308-309
     if (da) x.finish_da(M);                                                                     // ≙ final_ϵ, :313
     next_t += uint32_t(N);
     if (dm.on && chain_out) xf_device(M.draws, int64_t(M.C) * N, dm.dLt);   // draws back to user coordinates: q = L q̃

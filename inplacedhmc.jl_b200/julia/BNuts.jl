@@ -1,9 +1,10 @@
 # BNuts.jl — Julia host side of the B200 batched-chain NUTS engine.
 #
 # Thin `ccall` bindings over include/bnuts.h behind InplaceDHMC.jl's names
-# (export list src/InplaceDHMC.jl:3-11).  NOT EXECUTED IN THIS REPOSITORY'S CI:
+# (export list src/InplaceDHMC.jl:3-11).  UNTESTED — NOT EXECUTED ANYWHERE IN THIS REPOSITORY:
 # the build image has no Julia; the Python twin (../api.py) drives the same C ABI
-# and is what the tests exercise.  Every call below maps 1:1 to a tested C entry point.
+# and is what the tests exercise.  Every call below maps 1:1 to a tested C entry point;
+# tests/test_julia_binding_static.py checks this file's ccall signatures against include/bnuts.h.
 module BNuts
 
 export GaussianKineticEnergy, TuningNUTS, mcmc_with_warmup, threaded_mcmc, default_warmup_stages,
@@ -47,8 +48,15 @@ Base.@kwdef struct FindLocalOptimum; magnitude_penalty::Float64 = 1e-4; iteratio
 struct FixedStepsize end                                                                           # src/stepsize.jl:251-255
 struct TuningNUTS{M}                                                                               # src/warmup.jl:217-234
     N::Int; stepsize_adaptation::Union{DualAveraging,FixedStepsize}; λ::Float64
+    # inner constructor (an outer method of the same signature would call itself): λ defaults to 5/N, src/warmup.jl:228-229;
+    # the reference records N ≥ 20, λ ≥ 0 as commented-out @argcheck's (src/warmup.jl:230-231); enforced here and in the
+    # C ABI: λ ≥ 0, and N ≥ 2 when a metric is adapted (the variance needs two draws)
+    function TuningNUTS{M}(N::Integer, da::Union{DualAveraging,FixedStepsize}, λ::Real = 5.0 / N) where {M}
+        N ≥ (M === Nothing ? 1 : 2) || throw(ArgumentError("TuningNUTS needs N ≥ 2 to adapt a metric"))
+        λ ≥ 0 || throw(ArgumentError("TuningNUTS needs λ ≥ 0"))
+        new{M}(Int(N), da, Float64(λ))
+    end
 end
-TuningNUTS{M}(N::Integer, da::Union{DualAveraging,FixedStepsize}, λ = 5.0 / N) where {M} = TuningNUTS{M}(Int(N), da, Float64(λ))
 fixed_stepsize_warmup_stages(; local_optimization = FindLocalOptimum(), M = :Diagonal, middle_steps = 25, doubling_stages = 5) =
     (local_optimization, ntuple(d -> TuningNUTS{M}(middle_steps << (d - 1), FixedStepsize()), doubling_stages)...)   # src/warmup.jl:383-389
 Base.length(t::TuningNUTS) = t.N
@@ -132,6 +140,12 @@ function threaded_mcmc(ℓ, N; δ::Float64 = 0.8, initialization = (),
         end
         q = haskey(init, :q) ? init.q : nothing                      # D × nchains
         check(e, ccall((:bnuts_set_positions, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, q === nothing ? C_NULL : q))
+        if haskey(init, :ϵ)   # ≙ initialization = (ϵ = …,), src/warmup.jl:87-92,100: one value or one per chain
+            ϵs = init.ϵ isa Number ? fill(Float64(init.ϵ), nchains) : Vector{Float64}(init.ϵ)
+            check(e, ccall((:bnuts_set_stepsize, libbnuts), Int32, (Ptr{Cvoid}, Ptr{Float64}), e, ϵs))
+            # as api.py: a given ϵ replaces the search stage (the reference would run it and overwrite the value)
+            warmup_stages = filter(s -> !(s isa InitialStepsizeSearch), collect(warmup_stages))
+        end
         foreach(s -> warmup!(e, s), warmup_stages)
         chains = Array{Float64,3}(undef, D, N, nchains)
         stats = Matrix{TreeStatisticsNUTS}(undef, N, nchains)

@@ -1,18 +1,13 @@
 """Randomised differential test of the CUDA engine (deterministic gradient path) against the oracle: the GPU twin of
 tests/test_differential_random.py — shapes, targets, depth caps, step sizes, divergence thresholds, seeds, both dtypes;
-draws, statistics, selected indices, adapted step size and metric bit for bit.  Added after the round's GPU budget was
-spent: it has not run on a B200 yet, so it is skipped unless BNUTS_RUN_UNVALIDATED=1 (first thing to run next round)."""
+draws, statistics, selected indices, adapted step size and metric bit for bit.  First run on a B200 in round 2 (gpurun_out/r2a_gputests.log: 83 passed): enabled by default since."""
 import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st, HealthCheck
 
 from conftest import set_model
 
-import os
-
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("BNUTS_RUN_UNVALIDATED") != "1",
-                                 reason="written after the round's GPU budget was spent: set BNUTS_RUN_UNVALIDATED=1 to run; enable by default once it has passed on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 
 @settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
