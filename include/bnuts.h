@@ -165,10 +165,14 @@ int32_t bnuts_seed(bnuts_engine* e, uint64_t seed, uint32_t next_transition);
  * continued run is bit-identical to an uninterrupted one (checkpoint / resume; tests/test_checkpoint_resume.py). */
 int32_t bnuts_get_rng(bnuts_engine* e, uint64_t* seed, uint32_t* next_transition);
 
-/* ≙ sample_tree(...; p = …, directions = …) src/NUTS.jl:251-258: the next T
- * transitions of every chain use these directions and momenta instead of Philox.
- * dirs [T][C]; p [T][C][D] (either may be NULL to keep that stream random). */
-int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const double* p);
+/* ≙ sample_tree(rng, ...; p = …, directions = …) src/NUTS.jl:251-258 with a scripted rng: the next T transitions of
+ * every chain use these directions, momenta and merge exponentials instead of Philox — the three random streams of a
+ * transition.  dirs [T][C]; p [T][C][D]; exps [T][C][n_exps]: the k-th value of a row is the k-th randexp() the
+ * reference's rand_bool_logprob (src/NUTS.jl:32-34) would CONSUME in that transition, i.e. merges in the order the
+ * recursion performs them (post-order; the biased top-level merge of a doubling after its subtree), counting only
+ * merges with logprob2 < 0; consumption beyond n_exps falls back to the engine's own stream.  Any of the three may
+ * be NULL to keep that stream random. */
+int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const double* p, const double* exps, int32_t n_exps);
 
 /* ≙ stack leapfrog, src/kinetic_energy.jl:164-195: nsteps leapfrogs of signed
  * step eps[c] from the engine's current (q, ∇ℓ) with momentum p_in; engine state

@@ -108,7 +108,7 @@ def load_library(path=None):
     lib.bnuts_get_stepsize.argtypes = [_P, _P]
     lib.bnuts_seed.argtypes = [_P, C.c_uint64, C.c_uint32]
     lib.bnuts_get_rng.argtypes = [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
-    lib.bnuts_inject.argtypes = [_P, C.c_int32, _P, _P]
+    lib.bnuts_inject.argtypes = [_P, C.c_int32, _P, _P, _P, C.c_int32]
     lib.bnuts_leapfrog.argtypes = [_P, _P, _P, C.c_int32, _P, _P, _P, _P]
     lib.bnuts_find_local_optimum.argtypes = [_P, C.c_double, C.c_int32]
     lib.bnuts_find_initial_stepsize.argtypes = [_P, C.POINTER(StepsizeSearchParams)]
@@ -325,12 +325,19 @@ class Engine:
         self.seed(state["seed"], state["next_transition"])
         self.set_positions(state["q"])
 
-    def inject(self, T, dirs=None, p=None):
+    def inject(self, T, dirs=None, p=None, exps=None):
+        """≙ sample_tree(rng, ...; p, directions) with a scripted rng (src/NUTS.jl:251-258, :32-34): directions [T, C],
+        momenta [T, C, D], merge exponentials [T, C, n] in the order the reference would consume them."""
         if dirs is not None:
             dirs = np.ascontiguousarray(dirs, dtype=np.uint32)
             assert dirs.shape == (T, self.C)
         p = _f64(p, (T, self.C, self.D))
-        self._chk(self.lib.bnuts_inject(self.h, T, _ptr(dirs), _ptr(p)))
+        n_exps = 0
+        if exps is not None:
+            exps = np.ascontiguousarray(exps, dtype=np.float64)
+            assert exps.ndim == 3 and exps.shape[:2] == (T, self.C)
+            n_exps = exps.shape[2]
+        self._chk(self.lib.bnuts_inject(self.h, T, _ptr(dirs), _ptr(p), _ptr(exps), n_exps))
 
     def leapfrog(self, p, eps, nsteps=1):
         p = _f64(p, (self.C, self.D))

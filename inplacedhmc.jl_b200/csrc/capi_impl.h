@@ -123,7 +123,9 @@ int32_t bnuts_get_rng(bnuts_engine* e, uint64_t* seed, uint32_t* next_t) {
   else { *seed = ae->e32->rp.seed; *next_t = ae->e32->next_t; }
   return 0;
 }
-int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const double* p) { BN_DISPATCH(e, inject(T, dirs, p)); }
+int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const double* p, const double* exps, int32_t n_exps) {
+  BN_DISPATCH(e, inject(T, dirs, p, exps, n_exps));
+}
 int32_t bnuts_leapfrog(bnuts_engine* e, const double* p_in, const double* eps, int32_t nsteps, double* q_out,
                        double* p_out, double* g_out, double* l_out) {
   BN_DISPATCH(e, leapfrog(p_in, eps, nsteps, q_out, p_out, g_out, l_out));

@@ -85,7 +85,7 @@ template <class T, class X> struct EngineCore {
   // per-call device output buffers (grown on demand)
   size_t cap_draws = 0, cap_stats = 0;
   TreeStats* d_stats = nullptr; int32_t* d_sel = nullptr; double* d_eps_hist = nullptr;
-  uint32_t* d_inj_dirs = nullptr; double* d_inj_p = nullptr;
+  uint32_t* d_inj_dirs = nullptr; double* d_inj_p = nullptr; double* d_inj_exps = nullptr;
   double* d_tmp_cd = nullptr;   // [C][D] scratch (positions / momenta in)
   double* d_tmp_c = nullptr;    // [C]
   std::vector<double> h_draws;  // staging when caller strides are not compact
@@ -145,7 +145,7 @@ template <class T, class X> struct EngineCore {
     if (d_xf_in) { x.free(d_xf_in); x.free(d_xf_out); d_xf_in = d_xf_out = nullptr; }
     void* ptrs[] = {M.zs, M.zlq, M.st_rho, M.st_psf, M.m_rho, M.m_psm, M.m_psp, M.ps_cur, M.Minv, M.W, M.cs,
                     M.stage_q, M.stage_g, M.stage_l, M.stage_ld, M.stage_bh, M.stage_bm, M.stage_bl, M.stage_row, M.draws, d_stats, d_sel, d_eps_hist,
-                    d_inj_dirs, d_inj_p, d_tmp_cd, d_tmp_c, model.P, model.X, model.y, model.Xb, model.yf};
+                    d_inj_dirs, d_inj_p, d_inj_exps, d_tmp_cd, d_tmp_c, model.P, model.X, model.y, model.Xb, model.yf};
     for (void* p : ptrs) if (p) x.free(p);
     x.shutdown();
   }
@@ -739,10 +739,16 @@ template <class T, class X> struct EngineCore {
     if (l) x.d2h(l, o + 2 * n, size_t(M.C) * sizeof(double));
     return x.check(err);
   }
-  int32_t inject(int32_t Tn, const uint32_t* dirs, const double* p) {
+  int32_t inject(int32_t Tn, const uint32_t* dirs, const double* p, const double* exps, int32_t n_exps) {
     if (Tn < 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "T < 0");
+    if (exps && n_exps <= 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "exps given with n_exps <= 0");
     if (d_inj_dirs) { x.free(d_inj_dirs); d_inj_dirs = nullptr; }
     if (d_inj_p) { x.free(d_inj_p); d_inj_p = nullptr; }
+    if (d_inj_exps) { x.free(d_inj_exps); d_inj_exps = nullptr; }
+    if (exps && Tn > 0) {
+      d_inj_exps = x.template alloc<double>(size_t(Tn) * M.C * n_exps);
+      x.h2d(d_inj_exps, exps, size_t(Tn) * M.C * n_exps * sizeof(double));
+    }
     if (dirs && Tn > 0) {
       d_inj_dirs = x.template alloc<uint32_t>(size_t(Tn) * M.C);
       x.h2d(d_inj_dirs, dirs, size_t(Tn) * M.C * sizeof(uint32_t));
@@ -753,6 +759,7 @@ template <class T, class X> struct EngineCore {
       else x.h2d(d_inj_p, p, size_t(Tn) * M.C * M.D * sizeof(double));
     }
     rp.inj_T = Tn; rp.inj_start = next_t; rp.inj_dirs = d_inj_dirs; rp.inj_p = d_inj_p;
+    rp.inj_exps = d_inj_exps; rp.inj_nexp = d_inj_exps ? n_exps : 0;
     return x.check(err);
   }
   int32_t leapfrog(const double* p_in, const double* eps, int nsteps, double* q_out, double* p_out, double* g_out,

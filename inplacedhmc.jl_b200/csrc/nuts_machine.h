@@ -73,6 +73,7 @@ template <class T> struct ChainState {
   int32_t slot_minus, slot_plus, slot_zeta, i_zeta;
   T omega, pi_zeta, v_lsa;
   int32_t v_steps;
+  int32_t n_exp;       // merge exponentials consumed so far in this transition (index into the injected stream)
   // ---- running totals
   int64_t tot_leapfrogs, tot_transitions, tot_divergences;
   // ---- step size search (≙ locals of find_initial_stepsize, src/stepsize.jl:111-126)
@@ -108,6 +109,8 @@ template <class T> struct RunParams {
   uint32_t inj_start;
   const uint32_t* inj_dirs;  // [T][C] or null
   const double* inj_p;       // [T][C][D] or null
+  const double* inj_exps;    // [T][C][inj_nexp] or null: the k-th exponential CONSUMED by rand_bool_logprob (src/NUTS.jl:32-34)
+  int32_t inj_nexp;
   // outputs of the current call (device / host-emulation buffers), any may be null
   TreeStats* stats;          // [C][N]
   int32_t* sel;              // [C][N]
@@ -177,9 +180,18 @@ template <class T, class B> struct Machine {
   }
 
   // ≙ rand_bool_logprob, src/NUTS.jl:32-34
-  BN_HD bool select_second(T logprob2, uint32_t j, uint32_t k, uint32_t n) const {
+  // The reference consumes one randexp(rng) per call with logprob2 < 0, in call order (post-order over the merges of the
+  // recursion, which is the order this machine performs them in); an injected stream is consumed the same way, the
+  // engine's own draws are a pure function of the merge's position in the tree.
+  BN_HD bool select_second(T logprob2, uint32_t j, uint32_t k, uint32_t n) {
     if (logprob2 >= T(0)) return true;
-    const T e = std_exponential(rp.seed, gchain(), s.t, j, k, n, T(0));
+    T e;
+    const bool injected = rp.inj_exps && rp.inj_T > 0 && s.t >= rp.inj_start && s.t < rp.inj_start + (uint32_t)rp.inj_T;
+    if (injected && s.n_exp < rp.inj_nexp)
+      e = T(rp.inj_exps[((int64_t)(s.t - rp.inj_start) * rp.n_chains + c) * rp.inj_nexp + s.n_exp]);
+    else
+      e = std_exponential(rp.seed, gchain(), s.t, j, k, n, T(0));
+    s.n_exp += 1;
     return e > -logprob2;
   }
 
@@ -205,7 +217,7 @@ template <class T, class B> struct Machine {
     b.start_tx(s.slot_cur, ip, rp.seed, gchain(), s.t, &Ksum);
     s.pi0 = hamiltonian(b.get_lq(s.slot_cur), Ksum);
     s.slot_zeta = s.slot_cur; s.omega = T(0); s.pi_zeta = s.pi0; s.i_zeta = 0;
-    s.v_lsa = -lim<T>::inf(); s.v_steps = 0;
+    s.v_lsa = -lim<T>::inf(); s.v_steps = 0; s.n_exp = 0;
     s.slot_minus = s.slot_plus = s.slot_cur;
     s.i_minus = s.i_plus = 0;
     s.depth = 0;

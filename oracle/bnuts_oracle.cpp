@@ -159,6 +159,17 @@ struct DAState { double mu; int64_t m; double Hbar, logeps, logepsbar; };
 
 template <class T> struct ChainCtx;
 
+// Decision margins of one transition (test instrumentation, bnuts_oracle_trace): how far every data-dependent
+// decision of the tree was from its threshold, so a test can prove that a tolerance-parity engine (the tensor-core
+// gradient path) may only differ where a compared quantity sits within its error bound of the threshold.
+//   min_div    min over leaves of |Δ − min_Δ|                                  (divergence test, src/NUTS.jl:180)
+//   min_turn   min over merges of min(|ρ·p♯₋| / Σ|ρ_d p♯₋_d|, same for p♯₊)      (is_turning, src/NUTS.jl:148-170)
+//   min_sel    min over consuming merges of |e + logprob2|                      (rand_bool_logprob, src/NUTS.jl:32-34)
+//   scale_H    max over leaves of |ℓq| + |K|: the magnitude whose rounding bounds the error of every Δ and ω
+struct DecisionTrace { double min_div, min_turn, min_sel, scale_H; };
+thread_local DecisionTrace* g_trace = nullptr;
+inline void trace_min(double& slot, double v) { if (v < slot) slot = v; }
+
 template <class T> struct Engine {
   bnuts_config cfg{};
   int C = 0, D = 0;
@@ -182,6 +193,9 @@ template <class T> struct Engine {
   std::vector<uint32_t> inj_dirs;
   std::vector<double> inj_p;
   bool has_inj_dirs = false, has_inj_p = false;
+  std::vector<DecisionTrace> trace;   // [C] margins of each chain's LAST transition (empty: tracing off)
+  std::vector<double> inj_exps;   // [T][C][inj_nexp]: scripted randexp stream of rand_bool_logprob (src/NUTS.jl:32-34)
+  int inj_nexp = 0;
   bnuts_counter_block counters{};
   std::string err;
   std::vector<ChainCtx<T>> ctx;  // per OpenMP thread
@@ -293,6 +307,9 @@ template <class T> struct Trajectory {  // ≙ TrajectoryNUTS, src/NUTS.jl:5-16
   T pi0, eps, min_delta;
   uint64_t seed;
   uint32_t chain, t;  // RNG position
+  const double* exps = nullptr;  // scripted exponentials of this transition (bnuts_inject), or null
+  int n_exps = 0;
+  mutable int n_exp = 0;         // consumed so far
 };
 
 // ≙ leaf, src/NUTS.jl:176-191 (+ leaf_acceptance_statistic :76-78, leaf_turn_statistic :113-116)
@@ -302,6 +319,11 @@ void leaf(ChainCtx<T>& X, const Ham<T>& H, const Trajectory<T>& tr, const PhaseP
   const T Hz = is_initial ? tr.pi0 : logdensity(H, z);
   const T delta = is_initial ? T(0) : Hz - tr.pi0;
   *isdiv = delta < tr.min_delta;
+  if (g_trace) {
+    if (!is_initial) trace_min(g_trace->min_div, std::fabs(double(delta) - double(tr.min_delta)));
+    const double sc = std::fabs(double(z.lq)) + std::fabs(double(z.lq) - double(Hz));
+    if (sc > g_trace->scale_H && std::isfinite(sc)) g_trace->scale_H = sc;
+  }
   if (is_initial) { v->lsa = -bn::lim<T>::inf(); v->steps = 0; }
   else { v->lsa = (delta < T(0)) ? delta : T(0); v->steps = 1; }
   zeta->z = z; zeta->pi = Hz; zeta->idx = idx;
@@ -335,12 +357,22 @@ template <class T> bool is_turning(int D, const TurnStat<T>& tau) {
     pp[(d >> 2) & 31] = fma_(r, tau.psp[d], pp[(d >> 2) & 31]);
   }
   const T dm = butterfly(pm), dp = butterfly(pp);
+  if (g_trace) {
+    double am = 0.0, ap = 0.0;
+    for (int d = 0; d < D; ++d) { am += std::fabs(double(tau.rho[d]) * double(tau.psm[d])); ap += std::fabs(double(tau.rho[d]) * double(tau.psp[d])); }
+    trace_min(g_trace->min_turn, std::fabs(double(dm)) / (am > 0 ? am : 1.0));
+    trace_min(g_trace->min_turn, std::fabs(double(dp)) / (ap > 0 ? ap : 1.0));
+  }
   return (dm < T(0)) | (dp < T(0));
 }
 // ≙ rand_bool_logprob, src/NUTS.jl:32-34 — the draw is consumed only if logprob < 0
 template <class T> bool rand_bool_logprob(const Trajectory<T>& tr, T logprob, uint32_t j, uint32_t k, uint32_t n) {
   if (logprob >= T(0)) return true;
-  const T e = bn::std_exponential(tr.seed, tr.chain, tr.t, j, k, n, T(0));
+  T e;
+  if (tr.exps && tr.n_exp < tr.n_exps) e = T(tr.exps[tr.n_exp]);   // scripted stream: consumed in call order
+  else e = bn::std_exponential(tr.seed, tr.chain, tr.t, j, k, n, T(0));
+  tr.n_exp += 1;
+  if (g_trace) trace_min(g_trace->min_sel, std::fabs(double(e) + double(logprob)));
   return e > -logprob;
 }
 // ≙ combine_proposals_and_logweights, src/tree.jl:238-245 with
@@ -441,11 +473,14 @@ bnuts_tree_stats sample_tree(Engine<T>& E, ChainCtx<T>& X, int c, double eps, ui
     H.draw_momentum(z.p, E.seed, gchain, t);
   }
   Trajectory<T> tr{logdensity(H, z), T(eps), T(E.cfg.min_delta), E.seed, gchain, t};
+  if (injected && E.inj_nexp > 0) { tr.exps = E.inj_exps.data() + (it * E.C + c) * size_t(E.inj_nexp); tr.n_exps = E.inj_nexp; }
   Proposal<T> zeta;
   Visited<T> v;
   Invalid term;
   int32_t depth;
+  if (!E.trace.empty()) { E.trace[size_t(c)] = DecisionTrace{1e300, 1e300, 1e300, 0.0}; g_trace = &E.trace[size_t(c)]; }
   sample_trajectory(X, H, tr, z, E.cfg.max_depth, directions, &zeta, &v, &term, &depth);
+  g_trace = nullptr;
   bnuts_tree_stats st;
   st.pi = double(zeta.pi);
   const T a = exp_(v.lsa) / T(v.steps);  // ≙ acceptance_rate, src/NUTS.jl:84
@@ -840,12 +875,15 @@ template <class T> int32_t get_state(Engine<T>& E, double* q, double* g, double*
   if (l) for (int c = 0; c < E.C; ++c) l[c] = double(E.lq[c]);
   return 0;
 }
-template <class T> int32_t inject(Engine<T>& E, int32_t Tn, const uint32_t* dirs, const double* p) {
+template <class T> int32_t inject(Engine<T>& E, int32_t Tn, const uint32_t* dirs, const double* p, const double* exps, int32_t n_exps) {
   if (Tn < 0) return fail(E, BNUTS_ERR_INVALID_ARGUMENT, "T < 0");
+  if (exps && n_exps <= 0) return fail(E, BNUTS_ERR_INVALID_ARGUMENT, "exps given with n_exps <= 0");
   E.inj_T = Tn; E.inj_start = E.next_t;
   E.has_inj_dirs = dirs != nullptr; E.has_inj_p = p != nullptr;
   if (dirs) E.inj_dirs.assign(dirs, dirs + size_t(Tn) * E.C);
   if (p) E.inj_p.assign(p, p + size_t(Tn) * E.C * E.D);
+  E.inj_exps.clear(); E.inj_nexp = 0;
+  if (exps && Tn > 0) { E.inj_exps.assign(exps, exps + size_t(Tn) * E.C * size_t(n_exps)); E.inj_nexp = n_exps; }
   return 0;
 }
 
@@ -966,7 +1004,9 @@ int32_t bnuts_get_rng(bnuts_engine* e, uint64_t* seed, uint32_t* next_t) {
   if (!seed || !next_t) return BNUTS_ERR_INVALID_ARGUMENT;
   DISPATCH(e, ([&] { *seed = E.seed; *next_t = E.next_t; return 0; })(), ([&] { *seed = E.seed; *next_t = E.next_t; return 0; })());
 }
-int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const double* p) { DISPATCH(e, inject(E, T, dirs, p), inject(E, T, dirs, p)); }
+int32_t bnuts_inject(bnuts_engine* e, int32_t T, const uint32_t* dirs, const double* p, const double* exps, int32_t n_exps) {
+  DISPATCH(e, inject(E, T, dirs, p, exps, n_exps), inject(E, T, dirs, p, exps, n_exps));
+}
 int32_t bnuts_leapfrog(bnuts_engine* e, const double* p_in, const double* eps, int32_t nsteps, double* q_out,
                        double* p_out, double* g_out, double* l_out) {
   DISPATCH(e, bare_leapfrog(E, p_in, eps, nsteps, q_out, p_out, g_out, l_out),
@@ -1023,6 +1063,19 @@ double bnuts_oracle_normal(uint64_t seed, uint32_t chain, uint32_t t, uint32_t d
 float bnuts_oracle_normalf(uint64_t seed, uint32_t chain, uint32_t t, uint32_t d) { return bn::std_normal(seed, chain, t, d, 0.0f); }
 double bnuts_oracle_exponential(uint64_t seed, uint32_t chain, uint32_t t, uint32_t j, uint32_t k, uint32_t n) {
   return bn::std_exponential(seed, chain, t, j, k, n, 0.0);
+}
+// decision margins of every chain's last transition (see DecisionTrace); enable = 1 turns tracing on for later calls.
+// out [C][4] = (min_div, min_turn, min_sel, scale_H), may be NULL.
+int32_t bnuts_oracle_trace(bnuts_engine* e, int32_t enable, double* out) {
+  auto f = [&](auto& E) -> int32_t {
+    if (out)
+      for (size_t c = 0; c < E.trace.size(); ++c) {
+        out[4 * c] = E.trace[c].min_div; out[4 * c + 1] = E.trace[c].min_turn; out[4 * c + 2] = E.trace[c].min_sel; out[4 * c + 3] = E.trace[c].scale_H;
+      }
+    if (enable) E.trace.assign(size_t(E.C), DecisionTrace{1e300, 1e300, 1e300, 0.0}); else E.trace.clear();
+    return 0;
+  };
+  DISPATCH(e, f(E), f(E));
 }
 uint32_t bnuts_oracle_directions(uint64_t seed, uint32_t chain, uint32_t t) { return bn::draw_directions(seed, chain, t); }
 // ≙ adapt_stepsize table (src/stepsize.jl:220-229): state = {mu, m, Hbar, logeps, logepsbar}
