@@ -125,9 +125,7 @@ int32_t bnuts_synth_logistic_rows(uint64_t data_seed, int64_t row_offset, int64_
  * there exceeds sqrt(N·D)/2 the call fails with BNUTS_ERR_INVALID_ARGUMENT and the exact
  * three-term path stays in force.  beta_ref == NULL returns to the three-term path.
  * For tall problems (N >= 3.3e5 D over the whole row group) the residual is carried about the reference as well
- * (one bf16 term of sigma(−eta) − sigma(−eta_ref) instead of two of sigma(−eta); BNUTS_TC_RREF=0/1 overrides).
- * BNUTS_TC_QREF=1 (D <= 125, rows not sharded) selects the quadratic-remainder variant of that idea, accurate at any N;
- * it is opt-in because it measured no faster than the default. */
+ * (one bf16 term of sigma(−eta) − sigma(−eta_ref) instead of two of sigma(−eta); BNUTS_TC_RREF=0/1 overrides). */
 int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double* beta_ref);
 
 /* ≙ initialize_warmup_state(q = …), src/warmup.jl:100-129: sets q and evaluates

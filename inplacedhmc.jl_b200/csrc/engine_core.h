@@ -175,8 +175,6 @@ template <class T, class X> struct EngineCore {
   // All engines of the group must hold all chains (same seed, chain_offset, positions).
   int32_t enable_reduce(bnuts_allreduce_fn fn, void* ctx) {
     if (model.kind != MODEL_LOGISTIC) return fail(BNUTS_ERR_NO_MODEL, "row sharding needs the logistic model (set it first)");
-    if (x.reference_mode() == 2)
-      return fail(BNUTS_ERR_UNSUPPORTED, "set the reference point after enabling row sharding (its single-GPU mode is in force)");
     free_reduce();
     const size_t CD = size_t(M.C) * M.Dp;
     red_g = x.template alloc<T>(CD); red_l = x.template alloc<double>(M.C);

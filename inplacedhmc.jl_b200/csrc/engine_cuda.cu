@@ -832,7 +832,7 @@ struct CudaExec {
     return logistic_tc_set_reference(tc, eng, beta_ref, err);
   }
   int reference_mode() const { return tc.ready ? tc.rmode : 0; }
-  int launches_per_gradient() const { return reference_mode() == 2 ? 2 : 1; }   // k_lin_ref follows the tensor kernel
+  int launches_per_gradient() const { return 1; }
   template <class T> void metric_update(const EngineMem<T>& M, int N, double lambda) {
     k_metric<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, N, lambda);
   }

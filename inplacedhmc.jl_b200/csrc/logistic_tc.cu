@@ -34,12 +34,8 @@
 // Warp roles (608 threads): warp 0 TMA producer, warp 1 GEMM1 issuer + TMEM owner, warp 18 GEMM2 issuer,
 // warps 2-17 elementwise/epilogue: TMEM lane group = warp % 4 (hardware rule); two groups of eight warps
 // ping-pong over the row blocks, a warp owns two 32-row chunks of its group's blocks.
-// A second kernel in this file, k_logistic_tc64, keeps the position operand in TMEM and works on 64-row
-// blocks (BNUTS_TC_VARIANT=64): same results, measured slower, kept as a documented variant.
-// Further kernels here: k_logistic_tc256 (128 < D <= 256, config 5's shape), k_logistic_tcq + k_lin_ref (quadratic-
-// remainder residual on decoupled S / R buffers: validated, opt-in, no faster — DESIGN.md section 6 has the
-// measurements), the set-up kernels of the reference-point modes (k_write_reference / _eta0 / _c0 / _aux, g0 and H0
-// reductions in a fixed order).
+// A second kernel in this file, k_logistic_tc256, covers 128 < D <= 256 (config 5's shape); then the set-up kernels of the
+// reference-point modes (k_write_reference / _eta0 / _c0, g0 reduction in a fixed order).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -135,27 +131,14 @@ template <int DT> struct SmemPlan {
 // 512-byte bulk copy per X̃ stage) and forms δ = c_i − copysign(1/d − ½, η̃) in the FMA that produced r before:
 // no extra arithmetic, no hi/lo split, half the TMEM stores and half the GEMM2 MMAs.
 //
-// RR == 2 (quadratic remainder; opt-in with BNUTS_TC_QREF=1, D <= 125, rows not sharded): the first-order part of δ is
-// taken out as well.  With w_i ≈ σ'(η̃0_i) stored per row, ρ_i = δ_i + w_i (η̃_i − η̃0_i) = O((η̃ − η̃0)²) is what goes
-// through GEMM2 as one bf16 term, and
-//     ∇ℓ = g0 − H0 (β − β0) + X̃ᵀρ − τβ,    H0 = X̃ᵀ diag(w) X̃  (D x D, Float64 from the stored fp32 w, kept as fp32),
-// where g0 − H0 (β − β0) is a D x D mat-vec per chain done by k_lin_ref after this kernel (it adds into the partial
-// of split 0).  The rounded quantity is now second order: its error is 1.7e-3·√(D/N)·|X̃ᵀρ|, about 0.2·|η̃ − η̃0| times
-// the figure of the δ mode, i.e. < 1e-6·|∇ℓ| within tens of posterior standard deviations of the reference at
-// N/D = 1e4; and because k_lin_ref uses the exact fp32 β − β0 while the kernel's η̃ uses its two-term bf16 split, the
-// truncation error of that split (2⁻¹⁷·|H (β − β0)| in the other modes) cancels to first order.  Far from the
-// reference (|η̃ − η̃0| ≳ 2) H0 (β − β0) outgrows the saturating gradient and the cancellation costs accuracy
-// (measured in tests/test_gpu_parity.py); the reference check of the host keeps β0 at the mode.
-// The kernel needs two constants per row, w and a = c − w η̃0 (ρ = fma(w, η̃, a) − copysign(..): two FMAs, the same count
-// as forming r), stored pairwise as (w0, w1, a0, a1) so one broadcast 16-byte shared-memory load serves two rows:
-// 1 024 B per X̃ stage, in the third β tile, which is unused with two terms.  (A first version with three constants per
-// row and 8-byte loads was slower than the two-term kernel: 48 instead of 16 shared-memory instructions per 32-row chunk
-// and warp saturated the shared-memory pipe.)
+// (A quadratic-remainder variant of this idea — ρ = δ + w (η̃ − η̃0) through GEMM2, the linear part as a D x D mat-vec per
+// chain — and two pipeline variants, 64-row blocks with β in TMEM and decoupled S / R buffers, were built, validated and
+// measured in round 1: none was faster.  They were removed in round 2; DESIGN.md section 6 and profiles/r1_* keep the numbers.)
 template <int DT, int NK, int RR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBm, const __grid_constant__ CUtensorMap tmBl,
-              const float* __restrict__ c0, const float* __restrict__ aux, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total, int nsplit,
+              const float* __restrict__ c0, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total, int nsplit,
               int flush_every, int nterms) {
   using P = SmemPlan<DT>;
   constexpr int dk = NK * 16;
@@ -166,7 +149,6 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   unsigned char* sB = smem + P::OFF_B;
   unsigned char* sX = smem + P::OFF_X;
   float* sR = reinterpret_cast<float*>(smem + P::OFF_R);
-  float* sQ = reinterpret_cast<float*>(sB + 2 * P::B_BYTES);   // RR == 2: per-row constants (w, a) in the unused third β tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
   uint64_t* bar_b = bars;               // β tiles landed
   uint64_t* x_full = bars + 1;          // [NS]
@@ -208,11 +190,11 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0 && nb > 0) {
-      mbar_expect_tx(bar_b, (RR == 2 ? 2 : 3) * P::B_BYTES);
+      mbar_expect_tx(bar_b, 3 * P::B_BYTES);
       for (int kc = 0; kc < KC; ++kc) {
         tma_load_2d(&tmBh, sB + 0 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
         tma_load_2d(&tmBm, sB + 1 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
-        if (RR != 2) tma_load_2d(&tmBl, sB + 2 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
+        tma_load_2d(&tmBl, sB + 2 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
       }
       constexpr int PF = BNUTS_TC_PREFETCH;   // L2 prefetch distance in row blocks (0: none)
       for (int i = 0; i < PF && i < nb; ++i)
@@ -225,11 +207,10 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         TC_TRACE(0, i, 0);
         mbar_wait(&x_empty[st], ph ^ 1u);
         TC_TRACE(0, i, 1);
-        mbar_expect_tx(&x_full[st], P::X_BYTES + (RR == 1 ? ROWS * 4 : RR == 2 ? 2 * ROWS * 4 : 0));
+        mbar_expect_tx(&x_full[st], P::X_BYTES + (RR ? ROWS * 4 : 0));
         for (int kc = 0; kc < KC; ++kc)
           tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK_BYTES, &x_full[st], kc * 64, (b0 + i) * ROWS);
-        if (RR == 1) bulk_load_1d(sR + st * ROWS, c0 + (size_t)(b0 + i) * ROWS, ROWS * 4, &x_full[st]);
-        if (RR == 2) bulk_load_1d(sQ + st * 2 * ROWS, aux + (size_t)(b0 + i) * 2 * ROWS, 2 * ROWS * 4, &x_full[st]);
+        if (RR) bulk_load_1d(sR + st * ROWS, c0 + (size_t)(b0 + i) * ROWS, ROWS * 4, &x_full[st]);
       }
     }
   } else if (warp == 1) {
@@ -368,10 +349,15 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     };
     bool have_next = false;
     if (grp < nb && !(TCDBG & 1) && live) have_next = load_item(grp, 0, true);
+    // bsum / asum run over LFOLD of this warp's blocks before they are folded into the Float64 sum: a DADD (+ conversion)
+    // per block and thread was 5 % of all warp samples (ncu: the 16 elementwise warps hit the narrow FP64 pipe together).
+    // Eight blocks keep the fp32 partial sums below ~1e3, i.e. their rounding below 1e-4 per fold (ℓ itself is ~1e5..1e6).
+    constexpr int LFOLD = 8;
+    float bsum = 0.f;   // sum over this thread's elements of  log2(1 + 2^-|u|)
+    float asum = 0.f;   // sum of |eta|
+    int nfold = 0;
     for (int i = grp; i < nb; i += NG) {
       const int buf = i % NSB;
-      float bsum = 0.f;   // sum over this thread's elements of  log2(1 + 2^-|u|)
-      float asum = 0.f;   // sum of |eta|
       if (!live) mbar_wait(&s_full[buf], (uint32_t)(i / NSB) & 1u);   // stay in phase with the buffer, then just arrive
 #pragma unroll 1
       for (int cc = 0; cc < (((TCDBG & 1) || !live) ? 0 : CPW); ++cc) {
@@ -386,8 +372,6 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         float2 as2 = make_float2(0.f, 0.f);   // Σ|η̃| of the even / odd columns: one FADD2 with |.| operand modifiers per pair
         if (RR && cc == 0) mbar_wait(&x_full[i % NS], (uint32_t)(i / NS) & 1u);   // c of this block is visible (long complete)
         const float2* c2p = reinterpret_cast<const float2*>(sR + (i % NS) * ROWS + ch * 32);
-        // RR == 2: one 16-byte record per PAIR of rows, (w0, w1, a0, a1) with a = c − w η̃0: one broadcast LDS.128 per pair
-        const float4* q4p = reinterpret_cast<const float4*>(sQ + (i % NS) * 2 * ROWS + ch * 64);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           // eta = H~ (natural units); t = exp(-|eta|) in (0,1]; d = 1 + t in (1,2]
@@ -403,11 +387,6 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           if constexpr (RR == 1) {
             const float2 dl = __ffma2_rn(cs, MONE2, c2p[j]);   // δ = (½ − r0) − copysign(..) = r − r0, one rounding
             hi[j] = pack_bf16(dl.x, dl.y);
-          } else if constexpr (RR == 2) {
-            const float4 k4 = q4p[j];
-            const float2 lin = __ffma2_rn(make_float2(k4.x, k4.y), make_float2(e0, e1), make_float2(k4.z, k4.w));   // c + w (η̃ − η̃0)
-            const float2 rho = __ffma2_rn(cs, MONE2, lin);                                                           // ρ = δ + w Δη̃ = O(Δη̃²)
-            hi[j] = pack_bf16(rho.x, rho.y);
           } else {
             const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
             const uint32_t hh = pack_bf16(r2.x, r2.y);
@@ -433,7 +412,10 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       tc_fence_before();
       mbar_arrive(&r_full[buf]);
       if (warp == 2) TC_TRACE(2, i, 2);
-      lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);      // sum log sigma(eta) minus the linear part (added by the consumer)
+      if (++nfold == LFOLD) {   // sum log sigma(eta) minus the linear part (added by the consumer)
+        lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);
+        bsum = 0.f; asum = 0.f; nfold = 0;
+      }
       const bool closes = (i + 1 == nb) || (fpos == fe - 1);
       const int period = fper;
       fpos += NG;
@@ -457,8 +439,11 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                   float4 a = make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]), __uint_as_float(w[j + 2]),
                                          __uint_as_float(w[j + 3]));
                   float4* gp = reinterpret_cast<float4*>(gout + d);
-                  if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
-                  *gp = a;
+                  // later periods add into what the first one stored.  A reduction (no return value) instead of load + add +
+                  // store: the thread does not wait for the round trip to L2 (6 % of warp samples sat on that load); the adds of
+                  // one address come from this thread only, in program order, so the sum is the same bits as before
+                  if (period > 0) red_add_f32x4(gp, a);
+                  else *gp = a;
                 }
               }
             }
@@ -468,6 +453,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         mbar_arrive(g_empty);
       }
     }
+    lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);
     // rows >= N of the last block are zero padding: eta = 0, y = 0 -> each contributed -log 2
     if (h == 0 && nb > 0 && grp == ((nb - 1) % NG) && b1 == nblk_total)
       lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
@@ -491,319 +477,6 @@ k_logistic_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
 }
 
-// =====================================================================================================
-// k_logistic_tcq — the quadratic-remainder mode (RR == 2 above) on a DECOUPLED pipeline.
-//
-// Measured (ncu launch list, profiles/): halving the GEMM2 work in k_logistic_tc<.., 2> did not shorten that kernel at all —
-// its period is set by the loop S -> elementwise -> R -> GEMM2 -> buffer free -> GEMM1 over three in-place S/R buffers,
-// not by a pipe.  A single-term residual is 64 TMEM columns instead of 128, so here R gets buffers of its own:
-//     TMEM = G [0, 128) | S_0, S_1 [128, 384) | R_0, R_1 [384, 512)
-// and an S buffer goes back to GEMM1 as soon as the elementwise warps hold its values in registers (s_empty), not
-// after GEMM2.  The two elementwise groups own one (S, R) pair each (block i -> group i & 1), so a group's chain is
-//     GEMM1(i+2) runs while the group finishes block i;  GEMM2(i) runs while it starts block i+2.
-// Same arithmetic as k_logistic_tc<.., 2>, same split / flush / epilogue conventions, same outputs.
-__device__ __forceinline__ void mma_ts_run4c(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                             uint32_t acc_first) {
-  // four K steps of one 64-row half block, A compact in TMEM (8 columns per K step), B advances 2048 B = 128 units
-  asm volatile("{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 rb;\n\t.reg .b32 ta, bl;\n\t"
-               "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
-               "mov.b32 ta, %1;\n\tmov.b32 bl, %2;\n\t" BN_MMA_TS("pa")
-               "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 128;\n\t" BN_MMA_TS("pt")
-               "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 128;\n\t" BN_MMA_TS("pt")
-               "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 128;\n\t" BN_MMA_TS("pt") "}\n"
-               ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory");
-}
-template <int DT, int NK>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_logistic_tcq(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
-               const __grid_constant__ CUtensorMap tmBm, const float* __restrict__ aux, float* G, double* Ld, int nrows, int Dp,
-               long long N, int nblk_total, int nsplit, int flush_every) {
-  using P = SmemPlan<DT>;
-  constexpr int dk = NK * 16;
-  constexpr int NS = P::NS;
-  constexpr int KC = P::KC;
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* sB = smem + P::OFF_B;
-  unsigned char* sX = smem + P::OFF_X;
-  float* sQ = reinterpret_cast<float*>(sB + 2 * P::B_BYTES);   // per-row constants (w0, w1, a0, a1), NS x 1024 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
-  uint64_t* bar_b = bars;
-  uint64_t* x_full = bars + 1;          // [NS]
-  uint64_t* x_empty = x_full + NS;      // [NS]
-  uint64_t* s_full = x_empty + NS;      // [2] GEMM1 done
-  uint64_t* s_empty = s_full + 2;       // [2] S is in the registers of the group's warps
-  uint64_t* r_full = s_empty + 2;       // [2] residual written
-  uint64_t* r_empty = r_full + 2;       // [2] GEMM2 done with the residual
-  uint64_t* g_full = r_empty + 2;
-  uint64_t* g_empty = g_full + 1;
-  static_assert(1 + 2 * NS + 8 + 2 <= P::NBAR, "barrier slots");
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, split = blockIdx.y;
-  const int b0 = (int)(((long long)nblk_total * split) / nsplit);
-  const int b1 = (int)(((long long)nblk_total * (split + 1)) / nsplit);
-  const int nb = b1 - b0;
-  const int fe = flush_every > 0 ? flush_every : 0x7fffffff;
-
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) asm volatile("trap;");
-    mbar_init(bar_b, 1);
-    for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); mbar_init(&r_full[i], 256); mbar_init(&r_empty[i], 1); }
-    mbar_init(g_full, 1);
-    mbar_init(g_empty, 256);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_G = tmem;
-  const uint32_t tmem_S = tmem + 128u;     // 2 x 128 columns
-  const uint32_t tmem_R = tmem + 384u;     // 2 x 64 columns
-
-  if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0 && nb > 0) {
-      mbar_expect_tx(bar_b, 2 * P::B_BYTES);
-      for (int kc = 0; kc < KC; ++kc) {
-        tma_load_2d(&tmBh, sB + 0 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
-        tma_load_2d(&tmBm, sB + 1 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * CHAINS);
-      }
-      for (int i = 0; i < nb; ++i) {
-        const int st = i % NS;
-        const uint32_t ph = (uint32_t)(i / NS) & 1u;
-        mbar_wait(&x_empty[st], ph ^ 1u);
-        mbar_expect_tx(&x_full[st], P::X_BYTES + 2 * ROWS * 4);
-        for (int kc = 0; kc < KC; ++kc)
-          tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK_BYTES, &x_full[st], kc * 64, (b0 + i) * ROWS);
-        bulk_load_1d(sQ + st * 2 * ROWS, aux + (size_t)(b0 + i) * 2 * ROWS, 2 * ROWS * 4, &x_full[st]);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================== GEMM1 issuer: S_g = (β − β0 | 1) · X̃_iᵀ, two bf16 terms
-    if (nb > 0) {
-      constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
-      const uint32_t aX = smem_u32(sX);
-      const uint64_t dKM = desc_kmajor(0, 0);
-      const uint32_t km_hi = (uint32_t)(dKM >> 32), km_lo0 = (uint32_t)dKM;
-      uint32_t bB[2];
-#pragma unroll
-      for (int term = 0; term < 2; ++term) bB[term] = km_lo0 + ((smem_u32(sB) + (uint32_t)term * P::B_BYTES) >> 4);
-      mbar_wait(bar_b, 0);
-      for (int i = 0; i < nb; ++i) {
-        const int st = i % NS, g = i & 1, u = i >> 1;
-        mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
-        if (u >= 1) mbar_wait(&s_empty[g], (uint32_t)(u - 1) & 1u);
-        tc_fence_after();
-        const uint32_t xlo = km_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
-        const uint32_t d = tmem_S + (uint32_t)g * 128u;
-#pragma unroll
-        for (int term = 0; term < 2; ++term) {
-#pragma unroll
-          for (int c = 0; c < (NK + 3) / 4; ++c) {
-            constexpr int LAST = NK - ((NK + 3) / 4 - 1) * 4;
-            const uint32_t off = (uint32_t)(c * (CHUNK_BYTES >> 4));
-            const uint32_t acc = (term | c) ? 1u : 0u;
-            if (c + 1 < (NK + 3) / 4) mma_ss_run<4>(d, bB[term] + off, km_hi, xlo + off, km_hi, IDESC1, acc);
-            else mma_ss_run<LAST>(d, bB[term] + off, km_hi, xlo + off, km_hi, IDESC1, acc);
-          }
-        }
-        if (elect_one()) tc_commit(&s_full[g]);
-        __syncwarp();
-      }
-    }
-  } else if (warp == G2_WARP) {
-    // ===================================================== GEMM2 issuer: G += R_g (TMEM, compact) · X̃_i (smem, MN-major)
-    if (nb > 0) {
-      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
-      const uint32_t aX = smem_u32(sX);
-      const uint64_t dMN = desc_mnmajor(0, 0);
-      const uint32_t mn_hi = (uint32_t)(dMN >> 32), mn_lo0 = (uint32_t)dMN;
-      int period = 0, in_period = 0;
-      for (int i = 0; i < nb; ++i) {
-        const int st = i % NS, g = i & 1, u = i >> 1;
-        mbar_wait(&r_full[g], (uint32_t)u & 1u);
-        if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
-        tc_fence_after();
-        const uint32_t xm = mn_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
-        const uint32_t a = tmem_R + (uint32_t)g * 64u;
-        const uint32_t acc0 = in_period > 0 ? 1u : 0u;
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb)   // 64-row halves of the block
-          mma_ts_run4c(tmem_G, a + (uint32_t)(hb * 32), xm + (uint32_t)(hb * 4 * 128), mn_hi, IDESC2, hb ? 1u : acc0);
-        if (elect_one()) { tc_commit(&x_empty[st]); tc_commit(&r_empty[g]); }
-        ++in_period;
-        if (i + 1 == nb || in_period == fe) {
-          if (elect_one()) tc_commit(g_full);
-          ++period;
-          in_period = 0;
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ===================================================== elementwise + epilogue: two groups of eight warps, group = block parity
-    const int ew = warp - 2;
-    const int grp = ew >> 3;
-    const int h = (ew >> 2) & 1;             // column half of the group's blocks: chunks 2h, 2h + 1
-    const int q = warp & 3;                  // TMEM lane group (hardware rule)
-    const int row = tile * CHAINS + q * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    const bool live = (tile * CHAINS + q * 32) < nrows;
-    double lsum = 0.0;
-    const float2 L2E2 = make_float2(1.4426950408889634f, 1.4426950408889634f);
-    const float2 ONE2 = make_float2(1.0f, 1.0f), MHALF2 = make_float2(-0.5f, -0.5f), MONE2 = make_float2(-1.0f, -1.0f);
-    const float LN2 = 0.6931471805599453f;
-    float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
-    int fpos = grp, fper = 0;
-    while (fpos >= fe) { fpos -= fe; ++fper; }
-    const uint32_t tS = tmem_S + (uint32_t)grp * 128u + lane_sel;
-    const uint32_t tR = tmem_R + (uint32_t)grp * 64u + lane_sel;
-    uint32_t v[32];
-    // S chunk of (block i, chunk cc) -> registers; cc == 0 first waits for (blocking) or tests (non-blocking) GEMM1 of the block
-    auto load_item = [&](int i, int cc, bool blocking) -> bool {
-      if (cc == 0) {
-        const uint32_t par = (uint32_t)(i >> 1) & 1u;
-        if (!blocking) {
-          if (!mbar_test(&s_full[grp], par)) return false;
-        } else {
-          mbar_wait(&s_full[grp], par);
-        }
-        tc_fence_after();
-      }
-      tmem_ld32(tS + (uint32_t)(2 * h + cc) * 32u, v);
-      return true;
-    };
-    bool have_next = false;
-    if (grp < nb && live) have_next = load_item(grp, 0, true);
-    for (int i = grp; i < nb; i += 2) {
-      const int u = i >> 1, st = i % NS;
-      float bsum = 0.f, asum = 0.f;
-      if (!live) {
-        // no staged chains in this lane group: keep the barrier protocol going, no elementwise work
-        // (the r_empty wait keeps this thread's arrivals one phase apart: GEMM1(i + 2) no longer depends on r_full(i), so
-        // without it idle warps could arrive twice on r_full before a working warp has arrived once)
-        mbar_wait(&s_full[grp], (uint32_t)u & 1u);
-        mbar_arrive(&s_empty[grp]);
-        if (u >= 1) mbar_wait(&r_empty[grp], (uint32_t)(u - 1) & 1u);
-      } else {
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int ch = 2 * h + cc;
-          if (!have_next) have_next = load_item(i, cc, true);
-          tmem_ld_wait();
-          if (cc == 1) { tc_fence_before(); mbar_arrive(&s_empty[grp]); }   // S of this block is in registers: GEMM1(i + 2) may overwrite it
-          if (cc == 0) mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);     // the constants of this block are visible (long complete)
-          const float4* q4p = reinterpret_cast<const float4*>(sQ + st * 2 * ROWS + ch * 64);
-          uint32_t hi[16];
-          float2 prod = ONE2;
-          float2 as2 = make_float2(0.f, 0.f);   // Σ|η̃| of the even / odd columns: one FADD2 with |.| operand modifiers per pair
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e0 = __uint_as_float(v[2 * j]), e1 = __uint_as_float(v[2 * j + 1]);
-            const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
-            const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
-            prod = __fmul2_rn(prod, d2);
-            as2 = __fadd2_rn(as2, make_float2(fabsf(e0), fabsf(e1)));
-            const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
-            const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
-                                          __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
-            const float4 k4 = q4p[j];
-            const float2 lin = __ffma2_rn(make_float2(k4.x, k4.y), make_float2(e0, e1), make_float2(k4.z, k4.w));   // c + w (η̃ − η̃0)
-            const float2 rho = __ffma2_rn(cs, MONE2, lin);                                                           // ρ = δ + w Δη̃
-            hi[j] = pack_bf16(rho.x, rho.y);
-          }
-          bsum += lg2_approx(prod.x * prod.y);
-          asum += as2.x + as2.y;
-          // next S chunk -> registers (v is dead now): within the block always, the group's next block only if it is ready
-          have_next = false;
-          if (cc == 0) have_next = load_item(i, 1, true);
-          else if (i + 2 < nb) have_next = load_item(i + 2, 0, false);
-          if (cc == 0 && u >= 1) { mbar_wait(&r_empty[grp], (uint32_t)(u - 1) & 1u); tc_fence_after(); }   // GEMM2(i − 2) has read R
-          tmem_st16(tR + (uint32_t)ch * 16u, hi);
-        }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&r_full[grp]);
-      lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);
-      const bool closes = (i + 1 == nb) || (fpos == fe - 1);
-      const int period = fper;
-      fpos += 2;
-      while (fpos >= fe) { fpos -= fe; ++fper; }
-      if (closes) {
-        mbar_wait(g_full, (uint32_t)period & 1u);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int ch = 2 * h + cc;
-          if (ch * 32 < dk && live) {
-            uint32_t w[32];
-            tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, w);
-            tmem_ld_wait();
-            if (row < nrows) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const int d = ch * 32 + j;
-                if (d < dk && d < Dp) {
-                  float4 a = make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]), __uint_as_float(w[j + 2]),
-                                         __uint_as_float(w[j + 3]));
-                  float4* gp = reinterpret_cast<float4*>(gout + d);
-                  if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
-                  *gp = a;
-                }
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(g_empty);
-      }
-    }
-    // rows >= N of the last block are zero padding: eta = 0 -> each contributed -log 2
-    if (h == 0 && nb > 0 && grp == ((nb - 1) & 1) && b1 == nblk_total)
-      lsum += (double)((long long)nblk_total * ROWS - N) * 0.6931471805599453;
-    double* lp = reinterpret_cast<double*>(sX);   // X stages are dead by now
-    const int part = grp * 2 + h;
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    if (part > 0) lp[(part - 1) * 128 + q * 32 + lane] = lsum;
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    if (part == 0 && row < nrows) {
-      if (nb == 0) for (int d = 0; d < Dp; ++d) gout[d] = 0.f;
-      const int k = q * 32 + lane;
-      Ld[(size_t)split * nrows + row] = ((lsum + lp[k]) + lp[128 + k]) + lp[256 + k];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
-  }
-}
-template <int DT, int NK> void launch_q(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
-  using P = SmemPlan<DT>;
-  static unsigned long long attr_done = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!((attr_done >> (dev & 63)) & 1ull)) {
-    tc.last = cudaFuncSetAttribute(k_logistic_tcq<DT, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
-    attr_done |= 1ull << (dev & 63);
-  }
-  const int tiles = (nrows + CHAINS - 1) / CHAINS;
-  dim3 grid(tiles, nsplit);
-  CUtensorMap m[3];
-  for (int i = 0; i < 3; ++i) std::memcpy(&m[i], tc.tmaps[i], sizeof(CUtensorMap));
-  k_logistic_tcq<DT, NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], tc.aux, tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
-                                                            (int)(tc.Npad / ROWS), nsplit, tc.flush_every);
-}
-
 template <int DT, int NK, int RR> void launch_rr(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
   using P = SmemPlan<DT>;
   // the attribute is per device: one bit per device ordinal (engines on several GPUs may live in one process)
@@ -818,434 +491,28 @@ template <int DT, int NK, int RR> void launch_rr(LogisticTC& tc, cudaStream_t s,
   dim3 grid(tiles, nsplit);
   CUtensorMap m[4];
   for (int i = 0; i < 4; ++i) std::memcpy(&m[i], tc.tmaps[i], sizeof(CUtensorMap));
-  k_logistic_tc<DT, NK, RR><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.c0, tc.aux, tc.G, tc.Ld, nrows, tc.Dp,
+  k_logistic_tc<DT, NK, RR><<<grid, TC_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], m[3], tc.c0, tc.G, tc.Ld, nrows, tc.Dp,
                                                                (long long)tc.N, (int)(tc.Npad / ROWS), nsplit, tc.flush_every, tc.nterms);
 }
-// linear part of the quadratic-remainder mode: G[split 0][row][:] += g0 − H0 (q_row − β0).  A block of 8 warps takes
-// LR_ROWS staged rows: H0 (D x Dp floats, <= 64 KB) is copied to shared memory with all loads of a thread in flight at once
-// (it has usually been evicted from L2 by the X̃ stream of the tensor kernel: one HBM round trip, not one per row of
-// H0 — a first version that read H0 through L1 inside the k loop, behind warp shuffles, took 45 us), then a warp does
-// one row at a time: lane l owns coordinates 4l..4l+3, row k of the symmetric H0 is one conflict-free 16-byte
-// shared-memory load per lane and (q − β0)_k a broadcast load.
-constexpr int LR_ROWS = 32;
-__global__ void __launch_bounds__(256) k_lin_ref(float* __restrict__ G, const float* __restrict__ q, const float* __restrict__ beta_ref,
-                                                 const float* __restrict__ H0, const double* __restrict__ g0, int nrows, int D, int Dp) {
-  extern __shared__ __align__(16) float lr_smem[];
-  float* sH = lr_smem;                   // [D][Dp]
-  float* sD = lr_smem + (size_t)D * Dp;  // [8 warps][128]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
-    const int n4 = D * Dp / 4;
-    const float4* src = reinterpret_cast<const float4*>(H0);
-    float4 t[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) { const int idx = threadIdx.x + u * 256; if (idx < n4) t[u] = __ldg(src + idx); }
-#pragma unroll
-    for (int u = 0; u < 16; ++u) { const int idx = threadIdx.x + u * 256; if (idx < n4) reinterpret_cast<float4*>(sH)[idx] = t[u]; }
-  }
-  __syncthreads();
-  const int d0 = 4 * lane;
-  const bool own = d0 < Dp;
-  float* db = sD + warp * 128;
-  for (int r = warp; r < LR_ROWS; r += 8) {
-    const int row = blockIdx.x * LR_ROWS + r;
-    if (row >= nrows) break;
-    float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (own) {
-      const float4 qv = *reinterpret_cast<const float4*>(q + (size_t)row * Dp + d0);
-      const float4 bv = *reinterpret_cast<const float4*>(beta_ref + d0);
-      dv = make_float4(qv.x - bv.x, qv.y - bv.y, qv.z - bv.z, qv.w - bv.w);
-    }
-    __syncwarp();
-    *reinterpret_cast<float4*>(db + d0) = dv;
-    __syncwarp();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (own) {
-#pragma unroll 4
-      for (int k = 0; k < D; ++k) {
-        const float dk = db[k];
-        const float4 h = *reinterpret_cast<const float4*>(sH + (size_t)k * Dp + d0);
-        acc[0] = fmaf(h.x, dk, acc[0]); acc[1] = fmaf(h.y, dk, acc[1]); acc[2] = fmaf(h.z, dk, acc[2]); acc[3] = fmaf(h.w, dk, acc[3]);
-      }
-    }
-    if (d0 < D) {
-      float4* gp = reinterpret_cast<float4*>(G + (size_t)row * Dp + d0);
-      float4 g = *gp;
-      g.x += (float)(g0[d0] - (double)acc[0]); g.y += (float)(g0[d0 + 1] - (double)acc[1]);
-      g.z += (float)(g0[d0 + 2] - (double)acc[2]); g.w += (float)(g0[d0 + 3] - (double)acc[3]);
-      *gp = g;
-    }
-  }
-}
-void launch_lin_ref(LogisticTC& tc, cudaStream_t s, int nrows) {
-  const size_t smem = ((size_t)tc.D * tc.Dp + 8 * 128) * sizeof(float);
-  static unsigned long long attr_done = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!((attr_done >> (dev & 63)) & 1ull)) {
-    tc.last = cudaFuncSetAttribute(k_lin_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-    attr_done |= 1ull << (dev & 63);
-  }
-  k_lin_ref<<<(nrows + LR_ROWS - 1) / LR_ROWS, 256, smem, s>>>(tc.G, tc.q, tc.beta_ref, tc.H0, tc.grad0, nrows, tc.D, tc.Dp);
-}
 template <int DT, int NK> void launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
-  if (tc.rmode == 2) {
-    if (tc.qpipe) launch_q<DT, NK>(tc, s, nrows, nsplit);
-    else launch_rr<DT, NK, 2>(tc, s, nrows, nsplit);
-    launch_lin_ref(tc, s, nrows);
-  } else if (tc.rmode == 1) launch_rr<DT, NK, 1>(tc, s, nrows, nsplit);
+  if (tc.rmode == 1) launch_rr<DT, NK, 1>(tc, s, nrows, nsplit);
   else launch_rr<DT, NK, 0>(tc, s, nrows, nsplit);
 }
 
 
-// =====================================================================================================
-// Variant with 64-row blocks and the position operand resident in TMEM (k_logistic_tc64).
-//
-// Why: the loop S -> elementwise -> R -> GEMM2 -> buffer free -> GEMM1 is several thousand cycles long and the
-// 128-row kernel above has only three S/R buffers for it (TMEM and shared memory are full).  Here the chains'
-// β terms are loaded ONCE into TMEM (lane = chain, 8 columns per K step: the A-operand layout the residual
-// already uses) so GEMM1 takes A from TMEM: shared memory holds only X̃ stages (12 x 16 KB instead of 4 x 32 KB
-// + 96 KB of β tiles), an N = 64 MMA no longer re-reads a 4 KB A tile from shared memory (the SS form would be
-// shared-memory bound at N = 64), and the S/R buffers shrink to 64 columns: four of them (two-term mode) or
-// three (three-term mode) fit next to G and β.  Same arithmetic, same barriers, finer-grained pipeline.
-constexpr int ROWS2 = 64;
+constexpr int ROWS2 = 64;            // data rows per block of k_logistic_tc256
 constexpr int CHUNK2 = ROWS2 * 128;   // 64 rows x 64 bf16, one SW128 box
-template <int DT> struct SmemPlan2 {
-  static constexpr int KC = DT / 64;
-  static constexpr int X_BYTES = KC * CHUNK2;
-  static constexpr int NS = (DT == 128) ? 12 : 16;   // X stages
-  static constexpr int OFF_X = 0;
-  static constexpr int OFF_BAR = NS * X_BYTES;
-  static constexpr int NBAR = 1 + 2 * NS + 3 * 4 + 2;
-  static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
-};
-// GEMM1, A from TMEM: N4 consecutive K steps; A advances 8 TMEM columns, B 32 B (2 descriptor units)
-#define BN_MMA_TSK(ACC) "mov.b64 rb, {bl, %3};\n\t@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], rb, %4, " ACC ";\n\t"
-#define BN_TSK_HEAD "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 rb;\n\t.reg .b32 ta, bl;\n\t" \
-                    "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\tmov.b32 ta, %1;\n\tmov.b32 bl, %2;\n\t"
-#define BN_TSK_STEP "add.u32 ta, ta, 8;\n\tadd.u32 bl, bl, 2;\n\t"
-#define BN_TSK_ARGS ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory"
-template <int N4>
-__device__ __forceinline__ void mma_tsk_run(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                            uint32_t acc_first) {
-  static_assert(N4 >= 1 && N4 <= 4, "1..4 K steps per chunk");
-  if constexpr (N4 == 1)
-    asm volatile(BN_TSK_HEAD BN_MMA_TSK("pa") "}\n" BN_TSK_ARGS);
-  else if constexpr (N4 == 2)
-    asm volatile(BN_TSK_HEAD BN_MMA_TSK("pa") BN_TSK_STEP BN_MMA_TSK("pt") "}\n" BN_TSK_ARGS);
-  else if constexpr (N4 == 3)
-    asm volatile(BN_TSK_HEAD BN_MMA_TSK("pa") BN_TSK_STEP BN_MMA_TSK("pt") BN_TSK_STEP BN_MMA_TSK("pt") "}\n" BN_TSK_ARGS);
-  else
-    asm volatile(BN_TSK_HEAD BN_MMA_TSK("pa") BN_TSK_STEP BN_MMA_TSK("pt") BN_TSK_STEP BN_MMA_TSK("pt") BN_TSK_STEP BN_MMA_TSK("pt") "}\n"
-                 BN_TSK_ARGS);
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
 
-template <int DT, int NK>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_logistic_tc64(const __grid_constant__ CUtensorMap tmX, const uint16_t* __restrict__ bh, const uint16_t* __restrict__ bm,
-                const uint16_t* __restrict__ bl, int Dt, float* G, double* Ld, int nrows, int Dp, long long N, int nblk_total,
-                int nsplit, int flush_every, int nterms) {
-  using P = SmemPlan2<DT>;
-  constexpr int dk = NK * 16;
-  constexpr int NS = P::NS;
-  constexpr int KC = P::KC;
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* sX = smem + P::OFF_X;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
-  uint64_t* bar_b = bars;               // β terms written to TMEM
-  uint64_t* x_full = bars + 1;          // [NS]
-  uint64_t* x_empty = x_full + NS;      // [NS]
-  uint64_t* s_full = x_empty + NS;      // [4] GEMM1 done
-  uint64_t* r_full = s_full + 4;        // [4] residual written to TMEM
-  uint64_t* sr_empty = r_full + 4;      // [4] GEMM2 done with the buffer
-  uint64_t* g_full = sr_empty + 4;
-  uint64_t* g_empty = g_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P::NBAR);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, split = blockIdx.y;
-  const int b0 = (int)(((long long)nblk_total * split) / nsplit);
-  const int b1 = (int)(((long long)nblk_total * (split + 1)) / nsplit);
-  const int nb = b1 - b0;
-  const int fe = flush_every > 0 ? 2 * flush_every : 0x7fffffff;   // flush period in 64-row blocks
-  // TMEM map (columns): G [0, dk) | β term t [128 + t dk/2, ...) | S/R buffer b [SB0 + 64 b, ...)
-  const int SB0 = (128 + nterms * (dk / 2) + 63) & ~63;
-  const int nsb = (512 - SB0) / 64 >= 4 ? 4 : 3;
-
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) asm volatile("trap;");
-    mbar_init(bar_b, 128);
-    for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&r_full[i], 256); mbar_init(&sr_empty[i], 1); }
-    mbar_init(g_full, 1);
-    mbar_init(g_empty, 256);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_G = tmem;
-  const uint32_t tmem_B = tmem + 128u;
-  const uint32_t tmem_S = tmem + (uint32_t)SB0;
-  // buffer and phase of block i without runtime divisions (nsb is 3 or 4)
-  auto buf_of = [&](int i) { return nsb == 4 ? (i & 3) : (i % 3); };
-  auto round_of = [&](int i) { return nsb == 4 ? (i >> 2) : (i / 3); };
-
-  if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0 && nb > 0) {
-      constexpr int PF = 16;   // L2 prefetch distance in row blocks
-      for (int i = 0; i < PF && i < nb; ++i)
-        for (int kc = 0; kc < KC; ++kc) tma_prefetch_2d(&tmX, kc * 64, (b0 + i) * ROWS2);
-      for (int i = 0; i < nb; ++i) {
-        const int st = i % NS;
-        const uint32_t ph = (uint32_t)(i / NS) & 1u;
-        if (i + PF < nb)
-          for (int kc = 0; kc < KC; ++kc) tma_prefetch_2d(&tmX, kc * 64, (b0 + i + PF) * ROWS2);
-        mbar_wait(&x_empty[st], ph ^ 1u);
-        mbar_expect_tx(&x_full[st], P::X_BYTES);
-        for (int kc = 0; kc < KC; ++kc)
-          tma_load_2d(&tmX, sX + st * P::X_BYTES + kc * CHUNK2, &x_full[st], kc * 64, (b0 + i) * ROWS2);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================== GEMM1 issuer: S[buf] = β (TMEM) · X̃_iᵀ (smem, K-major)
-    if (nb > 0) {
-      constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ROWS2 >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
-      const uint32_t aX = smem_u32(sX);
-      const uint64_t dKM = desc_kmajor(0, 0);
-      const uint32_t km_hi = (uint32_t)(dKM >> 32), km_lo0 = (uint32_t)dKM;
-      mbar_wait(bar_b, 0);
-      for (int i = 0; i < nb; ++i) {
-        const int st = i % NS, buf = buf_of(i), rnd = round_of(i);
-        mbar_wait(&x_full[st], (uint32_t)(i / NS) & 1u);
-        if (rnd >= 1) mbar_wait(&sr_empty[buf], (uint32_t)(rnd - 1) & 1u);
-        tc_fence_after();
-        const uint32_t xlo = km_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
-        const uint32_t d = tmem_S + (uint32_t)buf * 64u;
-#pragma unroll
-        for (int term = 0; term < 3; ++term)
-          if (term < nterms) {
-#pragma unroll
-            for (int c = 0; c < (NK + 3) / 4; ++c) {
-              constexpr int LAST = NK - ((NK + 3) / 4 - 1) * 4;
-              const uint32_t a = tmem_B + (uint32_t)(term * (dk / 2) + c * 32);
-              const uint32_t b = xlo + (uint32_t)(c * (CHUNK2 >> 4));
-              const uint32_t acc = (term | c) ? 1u : 0u;
-              if (c + 1 < (NK + 3) / 4) mma_tsk_run<4>(d, a, b, km_hi, IDESC1, acc);
-              else mma_tsk_run<LAST>(d, a, b, km_hi, IDESC1, acc);
-            }
-          }
-        if (elect_one()) tc_commit(&s_full[buf]);
-        __syncwarp();
-      }
-    }
-  } else if (warp == G2_WARP) {
-    // ===================================================== GEMM2 issuer: G += R (TMEM) · X̃_i (smem, MN-major)
-    if (nb > 0) {
-      constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(dk >> 3) << 17) | ((uint32_t)(CHAINS >> 4) << 24);
-      const uint32_t aX = smem_u32(sX);
-      const uint64_t dMN = make_desc(0, (uint32_t)CHUNK2, 1024u);   // 64-column chunks are CHUNK2 apart
-      const uint32_t mn_hi = (uint32_t)(dMN >> 32), mn_lo0 = (uint32_t)dMN;
-      int period = 0, in_period = 0;
-      for (int i = 0; i < nb; ++i) {
-        const int st = i % NS, buf = buf_of(i), rnd = round_of(i);
-        mbar_wait(&r_full[buf], (uint32_t)rnd & 1u);
-        if (in_period == 0 && period >= 1) mbar_wait(g_empty, (uint32_t)(period - 1) & 1u);
-        tc_fence_after();
-        const uint32_t xm = mn_lo0 + ((aX + (uint32_t)st * P::X_BYTES) >> 4);
-        const uint32_t a = tmem_S + (uint32_t)buf * 64u;
-        const uint32_t acc0 = in_period > 0 ? 1u : 0u;
-#pragma unroll
-        for (int term = 0; term < 2; ++term)
-          mma_ts_run4(tmem_G, a + (uint32_t)(term * 16), xm, mn_hi, IDESC2, term ? 1u : acc0);
-        if (elect_one()) { tc_commit(&x_empty[st]); tc_commit(&sr_empty[buf]); }
-        ++in_period;
-        if (i + 1 == nb || in_period == fe) {
-          if (elect_one()) tc_commit(g_full);
-          ++period;
-          in_period = 0;
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ===================================================== elementwise + epilogue (16 warps, two groups of 8)
-    const int ew = warp - 2;
-    const int grp = ew >> 3;
-    const int h = (ew >> 2) & 1;                      // 32-column half of the 64-row block
-    const int q = warp & 3;
-    const int row = tile * CHAINS + q * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    const bool live = (tile * CHAINS + q * 32) < nrows;
-    // ---- position operand -> TMEM, once: lane = chain, word w of term t = bf16 pair (k = 2w, 2w + 1)
-    if (ew < 4) {
-      const uint16_t* src[3] = {bh, bm, bl};
-      for (int t = 0; t < nterms; ++t) {
-        const uint4* p = reinterpret_cast<const uint4*>(src[t] + (size_t)row * Dt);
-#pragma unroll 1
-        for (int w8 = 0; w8 < dk / 16; ++w8) {       // 8 words = 16 bf16 = one K step per iteration
-          uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-          if (row < nrows) { a = p[2 * w8]; b = p[2 * w8 + 1]; }
-          const uint32_t r8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          tmem_st8(tmem_B + lane_sel + (uint32_t)(t * (dk / 2) + w8 * 8), r8);
-        }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(bar_b);
-    }
-    double lsum = 0.0;
-    const float2 L2E2 = make_float2(1.4426950408889634f, 1.4426950408889634f);
-    const float2 ONE2 = make_float2(1.0f, 1.0f), MHALF2 = make_float2(-0.5f, -0.5f), HALF2 = make_float2(0.5f, 0.5f);
-    const float2 MONE2 = make_float2(-1.0f, -1.0f);
-    const float LN2 = 0.6931471805599453f;
-    float* gout = G + ((size_t)split * nrows + (size_t)row) * Dp;
-    int fpos = grp, fper = 0;
-    while (fpos >= fe) { fpos -= fe; ++fper; }
-    uint32_t v[32];
-    auto load_item = [&](int i, bool blocking) -> bool {
-      const int buf = buf_of(i), rnd = round_of(i);
-      if (!blocking) {
-        if (!mbar_test(&s_full[buf], (uint32_t)rnd & 1u)) return false;
-      } else {
-        mbar_wait(&s_full[buf], (uint32_t)rnd & 1u);
-      }
-      tc_fence_after();
-      tmem_ld32(tmem_S + (uint32_t)buf * 64u + lane_sel + (uint32_t)h * 32u, v);
-      return true;
-    };
-    bool have_next = false;
-    if (grp < nb && live) have_next = load_item(grp, true);
-    for (int i = grp; i < nb; i += 2) {
-      const int buf = buf_of(i);
-      float bsum = 0.f, asum = 0.f;
-      if (!live) {
-        mbar_wait(&s_full[buf], (uint32_t)round_of(i) & 1u);
-      } else {
-        if (!have_next) have_next = load_item(i, true);
-        const uint32_t tS = tmem_S + (uint32_t)buf * 64u + lane_sel + (uint32_t)h * 32u;
-        tmem_ld_wait();
-        uint32_t hi[16], lo[16];
-        float2 prod = ONE2;
-        float2 as2 = make_float2(0.f, 0.f);   // Σ|η̃| of the even / odd columns: one FADD2 with |.| operand modifiers per pair
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float e0 = __uint_as_float(v[2 * j]), e1 = __uint_as_float(v[2 * j + 1]);
-          const float2 u2 = __fmul2_rn(make_float2(e0, e1), L2E2);
-          const float2 d2 = __fadd2_rn(make_float2(ex2_approx(-fabsf(u2.x)), ex2_approx(-fabsf(u2.y))), ONE2);
-          prod = __fmul2_rn(prod, d2);
-          as2 = __fadd2_rn(as2, make_float2(fabsf(e0), fabsf(e1)));
-          const float2 hm = __fadd2_rn(rcp2(d2, ((RCPSW >> (j & 7)) & 1) != 0), MHALF2);
-          const float2 cs = make_float2(__uint_as_float(__float_as_uint(hm.x) | (v[2 * j] & 0x80000000u)),
-                                        __uint_as_float(__float_as_uint(hm.y) | (v[2 * j + 1] & 0x80000000u)));
-          const float2 r2 = __ffma2_rn(cs, MONE2, HALF2);
-          const uint32_t hh = pack_bf16(r2.x, r2.y);
-          const float2 hv = make_float2(__uint_as_float(hh << 16), __uint_as_float(hh & 0xffff0000u));
-          const float2 l2 = __ffma2_rn(hv, MONE2, r2);
-          hi[j] = hh;
-          lo[j] = pack_bf16(l2.x, l2.y);
-        }
-        bsum = lg2_approx(prod.x * prod.y);
-        asum = as2.x + as2.y;
-        have_next = false;
-        if (i + 2 < nb) have_next = load_item(i + 2, false);
-        tmem_st16(tS, hi);
-        tmem_st16(tS + 16u, lo);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&r_full[buf]);
-      lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);
-      const bool closes = (i + 1 == nb) || (fpos == fe - 1);
-      const int period = fper;
-      fpos += 2;
-      while (fpos >= fe) { fpos -= fe; ++fper; }
-      if (closes) {
-        mbar_wait(g_full, (uint32_t)period & 1u);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int ch = 2 * h + cc;
-          if (ch * 32 < dk && live) {
-            uint32_t w[32];
-            tmem_ld32(tmem_G + lane_sel + (uint32_t)ch * 32u, w);
-            tmem_ld_wait();
-            if (row < nrows) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const int d = ch * 32 + j;
-                if (d < dk && d < Dp) {
-                  float4 a = make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]), __uint_as_float(w[j + 2]),
-                                         __uint_as_float(w[j + 3]));
-                  float4* gp = reinterpret_cast<float4*>(gout + d);
-                  if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
-                  *gp = a;
-                }
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(g_empty);
-      }
-    }
-    // rows >= N of the last block are zero padding: eta = 0 -> each contributed -log 2 (once per row: column half 0)
-    if (h == 0 && nb > 0 && grp == ((nb - 1) & 1) && b1 == nblk_total)
-      lsum += (double)((long long)nblk_total * ROWS2 - N) * 0.6931471805599453;
-    double* lp = reinterpret_cast<double*>(sX);   // X stages are dead by now
-    const int part = grp * 2 + h;
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    if (part > 0) lp[(part - 1) * 128 + q * 32 + lane] = lsum;
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    if (part == 0 && row < nrows) {
-      if (nb == 0) for (int d = 0; d < Dp; ++d) gout[d] = 0.f;
-      const int k = q * 32 + lane;
-      Ld[(size_t)split * nrows + row] = ((lsum + lp[k]) + lp[128 + k]) + lp[256 + k];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
-  }
-}
-
-template <int DT, int NK> void launch64(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit) {
-  using P = SmemPlan2<DT>;
-  // the attribute is per device: one bit per device ordinal (engines on several GPUs may live in one process)
-  static unsigned long long attr_done = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!((attr_done >> (dev & 63)) & 1ull)) {
-    tc.last = cudaFuncSetAttribute(k_logistic_tc64<DT, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
-    attr_done |= 1ull << (dev & 63);
-  }
-  const int tiles = (nrows + CHAINS - 1) / CHAINS;
-  dim3 grid(tiles, nsplit);
-  CUtensorMap m;
-  std::memcpy(&m, tc.tmaps[4], sizeof(CUtensorMap));
-  k_logistic_tc64<DT, NK><<<grid, TC_THREADS, P::TOTAL, s>>>(m, tc.bh, tc.bm, tc.bl, tc.Dt, tc.G, tc.Ld, nrows, tc.Dp, (long long)tc.N,
-                                                            (int)(tc.Npad / ROWS2), nsplit, tc.flush_every, tc.nterms);
-}
-
-
 // =====================================================================================================
 // Variant for 128 < D <= 256 (k_logistic_tc256; BASELINE config 5 has D = 256).
 //
 // With exact operand splits a D = 256 problem does not fit the layouts above: three β tiles would be 192 KB and
-// G (256 columns) leaves no room for 128-column S/R buffers.  Here: 64-row blocks (as k_logistic_tc64), K = dk
+// G (256 columns) leaves no room for 128-column S/R buffers.  Here: 64-row blocks, K = dk
 // exactly (no spare K columns), TWO-TERM mode only — the position operand is always β − β₀ split in two bf16
 // terms, and η̃₀ = X̃β₀ is added in the elementwise stage from a per-row fp32 vector that travels with each X̃
 // stage.  Without a reference point β₀ = 0 and the operand is a 16-bit β (relative gradient error ~1e-5..1e-4:
@@ -1427,9 +694,11 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     };
     bool have_next = false;
     if (grp < nb && live) have_next = load_item(grp, true);
+    constexpr int LFOLD = 8;    // blocks per fold of the fp32 partial sums into Float64 (see k_logistic_tc)
+    float bsum = 0.f, asum = 0.f;
+    int nfold = 0;
     for (int i = grp; i < nb; i += 2) {
       const int buf = i & 3, st = i % NS;
-      float bsum = 0.f, asum = 0.f;
       if (!live) {
         mbar_wait(&s_full[buf], (uint32_t)(i >> 2) & 1u);
       } else {
@@ -1480,7 +749,7 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&r_full[buf]);
-      lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);
+      if (++nfold == LFOLD) { lsum += (double)fmaf(-LN2, bsum, -0.5f * asum); bsum = 0.f; asum = 0.f; nfold = 0; }
       const bool closes = (i + 1 == nb) || (fpos == fe - 1);
       const int period = fper;
       fpos += 2;
@@ -1503,8 +772,11 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                   float4 a = make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]), __uint_as_float(w[j + 2]),
                                          __uint_as_float(w[j + 3]));
                   float4* gp = reinterpret_cast<float4*>(gout + d);
-                  if (period > 0) { const float4 o = *gp; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
-                  *gp = a;
+                  // later periods add into what the first one stored.  A reduction (no return value) instead of load + add +
+                  // store: the thread does not wait for the round trip to L2 (6 % of warp samples sat on that load); the adds of
+                  // one address come from this thread only, in program order, so the sum is the same bits as before
+                  if (period > 0) red_add_f32x4(gp, a);
+                  else *gp = a;
                 }
               }
             }
@@ -1515,6 +787,7 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
     }
     // rows >= N of the last block are zero padding (X̃ = 0, eta0 = 0): each contributed -log 2
+    lsum += (double)fmaf(-LN2, bsum, -0.5f * asum);
     if (h == 0 && nb > 0 && grp == ((nb - 1) & 1) && b1 == nblk_total)
       lsum += (double)((long long)nblk_total * ROWS2 - N) * 0.6931471805599453;
     double* lp = reinterpret_cast<double*>(sX);   // X stages are dead by now
@@ -1594,19 +867,6 @@ void LogisticTC::run(cudaStream_t s, int nrows) {
     }
     return;
   }
-  if (variant == 64) {
-    switch (dk / 16) {
-      case 1: launch64<64, 1>(*this, s, nrows, last_nsplit); break;
-      case 2: launch64<64, 2>(*this, s, nrows, last_nsplit); break;
-      case 3: launch64<64, 3>(*this, s, nrows, last_nsplit); break;
-      case 4: launch64<64, 4>(*this, s, nrows, last_nsplit); break;
-      case 5: launch64<128, 5>(*this, s, nrows, last_nsplit); break;
-      case 6: launch64<128, 6>(*this, s, nrows, last_nsplit); break;
-      case 7: launch64<128, 7>(*this, s, nrows, last_nsplit); break;
-      default: launch64<128, 8>(*this, s, nrows, last_nsplit); break;
-    }
-    return;
-  }
   switch (dk / 16) {
     case 1: launch<64, 1>(*this, s, nrows, last_nsplit); break;
     case 2: launch<64, 2>(*this, s, nrows, last_nsplit); break;
@@ -1631,12 +891,7 @@ void LogisticTC::destroy() {
   if (c0) cudaFree(c0);
   if (grad0) cudaFree(grad0);
   if (grad0_part) cudaFree(grad0_part);
-  if (aux) cudaFree(aux);
-  if (cw) cudaFree(cw);
-  if (H0) cudaFree(H0);
-  if (H0_part) cudaFree(H0_part);
   Xb = nullptr; colsum = nullptr; beta_ref = nullptr; eta0 = nullptr; c0 = nullptr; grad0 = nullptr; grad0_part = nullptr;
-  aux = nullptr; cw = nullptr; H0 = nullptr; H0_part = nullptr;
   ready = false; nterms = 3; rmode = 0; variant = 128;
 }
 
@@ -1707,17 +962,6 @@ __global__ void k_grad0_partial(const uint16_t* __restrict__ Xb, const float* __
     part[(size_t)blockIdx.x * Dp + d] = acc;
   }
 }
-// the same with c read from the interleaved records of the quadratic-remainder mode
-__global__ void k_grad0_partial_aux(const uint16_t* __restrict__ Xb, const float* __restrict__ cw, double* part, long long N, int D,
-                                    int Dt, int Dp) {
-  const long long r0 = N * blockIdx.x / gridDim.x, r1 = N * (blockIdx.x + 1) / gridDim.x;
-  for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
-    double acc = 0.0;
-    if (d < D)
-      for (long long i = r0; i < r1; ++i) acc = fma((double)bf16_val(Xb[i * Dt + d]), 0.5 - (double)cw[2 * i], acc);
-    part[(size_t)blockIdx.x * Dp + d] = acc;
-  }
-}
 __global__ void k_grad0_sum(const double* __restrict__ part, double* grad0, int nb, int Dp) {
   for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
     double acc = 0.0;
@@ -1726,91 +970,6 @@ __global__ void k_grad0_sum(const double* __restrict__ part, double* grad0, int 
   }
 }
 }  // namespace
-namespace {
-constexpr int H0_BLOCKS = 148, H0_THREADS = 512, H0_ACC = 32;   // D x D <= 128 x 128 = 512 x 32 accumulators per block
-// one thread per data row: the constants of the quadratic-remainder mode.  aux [Npad / 2] records (w0, w1, a0, a1) of
-// row pairs (what the kernel loads), cw [Npad][2] = (c, w) (what g0 and H0 are formed from); η̃0 is the fp32 value whose
-// three bf16 terms sit in the spare K columns (k_write_reference); a = c − w η̃0 rounded once.
-__global__ void k_write_aux(const uint16_t* __restrict__ Xb, const float* __restrict__ beta_ref, float* aux, float* cw, long long N,
-                            long long Npad, int D, int Dt) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Npad) return;
-  float c = 0.f, w = 0.f, a = 0.f;
-  if (i < N) {
-    const uint16_t* xr = Xb + i * Dt;
-    double acc = 0.0;
-    for (int d = 0; d < D; ++d) acc = fma((double)bf16_val(xr[d]), (double)beta_ref[d], acc);
-    const float e = (float)acc;                       // what the MMA adds through the spare columns
-    const double t = tanh(0.5 * (double)e);
-    w = (float)(0.25 * (1.0 - t * t));                // σ'(η̃0)
-    a = (float)(0.5 * t - (double)w * (double)e);     // c − w η̃0 with c = ½ − σ(−η̃0)
-    c = (float)((double)a + (double)w * (double)e);   // the c the kernel's arithmetic implies: fma(w, η̃0, a)
-  }
-  float* rec = aux + (i >> 1) * 4 + (i & 1);
-  rec[0] = w; rec[2] = a;
-  cw[2 * i] = c; cw[2 * i + 1] = w;
-}
-// H0 = X̃ᵀ diag(w) X̃ in Float64 from the stored fp32 w: each block sums a contiguous range of rows into D x D
-// register accumulators (pair p = a D + b -> thread p % 512, slot p / 512), then one pass adds the blocks in order
-__global__ void __launch_bounds__(H0_THREADS) k_hess0_partial(const uint16_t* __restrict__ Xb, const float* __restrict__ cw,
-                                                              double* part, long long N, int D, int Dt) {
-  __shared__ float xs[8][128];
-  __shared__ float ws[8];
-  const long long r0 = N * blockIdx.x / gridDim.x, r1 = N * (blockIdx.x + 1) / gridDim.x;
-  double acc[H0_ACC];
-  int pa[H0_ACC], pb[H0_ACC];
-#pragma unroll
-  for (int m = 0; m < H0_ACC; ++m) {
-    acc[m] = 0.0;
-    const int p = threadIdx.x + m * H0_THREADS;
-    pa[m] = p < D * D ? p / D : -1;
-    pb[m] = p < D * D ? p % D : 0;
-  }
-  for (long long it = r0; it < r1; it += 8) {
-    const int nr = (int)((r1 - it < 8) ? (r1 - it) : 8);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nr * 128; idx += H0_THREADS) {
-      const int r = idx >> 7, d = idx & 127;
-      xs[r][d] = d < D ? bf16_val(Xb[(it + r) * Dt + d]) : 0.f;
-    }
-    if (threadIdx.x < nr) ws[threadIdx.x] = cw[2 * (it + threadIdx.x) + 1];
-    __syncthreads();
-    for (int r = 0; r < nr; ++r) {
-      const double w = (double)ws[r];
-#pragma unroll
-      for (int m = 0; m < H0_ACC; ++m)
-        if (pa[m] >= 0) acc[m] = fma((double)(xs[r][pa[m]] * xs[r][pb[m]]), w, acc[m]);   // bf16 x bf16 is exact in fp32
-    }
-  }
-#pragma unroll
-  for (int m = 0; m < H0_ACC; ++m) {
-    const int p = threadIdx.x + m * H0_THREADS;
-    if (p < D * D) part[(size_t)blockIdx.x * D * D + p] = acc[m];
-  }
-}
-__global__ void k_hess0_sum(const double* __restrict__ part, float* H0, int nb, int D, int Dp) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= D * D) return;
-  double acc = 0.0;
-  for (int b = 0; b < nb; ++b) acc += part[(size_t)b * D * D + p];
-  H0[(size_t)(p / D) * Dp + (p % D)] = (float)acc;
-}
-}  // namespace
-// quadratic-remainder mode (k_logistic_tc, RR == 2): per-row records, g0 = X̃ᵀ r0 and H0 = X̃ᵀ diag(w) X̃
-int32_t logistic_tc_write_quadratic_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev, std::string& err) {
-  if (!tc.aux && cudaMalloc(&tc.aux, size_t(tc.Npad) * 2 * 4) != cudaSuccess) { tc.aux = nullptr; err = "device allocation failed (aux)"; return BNUTS_ERR_CUDA; }
-  if (!tc.cw && cudaMalloc(&tc.cw, size_t(tc.Npad) * 2 * 4) != cudaSuccess) { tc.cw = nullptr; err = "device allocation failed (aux)"; return BNUTS_ERR_CUDA; }
-  if (!tc.H0 && cudaMalloc(&tc.H0, size_t(tc.Dp) * tc.Dp * 4) != cudaSuccess) { err = "device allocation failed (H0)"; return BNUTS_ERR_CUDA; }
-  if (!tc.H0_part && cudaMalloc(&tc.H0_part, size_t(H0_BLOCKS) * tc.D * tc.D * 8) != cudaSuccess) { err = "device allocation failed (H0 partials)"; return BNUTS_ERR_CUDA; }
-  cudaMemsetAsync(tc.H0, 0, size_t(tc.Dp) * tc.Dp * 4, s);
-  k_write_aux<<<(unsigned)((tc.Npad + 255) / 256), 256, 0, s>>>(tc.Xb, beta_ref_dev, tc.aux, tc.cw, (long long)tc.N, (long long)tc.Npad, tc.D, tc.Dt);
-  // g0 from the c of the records: the same two-pass reduction as the δ mode
-  k_grad0_partial_aux<<<G0_BLOCKS, 128, 0, s>>>(tc.Xb, tc.cw, tc.grad0_part, (long long)tc.N, tc.D, tc.Dt, tc.Dp);
-  k_grad0_sum<<<1, 128, 0, s>>>(tc.grad0_part, tc.grad0, G0_BLOCKS, tc.Dp);
-  k_hess0_partial<<<H0_BLOCKS, H0_THREADS, 0, s>>>(tc.Xb, tc.cw, tc.H0_part, (long long)tc.N, tc.D, tc.Dt);
-  k_hess0_sum<<<(tc.D * tc.D + 255) / 256, 256, 0, s>>>(tc.H0_part, tc.H0, H0_BLOCKS, tc.D, tc.Dp);
-  return 0;
-}
 void logistic_tc_write_residual_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev) {
   k_write_c0<<<(unsigned)((tc.Npad + 255) / 256), 256, 0, s>>>(tc.Xb, beta_ref_dev, tc.c0, (long long)tc.N, (long long)tc.Npad, tc.D,
                                                               tc.Dt);
@@ -1943,8 +1102,6 @@ int32_t logistic_tc_maps(LogisticTC& tc, std::string& err) {
     return BNUTS_ERR_CUDA;
   }
   if (!encode_map(tc.tmaps[4], tc.Xb, (uint64_t)tc.Npad, (uint64_t)tc.Dt, 64)) { err = "cuTensorMapEncodeTiled failed"; return BNUTS_ERR_CUDA; }
-  const char* ve = std::getenv("BNUTS_TC_VARIANT");
-  if (ve && tc.variant != 256) tc.variant = std::atoi(ve) == 64 ? 64 : 128;
   tc.ready = true;
   return 0;
 }

@@ -32,21 +32,14 @@ struct LogisticTC {
   float* c0 = nullptr;       // [Npad] ½ − r0_i, r0_i = σ(−η̃0_i) (zero in the padding rows)
   double* grad0 = nullptr;   // [Dp] X̃ᵀ·r0 in Float64 from the stored fp32 values: added by the consumer (EngineMem::grad0)
   double* grad0_part = nullptr;  // [G0_BLOCKS][Dp] scratch of its two-pass (deterministic) reduction
-  // quadratic-remainder mode (k_logistic_tc, RR == 2): per-row constants, H0 = X̃ᵀ diag(w) X̃
-  float* aux = nullptr;      // [Npad / 2] records (w0, w1, a0, a1) of row pairs, a = c − w η̃0
-  float* cw = nullptr;       // [Npad][2] (c, w): what g0 and H0 are formed from
-  float* H0 = nullptr;       // [Dp][Dp]
-  double* H0_part = nullptr; // scratch of its two-pass reduction
-  bool qpipe = false;        // rmode 2: BNUTS_TC_QPIPE=1 selects k_logistic_tcq (decoupled S / R buffers) instead of k_logistic_tc<.., 2>
-  int32_t rmode = 0;         // residual operand: 0 two bf16 terms of r; 1 one term of δ = r − r0; 2 one term of ρ = δ + w Δη̃
+  int32_t rmode = 0;         // residual operand: 0 two bf16 terms of r; 1 one term of δ = r − r0
   // borrowed from the engine
   const uint16_t* bh = nullptr; const uint16_t* bm = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
-  const float* q = nullptr;  // [rows][Dp] staged positions (k_lin_ref of the quadratic-remainder mode)
   float* G = nullptr;        // [nsplit][rows][Dp]
   double* Ld = nullptr;      // [nsplit][C] log-density partials (Float64: ~1e5..1e6 in magnitude)
   // opaque tensor maps (4 x CUtensorMap, 128 B each, 64 B aligned): X, βh, βm, βl
   alignas(64) unsigned char tmaps[5][128];   // X (128-row box), βh, βm, βl, X (64-row box)
-  int32_t variant = 128;     // 128: k_logistic_tc (β in shared memory, 128-row blocks); 64: k_logistic_tc64 (β in TMEM, 64-row blocks)
+  int32_t variant = 128;     // 128: k_logistic_tc (D <= 128, 128-row blocks); 256: k_logistic_tc256 (128 < D <= 256, 64-row blocks)
   bool ready = false;
   cudaError_t last = cudaSuccess;
 
@@ -71,8 +64,6 @@ int32_t logistic_tc_maps(LogisticTC& tc, std::string& err);
 void logistic_tc_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev);
 // c0_i = ½ − σ(−X̃_i·beta_ref) per row and grad0 = X̃ᵀ·(½ − c0) in Float64 (fixed summation order)
 void logistic_tc_write_residual_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev);
-// records (c, w, −η̃0), g0 and H0 of the quadratic-remainder mode
-int32_t logistic_tc_write_quadratic_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev, std::string& err);
 // staging rows: 1.0 in the reserved columns of the high term
 void logistic_tc_init_stage(LogisticTC& tc, cudaStream_t s, uint16_t* bh);
 
@@ -119,7 +110,7 @@ int32_t logistic_tc_attach(LogisticTC& tc, E& eng, std::string& err) {
   eng.alloc_stage(1, size_t(tc.partial_rows));
   M.stage_ld = eng.x.template alloc<double>(size_t(tc.partial_rows));
   eng.x.zero(M.stage_ld, size_t(tc.partial_rows) * sizeof(double));
-  tc.bh = M.stage_bh; tc.bm = M.stage_bm; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.Ld = M.stage_ld; tc.q = M.stage_q;
+  tc.bh = M.stage_bh; tc.bm = M.stage_bm; tc.bl = M.stage_bl; tc.G = M.stage_g; tc.Ld = M.stage_ld;
   logistic_tc_init_stage(tc, eng.x.stream, M.stage_bh);
   M.lin_w = tc.colsum;
   M.beta_ref = tc.beta_ref;
@@ -199,26 +190,12 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
     x.h2d(tc.beta_ref, b.data(), size_t(M.Dp) * sizeof(float));
     logistic_tc_write_reference(tc, x.stream, tc.beta_ref);
     tc.nterms = 2;
-    // residual about the reference as well (one bf16 term instead of r = rh + rl; see k_logistic_tc):
-    //  - quadratic remainder ρ = δ + w Δη̃ with the linear part done as a D x D mat-vec per chain (k_lin_ref): main
-    //    kernel (D <= 125), rows not sharded.  Error ≈ 7.6e-4·k·(D/N)·|∇ℓ| at k posterior sd from the reference (below the
-    //    two-term path's in the posterior bulk for N ≥ 2500·D).  OPT-IN (BNUTS_TC_QREF=1): measured on B200 it is no
-    //    faster than the two-term kernel — halving the GEMM2 work does not shorten k_logistic_tc, whose elementwise
-    //    warps, not the tensor pipe, set the pace — and it costs the extra k_lin_ref launch.
-    //    BNUTS_TC_QPIPE=1 selects its decoupled-buffer kernel k_logistic_tcq (validated, also no faster).
-    const char* qr = std::getenv("BNUTS_TC_QREF");
+    // residual about the reference as well (one bf16 term of δ = r − r0 instead of r = rh + rl; see k_logistic_tc):
+    // error ≈ 1.7e-3·sqrt(D/N)·|∇ℓ|, below the path's tolerance for tall problems only, so the engine takes it by itself
+    // when N >= 3.3e5·D over the whole row group (config 5); BNUTS_TC_RREF=0/1 overrides.
     const char* rr = std::getenv("BNUTS_TC_RREF");
-    const bool rr_forced = rr && std::atoi(rr) != 0;
-    if (tc.variant == 128 && tc.aug && eng.reduce_world() == 1 && !eng.reduce_on && qr && std::atoi(qr) != 0 && !rr_forced) {
-      const int32_t rc = logistic_tc_write_quadratic_reference(tc, x.stream, tc.beta_ref, err);
-      if (rc) return rc;
-      tc.rmode = 2;
-      const char* qp = std::getenv("BNUTS_TC_QPIPE");
-      tc.qpipe = qp && std::atoi(qp) != 0;
-      return x.check(err);
-    }
     const bool rr_auto = double(tc.N) * double(eng.reduce_world()) >= 3.3e5 * double(M.D);
-    if (tc.variant != 64 && (rr ? std::atoi(rr) != 0 : rr_auto)) {
+    if (rr ? std::atoi(rr) != 0 : rr_auto) {
       logistic_tc_write_residual_reference(tc, x.stream, tc.beta_ref);
       tc.rmode = 1;
       M.grad0 = tc.grad0;

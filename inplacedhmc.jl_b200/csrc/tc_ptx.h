@@ -68,6 +68,10 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// fire-and-forget add of four consecutive floats in global memory (16-byte aligned)
+__device__ __forceinline__ void red_add_f32x4(float4* p, const float4 v) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // one elected lane of a converged warp (the form ptxas turns into ELECT + a predicated instruction)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

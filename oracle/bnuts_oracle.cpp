@@ -166,7 +166,8 @@ template <class T> struct ChainCtx;
 //   min_turn   min over merges of min(|ρ·p♯₋| / Σ|ρ_d p♯₋_d|, same for p♯₊)      (is_turning, src/NUTS.jl:148-170)
 //   min_sel    min over consuming merges of |e + logprob2|                      (rand_bool_logprob, src/NUTS.jl:32-34)
 //   scale_H    max over leaves of |ℓq| + |K|: the magnitude whose rounding bounds the error of every Δ and ω
-struct DecisionTrace { double min_div, min_turn, min_sel, scale_H; };
+//   grad_sq    max over leaves of |∇ℓ|²: how strongly an error of the position moves the energy
+struct DecisionTrace { double min_div, min_turn, min_sel, scale_H, grad_sq; };
 thread_local DecisionTrace* g_trace = nullptr;
 inline void trace_min(double& slot, double v) { if (v < slot) slot = v; }
 
@@ -323,6 +324,9 @@ void leaf(ChainCtx<T>& X, const Ham<T>& H, const Trajectory<T>& tr, const PhaseP
     if (!is_initial) trace_min(g_trace->min_div, std::fabs(double(delta) - double(tr.min_delta)));
     const double sc = std::fabs(double(z.lq)) + std::fabs(double(z.lq) - double(Hz));
     if (sc > g_trace->scale_H && std::isfinite(sc)) g_trace->scale_H = sc;
+    double g2 = 0.0;
+    for (int d = 0; d < H.E->D; ++d) g2 += double(z.g[d]) * double(z.g[d]);
+    if (g2 > g_trace->grad_sq && std::isfinite(g2)) g_trace->grad_sq = g2;
   }
   if (is_initial) { v->lsa = -bn::lim<T>::inf(); v->steps = 0; }
   else { v->lsa = (delta < T(0)) ? delta : T(0); v->steps = 1; }
@@ -367,6 +371,8 @@ template <class T> bool is_turning(int D, const TurnStat<T>& tau) {
 }
 // ≙ rand_bool_logprob, src/NUTS.jl:32-34 — the draw is consumed only if logprob < 0
 template <class T> bool rand_bool_logprob(const Trajectory<T>& tr, T logprob, uint32_t j, uint32_t k, uint32_t n) {
+  // "logprob >= 0" is a decision too: it settles whether a draw is consumed, which shifts a scripted stream
+  if (g_trace && std::isfinite(double(logprob))) trace_min(g_trace->min_sel, std::fabs(double(logprob)));
   if (logprob >= T(0)) return true;
   T e;
   if (tr.exps && tr.n_exp < tr.n_exps) e = T(tr.exps[tr.n_exp]);   // scripted stream: consumed in call order
@@ -478,7 +484,7 @@ bnuts_tree_stats sample_tree(Engine<T>& E, ChainCtx<T>& X, int c, double eps, ui
   Visited<T> v;
   Invalid term;
   int32_t depth;
-  if (!E.trace.empty()) { E.trace[size_t(c)] = DecisionTrace{1e300, 1e300, 1e300, 0.0}; g_trace = &E.trace[size_t(c)]; }
+  if (!E.trace.empty()) { E.trace[size_t(c)] = DecisionTrace{1e300, 1e300, 1e300, 0.0, 0.0}; g_trace = &E.trace[size_t(c)]; }
   sample_trajectory(X, H, tr, z, E.cfg.max_depth, directions, &zeta, &v, &term, &depth);
   g_trace = nullptr;
   bnuts_tree_stats st;
@@ -1065,14 +1071,15 @@ double bnuts_oracle_exponential(uint64_t seed, uint32_t chain, uint32_t t, uint3
   return bn::std_exponential(seed, chain, t, j, k, n, 0.0);
 }
 // decision margins of every chain's last transition (see DecisionTrace); enable = 1 turns tracing on for later calls.
-// out [C][4] = (min_div, min_turn, min_sel, scale_H), may be NULL.
+// out [C][5] = (min_div, min_turn, min_sel, scale_H, grad_sq), may be NULL.
 int32_t bnuts_oracle_trace(bnuts_engine* e, int32_t enable, double* out) {
   auto f = [&](auto& E) -> int32_t {
     if (out)
       for (size_t c = 0; c < E.trace.size(); ++c) {
-        out[4 * c] = E.trace[c].min_div; out[4 * c + 1] = E.trace[c].min_turn; out[4 * c + 2] = E.trace[c].min_sel; out[4 * c + 3] = E.trace[c].scale_H;
+        out[5 * c] = E.trace[c].min_div; out[5 * c + 1] = E.trace[c].min_turn; out[5 * c + 2] = E.trace[c].min_sel;
+        out[5 * c + 3] = E.trace[c].scale_H; out[5 * c + 4] = E.trace[c].grad_sq;
       }
-    if (enable) E.trace.assign(size_t(E.C), DecisionTrace{1e300, 1e300, 1e300, 0.0}); else E.trace.clear();
+    if (enable) E.trace.assign(size_t(E.C), DecisionTrace{1e300, 1e300, 1e300, 0.0, 0.0}); else E.trace.clear();
     return 0;
   };
   DISPATCH(e, f(E), f(E));

@@ -162,21 +162,6 @@ def test_tensor_reference_point(bn, oracle_lib, cuda_lib):
     assert g3c.tobytes() == g3.tobytes()
 
 
-def test_tensor_variant_64_row_blocks(bn, oracle_lib, cuda_lib, monkeypatch):
-    """k_logistic_tc64 (beta operand resident in TMEM, 64-row blocks): same tolerance as the default kernel."""
-    monkeypatch.setenv("BNUTS_TC_VARIANT", "64")
-    for (N, D, C) in [(3000, 100, 200), (200, 17, 5), (700, 128, 130)]:
-        X, y, beta = make_logistic(N, D)
-        rng = np.random.default_rng(1)
-        q = _f32(beta[None, :] + rng.normal(size=(C, D)) * 0.3)
-        ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0, row_blocks=1); ref.set_positions(q)
-        tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0); tc.set_positions(q)
-        _, g0, l0 = ref.get_state(); _, g1, l1 = tc.get_state()
-        assert np.max(_rel(g1, g0)) < TOL32 and np.max(np.abs(l1 - l0) / np.abs(l0)) < TOL32
-        if D + 3 <= 128:
-            tc.logistic_set_reference(None)
-
-
 def test_tensor_per_leapfrog_parity(bn, oracle_lib, cuda_lib):
     N, D, C = 3000, 100, 256
     X, y, beta = make_logistic(N, D)
@@ -192,38 +177,46 @@ def test_tensor_per_leapfrog_parity(bn, oracle_lib, cuda_lib):
         assert np.max(_rel(b[2], a[2])) < 5 * TOL32
 
 
-# Error model of the tensor (fp32-variant) path against the Float64 oracle on identical inputs, used to ATTRIBUTE every
-# teacher-forced decision mismatch (north_star: decisions are bit-exact on the deterministic path; on the tolerance-parity
-# tensor path a decision may flip only where the compared quantity is within the path's error of its threshold):
-#   energies  H = ℓ − K are fp32 numbers of magnitude scale_H = |ℓ| + K: every Δ = H − π₀ and every log-weight ω built
-#             from them carries at most KAPPA_H · scale_H of error (ℓ of the tensor path agrees with Float64 to 1e-6,
-#             tested above; 2e-6 covers both ends of a difference)
-#   divergence test  Δ < min_Δ:               margin |Δ − min_Δ|      ≤ 2 · KAPPA_H · scale_H
-#   selection        e > −logprob2:           margin |e + logprob2|   ≤ 4 · KAPPA_H · scale_H   (ω₂ − logaddexp(ω₁, ω₂))
-#   turn test        ρ·p♯ < 0:                margin |ρ·p♯| / Σ|ρ_d p♯_d| ≤ KAPPA_TURN · steps  (momenta accumulate one
-#             gradient error of 5·TOL32 per leapfrog, see test_tensor_per_leapfrog_parity)
+# Tree decisions of the tensor (fp32-variant, tolerance-parity) path as a PROOF.  north_star: decisions are bit-exact on the
+# deterministic path; on the tensor path a decision may flip only where the compared quantity is within the path's error
+# of its threshold.  The test ATTRIBUTES every teacher-forced mismatch to such a decision:
+#   * the Float64 oracle records how far each of its decisions was from its threshold (bnuts_oracle_trace):
+#       divergence test  Δ < min_Δ        margin |Δ − min_Δ|
+#       selection        e > −logprob2    margin min(|e + logprob2|, |logprob2|)   (logprob2 is a difference of two log-weights;
+#                                         its sign decides whether a draw is CONSUMED, which shifts a scripted stream)
+#       turn test        ρ·p♯ < 0         margin |ρ·p♯| / Σ|ρ_d p♯_d|
+#   * the energy error E of the tensor path is MEASURED in the same run: on every chain-transition whose tree is identical
+#     the two sides select the same leaf, and |π_tensor − π_oracle| (TreeStatisticsNUTS.π, the Hamiltonian at that leaf) is
+#     the discrepancy of one energy; KAPPA_EMP = max of it relative to scale_H = |ℓ| + K.  A divergence margin may be
+#     crossed by 2 E (two energies in Δ = H − π₀), a selection margin by 4 E (two log-weights); turn dots accumulate one
+#     gradient error of 5·TOL32 per leapfrog (test_tensor_per_leapfrog_parity)
+#   * and E itself must respect the error MODEL of the path: rounding of the fp32 energies, KAPPA_H · scale_H, plus the
+#     position error a force error of TOL32·|∇ℓ| builds up over a trajectory of length L = steps·ϵ (unit metric:
+#     |δq| ≤ TOL32 |∇ℓ| L²/2) times the slope |∇ℓ| of the energy.
 KAPPA_H = 2e-6
 KAPPA_TURN = 5 * TOL32
 
 
 def _oracle_trace(lib, e, enable):
     import ctypes as C_
-    out = np.zeros((e.C, 4))
+    out = np.zeros((e.C, 5))
     lib.bnuts_oracle_trace.argtypes = [C_.c_void_p, C_.c_int32, C_.c_void_p]
     lib.bnuts_oracle_trace.restype = C_.c_int32
     assert lib.bnuts_oracle_trace(e.h, 1 if enable else 0, out.ctypes.data_as(C_.c_void_p)) == 0
     return out
 
 
-@pytest.mark.parametrize("N,D,C,T,depth,eps,use_ref", [(2000, 50, 128, 10, 6, 0.02, False),
-                                                       (100_000, 100, 64, 5, 5, 0.004, True)])
-def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib, N, D, C, T, depth, eps, use_ref):
-    """Tree decisions of the tensor path as a PROOF, not a percentage.  Both sides restart every transition from the same
-    fp32-representable state with the same injected directions, momenta AND merge exponentials (all three random
-    streams); the Float64 oracle records how far each of its decisions was from its threshold (bnuts_oracle_trace).
-    Every chain-transition whose depth / termination / steps / selected index differ must contain a decision within the
-    error model above of its threshold; everything else must agree exactly.  The second case is the shape and mode of
-    the bench (D = 100, reference point at the mode: the two-term position operand)."""
+@pytest.mark.parametrize("N,D,C,T,depth,eps,use_ref,min_clear", [(2000, 50, 128, 10, 6, 0.02, False, 0.6),
+                                                                 (100_000, 100, 64, 5, 5, 0.004, True, 0.3)])
+def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib, N, D, C, T, depth, eps, use_ref, min_clear):
+    """Both sides restart every transition from the same fp32-representable state with the same injected directions,
+    momenta AND merge exponentials (all three random streams of src/NUTS.jl:251-258, :32-34).  Every chain-transition
+    whose depth / termination / steps / selected index differ must contain a decision within the measured error of its
+    threshold; everything else must agree exactly, and most of the run must be in that second class.  The second case is
+    the shape and mode of the bench (D = 100, reference point at the mode: the two-term position operand); there the fp32
+    energies are ~6e4 with an ulp of 4e-3, so more selections sit within the measured error (1.5e-2) of their threshold
+    and the provably-identical class is smaller (measured on B200: 140 of 320, against 1033 of 1280 in the first case;
+    2 and 3 mismatches, each with a decision within 1 % / 7 % of its bound)."""
     X, y, beta = make_logistic(N, D)
     b, sd = _newton_mode(X, y, beta)
     rng = np.random.default_rng(3)
@@ -233,8 +226,7 @@ def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib, N, D, C,
         tc.logistic_set_reference(b)
     q = _f32(b[None, :] + rng.normal(size=(C, D)) * sd[None, :])
     _oracle_trace(oracle_lib, ref, True)
-    n_mis = n_clear = total = 0
-    kappa_needed = 0.0
+    same_l, trace_l, steps_l, dpi_l = [], [], [], []
     for t in range(T):
         p = _f32(rng.normal(size=(1, C, D)))
         dirs = rng.integers(0, 2 ** 32, size=(1, C), dtype=np.uint64).astype(np.uint32)
@@ -243,26 +235,30 @@ def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib, N, D, C,
             e.seed(77, t); e.set_positions(q); e.set_stepsize(eps); e.inject(1, dirs, p, exps)
         ca, sa, ia = ref.sample(1, want_index=True)
         cb, sb, ib = tc.sample(1, want_index=True)
-        tr = _oracle_trace(oracle_lib, ref, True)
         same = ((sa["depth"] == sb["depth"]) & (sa["steps"] == sb["steps"]) & (sa["term_left"] == sb["term_left"]) &
                 (sa["term_right"] == sb["term_right"]) & (ia == ib))[:, 0]
-        steps = sa["steps"][:, 0].astype(np.float64)
-        # each margin in units of its bound; a chain-transition is "clear" when every decision is more than 1 away
-        units = np.minimum.reduce([tr[:, 0] / (2 * KAPPA_H * tr[:, 3]), tr[:, 2] / (4 * KAPPA_H * tr[:, 3]),
-                                   tr[:, 1] / (KAPPA_TURN * steps)])
-        clear = units > 1.0
-        assert same[clear].all(), ("decision differs although every margin exceeds the error model",
-                                   t, np.nonzero(clear & ~same)[0], units[clear & ~same], tr[clear & ~same])
-        n_mis += int((~same).sum()); n_clear += int(clear.sum()); total += C
-        if (~same).any():
-            kappa_needed = max(kappa_needed, float(units[~same].max()))
-        ok = same
-        assert np.max(_rel(cb[ok, 0], ca[ok, 0])) < 1e-4      # same tree, same selected leaf: the draw agrees to the path's tolerance
+        same_l.append(same); trace_l.append(_oracle_trace(oracle_lib, ref, True)); steps_l.append(sa["steps"][:, 0].astype(np.float64))
+        dpi_l.append(np.abs(sa["pi"][:, 0] - sb["pi"][:, 0]))
+        assert np.max(_rel(cb[same, 0], ca[same, 0])) < 1e-4      # same tree, same selected leaf: the draw agrees to the path's tolerance
         q = _f32(ca[:, 0])
-    print("teacher-forced: %d chain-transitions, %d mismatches (all within %.2f of their bound), %d clear" %
-          (total, n_mis, kappa_needed, n_clear))
-    assert n_clear >= 0.5 * total, (n_clear, total)           # the proof must not be vacuous
-    assert n_mis <= 0.15 * total, (n_mis, total)
+    same = np.concatenate(same_l); tr = np.concatenate(trace_l); steps = np.concatenate(steps_l); dpi = np.concatenate(dpi_l)
+    scale_H, grad_sq = tr[:, 3], tr[:, 4]
+    # measured energy error of the path, and the model that must bound it
+    kappa_emp = float(np.max(dpi[same] / scale_H[same]))
+    model = KAPPA_H * scale_H + TOL32 * grad_sq * (steps * eps) ** 2 / 2
+    assert np.all(dpi[same] <= model[same]), (np.max(dpi[same] / model[same]), kappa_emp)
+    E = kappa_emp * scale_H
+    units = np.minimum.reduce([tr[:, 0] / (2 * E), tr[:, 2] / (4 * E), tr[:, 1] / (KAPPA_TURN * steps)])
+    clear = units > 1.0
+    mis = ~same
+    print("teacher-forced N=%d D=%d: %d chain-transitions, %d mismatches (largest margin of a mismatch: %.2f of its bound), %d clear; "
+          "measured energy error %.1e of scale_H (%.3g absolute at most), model allows up to %.3g" %
+          (N, D, same.size, int(mis.sum()), float(units[mis].max()) if mis.any() else 0.0, int(clear.sum()), kappa_emp,
+           float(np.max(dpi[same])), float(np.max(model))))
+    assert same[clear].all(), ("decision differs although every margin exceeds the measured error", np.nonzero(clear & mis)[0],
+                               units[clear & mis], tr[clear & mis])
+    assert clear.sum() >= min_clear * same.size, (int(clear.sum()), same.size)     # the proof must not be vacuous
+    assert mis.sum() <= 0.1 * same.size, (int(mis.sum()), same.size)
 
 
 def test_tensor_full_size_known_answers(bn, cuda_lib):
@@ -438,15 +434,14 @@ def test_tensor_single_term_residual_forced(bn, oracle_lib, cuda_lib, monkeypatc
 
 def test_tensor_reference_modes_full_size(bn, cuda_lib, monkeypatch):
     """BASELINE config 3 shape (N = 1e6, D = 100) around the optimum found on the device: gradients in the posterior bulk
-    and its tails against numpy Float64 for the three residual modes of the reference-point path.  Two bf16 terms of r
-    (what the engine takes here) and the quadratic remainder (opt-in): north-star fp32 tolerance, or the fp32 conditioning floor N * eps32 where
+    and its tails against numpy Float64 for the two residual modes of the reference-point path.  Two bf16 terms of r
+    (what the engine takes here): north-star fp32 tolerance, or the fp32 conditioning floor N * eps32 where
     |grad| -> 0; slot / tile invariance bit for bit.  One term of delta forced on: within three times its error model
     (1.7e-5 |grad| at this N / D, which is why it is not taken by itself here)."""
     N, D, C = 1_000_000, 100, 256
     X, y, beta = make_logistic(N, D)
     rng = np.random.default_rng(4)
-    for v in ("BNUTS_TC_RREF", "BNUTS_TC_QREF"):
-        monkeypatch.delenv(v, raising=False)
+    monkeypatch.delenv("BNUTS_TC_RREF", raising=False)
     tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0)
     tc.set_positions(np.repeat(_f32(beta)[None, :], C, axis=0))
     tc.find_local_optimum(1e-4, 50)
@@ -461,9 +456,8 @@ def test_tensor_reference_modes_full_size(bn, cuda_lib, monkeypatch):
     gref = ((y[:, None] - 1 / (1 + np.exp(-eta))).T @ X) - q[1:1 + nw]
     nrm = np.linalg.norm(gref, axis=1)
     out = {}
-    for mode, env in (("two", {}), ("quad", {"BNUTS_TC_QREF": "1"}), ("delta", {"BNUTS_TC_RREF": "1"})):
-        for v in ("BNUTS_TC_RREF", "BNUTS_TC_QREF"):
-            monkeypatch.delenv(v, raising=False)
+    for mode, env in (("two", {}), ("delta", {"BNUTS_TC_RREF": "1"})):
+        monkeypatch.delenv("BNUTS_TC_RREF", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         tc.logistic_set_reference(b); tc.set_positions(q); _, g, l = tc.get_state()
@@ -474,72 +468,8 @@ def test_tensor_reference_modes_full_size(bn, cuda_lib, monkeypatch):
             assert g[k].tobytes() == g[1 + (k - 1 - nw) % nw].tobytes() and l[k] == l[1 + (k - 1 - nw) % nw]
         out[mode] = (g, l, err)
         print("N=1e6 D=100 mode", mode, "|grad|", nrm, "err", err, "rel", err / nrm)
-    assert out["two"][0].tobytes() != out["quad"][0].tobytes() != out["delta"][0].tobytes()
-    assert out["two"][1].tobytes() == out["quad"][1].tobytes() == out["delta"][1].tobytes()      # the log density is untouched
-    assert np.all(out["quad"][2][1:] < out["two"][2][1:])     # the quadratic remainder is the more accurate one in the bulk
-
-
-QR_MODEL = 7.6e-4   # gradient error of the quadratic-remainder mode: QR_MODEL * k * (D / N) * |grad| at k posterior sd
-
-
-@pytest.mark.parametrize("N,D,C,pipe", [(20000, 100, 256, "0"), (5000, 61, 40, "1"), (9000, 125, 150, "0"), (3000, 17, 5, "1"),
-                                        (300000, 100, 64, "0"), (300000, 100, 160, "1")])
-def test_tensor_quadratic_remainder_mode(bn, oracle_lib, cuda_lib, monkeypatch, N, D, C, pipe):
-    """Quadratic-remainder mode of the reference-point path (opt-in, BNUTS_TC_QREF=1; k_logistic_tc with RR = 2 or, with
-    BNUTS_TC_QPIPE=1, the decoupled-buffer kernel k_logistic_tcq, + k_lin_ref): the residual operand is
-    rho = r - r0 + w (eta - eta0), one bf16 term, and g0 - H0 (beta - beta0) is added per chain.  Error model
-    7.6e-4 k (D / N) |grad| at k posterior sd from the reference: north-star tolerance out to 10 sd when N >= 2500 D (last
-    two cases), three times the model at the small sizes.  Far tails (10..60 sd): bounded loss.  Leaving the mode restores
-    the exact path."""
-    force = N < 2500 * D
-    monkeypatch.setenv("BNUTS_TC_QPIPE", pipe)
-    for v in ("BNUTS_TC_RREF", "BNUTS_TC_QREF"):
-        monkeypatch.delenv(v, raising=False)
-    X, y, beta = make_logistic(N, D)
-    rng = np.random.default_rng(11)
-    b, sd = _newton_mode(X, y, beta)
-    scale = np.concatenate([np.linspace(0.02, 10.0, C - C // 4), np.linspace(10.0, 60.0, C // 4)])
-    q = _f32(b[None, :] + rng.normal(size=(C, D)) * sd[None, :] * scale[:, None])
-    ref = bn.Engine(C, D, dtype=F64, lib=oracle_lib); ref.model_logistic(X, y, 1.0, row_blocks=1)
-    ref.set_positions(q); _, g0, l0 = ref.get_state()
-    tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0)
-    tc.set_positions(q); _, g3, l3 = tc.get_state()                                   # exact three-term path
-    monkeypatch.setenv("BNUTS_TC_QREF", "0")
-    tc.logistic_set_reference(b); tc.set_positions(q); _, g2, l2 = tc.get_state()      # two-term operand, r = rh + rl
-    monkeypatch.setenv("BNUTS_TC_QREF", "1")
-    tc.logistic_set_reference(b); tc.set_positions(q); _, gq, lq = tc.get_state()      # quadratic remainder
-    assert gq.tobytes() != g2.tobytes() and lq.tobytes() == l2.tobytes()
-    nrm = np.linalg.norm(g0, axis=1)
-    floor = 3 * N * 6e-8
-    eq = np.linalg.norm(gq - g0, axis=1); e2 = np.linalg.norm(g2 - g0, axis=1)
-    near = scale <= 10.0
-    tol = np.maximum(TOL32, 3 * QR_MODEL * scale * D / N) if force else np.full(C, TOL32)
-    assert np.all(eq[near] < np.maximum(tol[near] * nrm[near], floor)), np.max(eq[near] / np.maximum(tol[near] * nrm[near], floor))
-    far = scale > 10.0 if np.any(scale > 10.0) else near
-    assert np.all(eq[far] < np.maximum(5e-3 * nrm[far], floor)), np.max(eq[far] / nrm[far])   # far tails: bounded loss
-    print("quadratic remainder N=%d D=%d: max rel err near %.2e (two-term %.2e), far %.2e (two-term %.2e)" % (
-        N, D, np.max(eq[near] / nrm[near]), np.max(e2[near] / nrm[near]), np.max(eq[far] / nrm[far]), np.max(e2[far] / nrm[far])))
-    assert np.max(np.abs(lq - l0) / np.abs(l0)) < TOL32
-    # a chain AT the reference: rho = 0 in every row, the gradient is the stored Float64 constant
-    at = np.repeat(_f32(b)[None, :], C, axis=0)
-    tc.set_positions(at); _, gb, _ = tc.get_state()
-    ref.set_positions(at); _, gb0, _ = ref.get_state()
-    assert np.max(np.linalg.norm(gb - gb0, axis=1)) < floor
-    # per-leapfrog parity (chains within 3 sd), a free run with ragged launches (compacted rows), slot invariance
-    qn = _f32(b[None, :] + rng.normal(size=(C, D)) * sd[None, :] * np.linspace(0.05, 3.0, C)[:, None])
-    ref.set_positions(qn); tc.set_positions(qn)
-    p = _f32(rng.normal(size=(C, D)) * np.sqrt(N) * 0.3)
-    a = ref.leapfrog(p, 1e-3, 3); c = tc.leapfrog(p, 1e-3, 3)
-    assert np.max(_rel(c[0], a[0])) < TOL32
-    tc.set_positions(q[:1].repeat(C, axis=0)); _, gs, ls = tc.get_state()
-    assert all(gs[k].tobytes() == gs[0].tobytes() for k in range(C)) and np.all(ls == ls[0])
-    tc.set_positions(qn); tc.set_stepsize(0.5 / np.sqrt(N)); ch, st = tc.sample(3)
-    assert np.isfinite(ch).all() and (st["steps"] > 0).all()
-    # row sharding cannot be switched on under the mode; leaving it restores the exact path bit for bit
-    with pytest.raises(bn.BnutsError):
-        tc.set_allreduce(lambda buf, count, dtype: None)
-    tc.logistic_set_reference(None); tc.set_positions(q); _, g3b, _ = tc.get_state()
-    assert g3b.tobytes() == g3.tobytes()
+    assert out["two"][0].tobytes() != out["delta"][0].tobytes()
+    assert out["two"][1].tobytes() == out["delta"][1].tobytes()      # the log density is untouched
 
 
 def test_synthetic_rows_on_device(bn, oracle_lib, cuda_lib):
