@@ -300,12 +300,16 @@ def setup_engine(a, bn, rank, world, local):
         e.set_positions(None)
         e.find_local_optimum(1e-4, a.opt_iters)
         # reference point of the tensor path (include/bnuts.h) = the optimum just found (across-chain mean); the engine
-        # checks it and keeps the exact three-term path if it is refused
+        # checks it and keeps the exact three-term path if it is refused.  D > 128 always works about a reference (16-bit
+        # operand about zero at first), so there the search is repeated from the more accurate operand
         info["position_operand_terms"] = 3 if D <= 128 else 2
         if not a.no_reference:
             try:
                 e.logistic_set_reference(e.get_state()[0].mean(axis=0))
                 info["position_operand_terms"] = 2
+                for _ in range(2 if D > 128 else 0):
+                    e.find_local_optimum(1e-4, a.opt_iters)
+                    e.logistic_set_reference(e.get_state()[0].mean(axis=0))
             except bn.BnutsError as ex:
                 print("reference point refused: %s" % ex, file=sys.stderr)
         e.find_initial_stepsize()

@@ -123,7 +123,9 @@ int32_t bnuts_synth_logistic_rows(uint64_t data_seed, int64_t row_offset, int64_
  * posterior mode lets the kernel evaluate X·beta as X·beta_ref (stored) + X·(beta − beta_ref) with
  * two instead of three bf16 terms for the fp32 position.  The point is checked: if the gradient
  * there exceeds sqrt(N·D)/2 the call fails with BNUTS_ERR_INVALID_ARGUMENT and the exact
- * three-term path stays in force.  beta_ref == NULL returns to the three-term path.
+ * three-term path stays in force.  beta_ref == NULL returns to the three-term path.  For 128 < D <= 256 the kernel always
+ * works about a reference point (zero until one is set; there is no three-term form to fall back to), so any finite
+ * point is accepted there: optimise, set the reference, optimise again from the more accurate operand, set it again.
  * For tall problems (N >= 3.3e5 D over the whole row group) the residual is carried about the reference as well
  * (one bf16 term of sigma(−eta) − sigma(−eta_ref) instead of two of sigma(−eta); BNUTS_TC_RREF=0/1 overrides). */
 int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double* beta_ref);

@@ -13,7 +13,7 @@
 // Layout (T = engine arithmetic type, Dp = D rounded up to 32, chain-major so a
 // warp streams contiguous memory and GEMM staging is K-major):
 //   zs      [C][S][3][Dp]  phase-point slots (q, p, ∇ℓ)      ≙ Tree z-slots, src/tree.jl:69-82
-//   zlq     [C][S]         ℓ(q) per slot                      ≙ EvaluatedLogDensity.ℓq
+//   zlq     [C][S]         ℓ(q) per slot, Float64 for both T  ≙ EvaluatedLogDensity.ℓq
 //   st_rho  [C][L][Dp]     Σρ of pending left siblings        ≙ Σρ slots, src/tree.jl:95-105
 //   st_psf  [C][L][Dp]     p♯ of their first-built leaf       ≙ ρ♯ slots, src/tree.jl:83-94
 //   m_rho, m_psm, m_psp, ps_cur [C][Dp]   main-tree turn statistic, p♯ of the newest leaf
@@ -26,7 +26,7 @@ namespace bn {
 template <class T> struct EngineMem {
   int32_t C, D, Dp, S, L;
   int32_t model_kind;
-  T* zs; T* zlq; T* st_rho; T* st_psf;
+  T* zs; double* zlq; T* st_rho; T* st_psf;
   T* m_rho; T* m_psm; T* m_psp; T* ps_cur; T* Minv; T* W;
   ChainState<T>* cs;
   // gradient staging for models evaluated by a separate batched kernel
@@ -177,8 +177,8 @@ template <class T, class LP> struct Backend {
   BN_HD T* stpsf(int k) const { return M.st_psf + ((int64_t)c * M.L + k) * M.Dp; }
   BN_HD T* cv(T* base) const { return base + (int64_t)c * M.Dp; }
 
-  BN_HD T get_lq(int s) const { return M.zlq[(int64_t)c * M.S + s]; }
-  BN_HD void set_lq(int s, T v) const {
+  BN_HD double get_lq(int s) const { return M.zlq[(int64_t)c * M.S + s]; }
+  BN_HD void set_lq(int s, double v) const {
     if (lp.lane0()) M.zlq[(int64_t)c * M.S + s] = v;
     lp.sync();
   }
@@ -363,10 +363,11 @@ template <class T, class LP> struct Backend {
   // ≙ logdensity_and_gradient! (call site src/kinetic_energy.jl:73); SURVEY.md §A.4 targets.
   // Elementwise targets are evaluated here; batched targets were evaluated by a
   // separate kernel into the staging buffers and are finalised here.
-  BN_HD T model_grad(int slot) const {
+  // Returns ℓ as Float64: what a target computes in T is widened once; the tensor path's Float64 partial sums stay Float64.
+  BN_HD double model_grad(int slot) const {
     const T* q = zq(slot);
     T* g = zg(slot);
-    T l;
+    double l;
     switch (M.model_kind) {
       case MODEL_IID_NORMAL: {
         BN_FOR4(d0, nv) {
@@ -375,7 +376,7 @@ template <class T, class LP> struct Backend {
           for (int e = 0; e < 4; ++e) gv[e] = iid_grad(qv[e]);
           st4(g + d0, gv, nv);
         }
-        l = iid_value(dot(q, q));
+        l = (double)iid_value(dot(q, q));
         break;
       }
       case MODEL_FUNNEL: {
@@ -395,7 +396,7 @@ template <class T, class LP> struct Backend {
           for (int e = 0; e < 4; ++e) gv[e] = (d0 + e == 0) ? funnel_grad_v(v, S, ex, M.D) : funnel_grad_x(qv[e], ex);
           st4(g + d0, gv, nv);
         }
-        l = funnel_value(v, S, ex, M.D);
+        l = (double)funnel_value(v, S, ex, M.D);
         break;
       }
       case MODEL_GAUSSIAN: {
@@ -406,7 +407,7 @@ template <class T, class LP> struct Backend {
           st4(g + d0, gv, nv);
         }
         lp.sync();
-        l = T(0.5) * dot(q, g);
+        l = (double)(T(0.5) * dot(q, g));
         break;
       }
       case MODEL_LOGISTIC: {
@@ -429,8 +430,7 @@ template <class T, class LP> struct Backend {
           for (int e = 0; e < 4; ++e) gv[e] = fma_(-M.tau, qv[e], acc[e]);
           st4(g + d0, gv, nv);
         }
-        T ls = T(0);
-        if (M.stage_ld) {  // tensor path: partials are ~1e5 in magnitude, summed in Float64
+        if (M.stage_ld) {  // tensor path: partials are ~1e5..1e7 in magnitude, summed and kept in Float64
           double lsd = 0.0;
           for (int b = 0; b < M.stage_nb; ++b) lsd = lsd + M.stage_ld[b * rows + row];
           if (M.lin_w) {  // linear part of Σ log σ(η̃): ½ Σ_i η̃_i = ½ colsum(X̃)·q
@@ -443,14 +443,15 @@ template <class T, class LP> struct Backend {
             }
             lsd = fma_(0.5, lp.reduce(part), lsd);
           }
-          ls = T(lsd);
+          l = fma_(-0.5 * (double)M.tau, (double)dot(q, q), lsd);
         } else {
+          T ls = T(0);
           for (int b = 0; b < M.stage_nb; ++b) ls = ls + M.stage_l[b * rows + row];
+          l = (double)fma_(T(-0.5) * M.tau, dot(q, q), ls);
         }
-        l = fma_(T(-0.5) * M.tau, dot(q, q), ls);
         break;
       }
-      default: l = lim<T>::nan();
+      default: l = lim<double>::nan();
     }
     lp.sync();
     return l;
@@ -538,7 +539,7 @@ template <class T, class LP> struct Backend {
     for (int d = lp.first(); d < M.D; d += lp.stride()) {
       o[d] = (double)q[d]; o[blk + d] = (double)p[d]; o[2 * blk + d] = (double)g[d];
     }
-    if (lp.lane0()) M.bare_out[3 * blk + c] = (double)get_lq(slot);
+    if (lp.lane0()) M.bare_out[3 * blk + c] = get_lq(slot);
   }
   // set_positions: q -> slot (and staging); ≙ src/warmup.jl:119 / random_position! :73
   BN_HD void load_position(int slot, uint64_t seed, uint32_t gchain) const {

@@ -114,7 +114,7 @@ template <class T, class X> struct EngineCore {
     M.model_kind = MODEL_NONE;
     const size_t CD = size_t(M.C) * M.Dp;
     M.zs = x.template alloc<T>(CD * M.S * 3);
-    M.zlq = x.template alloc<T>(size_t(M.C) * M.S);
+    M.zlq = x.template alloc<double>(size_t(M.C) * M.S);
     M.st_rho = x.template alloc<T>(CD * M.L);
     M.st_psf = x.template alloc<T>(CD * M.L);
     M.m_rho = x.template alloc<T>(CD); M.m_psm = x.template alloc<T>(CD); M.m_psp = x.template alloc<T>(CD);
@@ -128,9 +128,9 @@ template <class T, class X> struct EngineCore {
       if (x.check(err)) return BNUTS_ERR_CUDA;
     }
     x.zero(M.zs, CD * M.S * 3 * sizeof(T));
-    x.zero(M.zlq, size_t(M.C) * M.S * sizeof(T));
+    x.zero(M.zlq, size_t(M.C) * M.S * sizeof(double));
     x.zero(M.cs, size_t(M.C) * sizeof(ChainState<T>));
-    rp.max_depth = c.max_depth; rp.min_delta = T(c.min_delta); rp.seed = c.seed;
+    rp.max_depth = c.max_depth; rp.min_delta = c.min_delta; rp.seed = c.seed;
     rp.chain_offset = c.chain_offset; rp.n_chains = c.n_chains; rp.n_slots = M.S;
     std::vector<double> ones(size_t(M.C) * M.D, 1.0);
     set_metric(nullptr);

@@ -110,7 +110,7 @@ template <class T> __global__ void k_gather_state(EngineMem<T> M, double* o) {
     o[(int64_t)c * M.D + d] = (double)q[d];
     o[n + (int64_t)c * M.D + d] = (double)q[2 * M.Dp + d];
   }
-  if (lane == 0) o[2 * n + c] = (double)M.zlq[(int64_t)c * M.S + s];
+  if (lane == 0) o[2 * n + c] = M.zlq[(int64_t)c * M.S + s];
 }
 
 // ------------------------------------------------------------------ row-sharded mode

@@ -182,7 +182,10 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
     const double bound = 0.5 * std::sqrt(double(tc.N) * double(eng.reduce_world()) * double(M.D));
     // BNUTS_TC_DEBUG_NOCHECK=1: timing experiments with ablated kernel builds (-DBNUTS_TC_DEBUG, wrong results by design)
     const char* nochk = std::getenv("BNUTS_TC_DEBUG_NOCHECK");
-    if (!(n2 <= bound * bound) && !(nochk && std::atoi(nochk) != 0)) {
+    // D > 128 (k_logistic_tc256) ALWAYS works about a reference point (zero until one is set) and has no exact
+    // alternative to fall back to: any finite point nearer to the chains than the current one improves the operand
+    // β − β₀, so a point that is not yet at the mode is accepted there (callers iterate: optimise, set, optimise, set)
+    if (!(n2 <= bound * bound) && tc.variant != 256 && !(nochk && std::atoi(nochk) != 0)) {
       err = "reference point rejected: |grad| = " + std::to_string(std::sqrt(n2)) + " exceeds sqrt(N D)/2 = " +
             std::to_string(bound) + " (not at the mode); exact three-term path kept";
       return BNUTS_ERR_INVALID_ARGUMENT;

@@ -66,26 +66,28 @@ template <class T> struct ChainState {
   int32_t slot_cur;    // slot holding the chain's current (q, ∇ℓ, ℓ)
   int32_t slot_new;    // slot receiving the leapfrog in flight
   // ---- transition-local (≙ locals of sample_trajectory, src/tree.jl:388-393)
-  T pi0, teps;
+  // Energy scalars (ℓ, H, Δ, log-weights) are Float64 for both engine types: the reference is Float64-only and an fp32 ℓ of
+  // magnitude N·log 2 has an ulp of 0.03 at N = 1e6, 8 at N = 1e8.  The fp32 variant is fp32 state VECTORS and vector arithmetic.
+  double pi0; T teps;
   uint32_t dirs;
   int32_t depth, fwd, n, sp;
   int32_t i_cur, i_minus, i_plus;
   int32_t slot_minus, slot_plus, slot_zeta, i_zeta;
-  T omega, pi_zeta, v_lsa;
+  double omega, pi_zeta, v_lsa;
   int32_t v_steps;
   int32_t n_exp;       // merge exponentials consumed so far in this transition (index into the injected stream)
   // ---- running totals
   int64_t tot_leapfrogs, tot_transitions, tot_divergences;
   // ---- step size search (≙ locals of find_initial_stepsize, src/stepsize.jl:111-126)
   double ss_e0, ss_A0, ss_lo, ss_hi, ss_try, ss_s, ss_a, ss_Cf;
-  T ss_target;
+  double ss_target;
   int32_t ss_stage, ss_iter;
   int32_t bare_src;  // slot to restore after the bare integrator
   // ---- local optimum search (≙ warmup!(FindLocalOptimum), src/warmup.jl:152-186)
   double opt_alpha, opt_f, opt_dd, opt_lambda;
   int32_t opt_iter, opt_bt, opt_tries, opt_pad;
   // ---- subtree stack (one entry per pending left sibling)
-  T st_omega[MAX_LEVELS], st_pi[MAX_LEVELS], st_vlsa[MAX_LEVELS];
+  double st_omega[MAX_LEVELS], st_pi[MAX_LEVELS], st_vlsa[MAX_LEVELS];
   int32_t st_first_i[MAX_LEVELS], st_slot[MAX_LEVELS], st_izeta[MAX_LEVELS];
 };
 
@@ -95,7 +97,7 @@ struct OptP { double penalty; int32_t iterations; int32_t pad; };   // ≙ FindL
 
 template <class T> struct RunParams {
   int32_t max_depth;
-  T min_delta;
+  double min_delta;
   uint64_t seed;
   int32_t chain_offset;
   int32_t n_chains;
@@ -138,14 +140,14 @@ template <class T> BN_HD void da_adapt(ChainState<T>& s, const DualAveragingP& P
 
 // The backend B provides, for the chain it is bound to:
 //   bool lane0(); void sync();
-//   T    get_lq(slot); void set_lq(slot, T);
+//   double get_lq(slot); void set_lq(slot, double);      (energy scalars are Float64 for both engine types)
 //   void start_tx(slot, const double* inj_p_or_null, seed, gchain, t, T* Ksum)
 //            p <- W .* N(0,1) (or injected); p# <- M^-1 p; main rho <- p; main p#- = p#+ <- p#; Ksum = sum p# p
 //   void pre_kick_drift(src_slot, dst_slot, T eh, T eps)       // ≙ src/kinetic_energy.jl:146-150
 //   T    post_kick(slot, T eh, int push_level)                 // ≙ :159-161 + kinetic energy + p#; returns sum p# p
 //   void merge_sub(int L, int rhoR_is_leaf, int slot_leaf, bool fwd, T* dm, T* dp)   // stack level merge, in place
 //   void merge_top(int rhoR_is_leaf, int slot_leaf, bool fwd, T* dm, T* dp)          // main tree merge, in place
-//   T    model_grad(slot)            // elementwise models: evaluate now; GEMM models: finalize staged result
+//   double model_grad(slot)          // elementwise models: evaluate now; GEMM models: finalize staged result
 //   void emit_draw(slot, n_done)     // copy q out as Float64
 //   void bare_load_p(slot); void bare_emit(slot);
 //   void opt_trial(src, dst, T alpha, T lambda)   q_dst = q + alpha (∇ℓ − λ q), staged for its gradient
@@ -165,10 +167,10 @@ template <class T, class B> struct Machine {
   BN_HD uint32_t gchain() const { return (uint32_t)(rp.chain_offset + c); }
 
   // ≙ logdensity(H, z), src/kinetic_energy.jl:107-112
-  BN_HD static T hamiltonian(T lq, T Ksum) {
-    if (!isfinite_(lq)) return -lim<T>::inf();
+  BN_HD static double hamiltonian(double lq, T Ksum) {
+    if (!isfinite_(lq)) return -lim<double>::inf();
     const T K = T(0.5) * Ksum;
-    return lq - (isfinite_(K) ? K : lim<T>::inf());
+    return lq - (isfinite_(K) ? (double)K : lim<double>::inf());
   }
 
   BN_HD int32_t alloc_slot() const {
@@ -183,16 +185,16 @@ template <class T, class B> struct Machine {
   // The reference consumes one randexp(rng) per call with logprob2 < 0, in call order (post-order over the merges of the
   // recursion, which is the order this machine performs them in); an injected stream is consumed the same way, the
   // engine's own draws are a pure function of the merge's position in the tree.
-  BN_HD bool select_second(T logprob2, uint32_t j, uint32_t k, uint32_t n) {
-    if (logprob2 >= T(0)) return true;
-    T e;
+  BN_HD bool select_second(double logprob2, uint32_t j, uint32_t k, uint32_t n) {
+    if (logprob2 >= 0.0) return true;
+    T e;   // the variate is a T (the engine type's stream); the comparison is Float64
     const bool injected = rp.inj_exps && rp.inj_T > 0 && s.t >= rp.inj_start && s.t < rp.inj_start + (uint32_t)rp.inj_T;
     if (injected && s.n_exp < rp.inj_nexp)
       e = T(rp.inj_exps[((int64_t)(s.t - rp.inj_start) * rp.n_chains + c) * rp.inj_nexp + s.n_exp]);
     else
       e = std_exponential(rp.seed, gchain(), s.t, j, k, n, T(0));
     s.n_exp += 1;
-    return e > -logprob2;
+    return (double)e > -logprob2;
   }
 
   // ---------------------------------------------------------------- transition entry
@@ -216,8 +218,8 @@ template <class T, class B> struct Machine {
     T Ksum;
     b.start_tx(s.slot_cur, ip, rp.seed, gchain(), s.t, &Ksum);
     s.pi0 = hamiltonian(b.get_lq(s.slot_cur), Ksum);
-    s.slot_zeta = s.slot_cur; s.omega = T(0); s.pi_zeta = s.pi0; s.i_zeta = 0;
-    s.v_lsa = -lim<T>::inf(); s.v_steps = 0; s.n_exp = 0;
+    s.slot_zeta = s.slot_cur; s.omega = 0.0; s.pi_zeta = s.pi0; s.i_zeta = 0;
+    s.v_lsa = -lim<double>::inf(); s.v_steps = 0; s.n_exp = 0;
     s.slot_minus = s.slot_plus = s.slot_cur;
     s.i_minus = s.i_plus = 0;
     s.depth = 0;
@@ -245,15 +247,15 @@ template <class T, class B> struct Machine {
 
   // fold the visited statistic of an invalid subtree up through its pending left
   // siblings and into the tree (src/tree.jl:347-348 on the way out, :414 at the top)
-  BN_HD void fold_invalid(T acc_v) {
+  BN_HD void fold_invalid(double acc_v) {
     for (int k = s.sp - 1; k >= 0; --k) acc_v = logaddexp_(g->st_vlsa[k], acc_v);
     s.v_lsa = logaddexp_(s.v_lsa, acc_v);
   }
 
   // ≙ second half of leapfrog + leaf + every merge this leaf completes
   BN_HD void post_leaf() {
-    T lq = b.model_grad(s.slot_new);
-    if (!isfinite_(lq)) lq = -lim<T>::inf();  // ≙ evaluate_ℓ!, src/kinetic_energy.jl:80-84
+    double lq = b.model_grad(s.slot_new);
+    if (!isfinite_(lq)) lq = -lim<double>::inf();  // ≙ evaluate_ℓ!, src/kinetic_energy.jl:80-84
     b.set_lq(s.slot_new, lq);
     const T e = s.fwd ? s.teps : -s.teps;
     const int32_t n1 = s.n + 1;
@@ -263,17 +265,17 @@ template <class T, class B> struct Machine {
     s.i_cur += s.fwd ? 1 : -1;
     s.n = n1;
     // ≙ leaf, src/NUTS.jl:176-191
-    const T Hz = hamiltonian(lq, Ksum);
-    const T delta = Hz - s.pi0;
+    const double Hz = hamiltonian(lq, Ksum);
+    const double delta = Hz - s.pi0;
     const bool isdiv = delta < rp.min_delta;
-    T acc_v = (delta < T(0)) ? delta : T(0);  // ≙ leaf_acceptance_statistic, src/NUTS.jl:76-78
+    double acc_v = (delta < 0.0) ? delta : 0.0;  // ≙ leaf_acceptance_statistic, src/NUTS.jl:76-78
     s.v_steps += 1;
     if (isdiv) {  // ≙ InvalidTree(i′), src/tree.jl:332,340,348,417
       fold_invalid(acc_v);
       finish(s.i_cur, s.i_cur);
       return;
     }
-    T acc_omega = delta, acc_pi = Hz;
+    double acc_omega = delta, acc_pi = Hz;
     int32_t acc_slot = s.slot_cur, acc_iz = s.i_cur, acc_first = s.i_cur;
     int rhoR_is_leaf = 1;
     int m = 0;
@@ -291,9 +293,9 @@ template <class T, class B> struct Machine {
         finish(left, s.i_cur);
         return;
       }
-      const T wl = g->st_omega[L];
-      const T w = logaddexp_(wl, acc_omega);
-      const T logprob2 = acc_omega - w;  // unbiased, src/tree.jl:261-263 with bias = false
+      const double wl = g->st_omega[L];
+      const double w = logaddexp_(wl, acc_omega);
+      const double logprob2 = acc_omega - w;  // unbiased, src/tree.jl:261-263 with bias = false
       if (!select_second(logprob2, (uint32_t)s.depth, (uint32_t)k, (uint32_t)n1)) {
         acc_slot = g->st_slot[L]; acc_pi = g->st_pi[L]; acc_iz = g->st_izeta[L];
       }
@@ -316,12 +318,12 @@ template <class T, class B> struct Machine {
   }
 
   // ≙ sample_trajectory after adjacent_tree returned valid, src/tree.jl:414-438
-  BN_HD void top_merge(T acc_v, T acc_omega, T acc_pi, int32_t acc_slot, int32_t acc_iz, int rhoR_is_leaf) {
+  BN_HD void top_merge(double acc_v, double acc_omega, double acc_pi, int32_t acc_slot, int32_t acc_iz, int rhoR_is_leaf) {
     s.v_lsa = logaddexp_(s.v_lsa, acc_v);
     if (s.fwd) { s.slot_plus = s.slot_cur; s.i_plus = s.i_cur; }
     else       { s.slot_minus = s.slot_cur; s.i_minus = s.i_cur; }
-    const T w = logaddexp_(s.omega, acc_omega);
-    const T logprob2 = acc_omega - s.omega;  // biased progressive, bias = true
+    const double w = logaddexp_(s.omega, acc_omega);
+    const double logprob2 = acc_omega - s.omega;  // biased progressive, bias = true
     if (select_second(logprob2, (uint32_t)s.depth, 0u, 0u)) {
       s.slot_zeta = acc_slot; s.pi_zeta = acc_pi; s.i_zeta = acc_iz;
     }
@@ -336,12 +338,12 @@ template <class T, class B> struct Machine {
   // ≙ tail of sample_tree (src/NUTS.jl:262) + per-transition work of warmup!/mcmc!
   //   (src/warmup.jl:297-303, :325-326)
   BN_HD void finish(int32_t term_left, int32_t term_right) {
-    const T a0 = exp_(s.v_lsa) / T(s.v_steps);  // ≙ acceptance_rate, src/NUTS.jl:84
-    const double a = (double)(a0 < T(1) ? a0 : T(1));
+    const double a0 = exp_(s.v_lsa) / (double)s.v_steps;  // ≙ acceptance_rate, src/NUTS.jl:84
+    const double a = a0 < 1.0 ? a0 : 1.0;
     if (b.lane0()) {
       if (rp.stats) {
         TreeStats st;
-        st.pi = (double)s.pi_zeta; st.acceptance_rate = a;
+        st.pi = s.pi_zeta; st.acceptance_rate = a;
         st.term_left = term_left; st.term_right = term_right;
         st.depth = s.depth; st.steps = s.v_steps;
         rp.stats[(int64_t)c * rp.n_total + s.n_done] = st;
@@ -383,12 +385,12 @@ template <class T, class B> struct Machine {
   BN_HD void search_fail() { s.status = ST_STEPSIZE_SEARCH; s.phase = PH_IDLE; }
   // ≙ find_initial_stepsize / find_crossing_stepsize / bisect_stepsize, src/stepsize.jl:51-126
   BN_HD void search_post() {
-    T lq = b.model_grad(s.slot_new);
-    if (!isfinite_(lq)) lq = -lim<T>::inf();
+    double lq = b.model_grad(s.slot_new);
+    if (!isfinite_(lq)) lq = -lim<double>::inf();
     b.set_lq(s.slot_new, lq);
     const T e = T(s.ss_try);
     const T Ksum = b.post_kick(s.slot_new, T(0.5) * e, -1);
-    const double A = (double)exp_(hamiltonian(lq, Ksum) - s.ss_target);  // ≙ local_acceptance_ratio
+    const double A = exp_(hamiltonian(lq, Ksum) - s.ss_target);  // ≙ local_acceptance_ratio
     const SearchP& P = rp.search;
     const bool inside = (P.a_min <= A) && (A <= P.a_max);
     if (s.ss_stage == 0) {
@@ -439,11 +441,11 @@ template <class T, class B> struct Machine {
   }
   BN_HD void opt_begin() {
     s.slot_minus = s.slot_plus = s.slot_zeta = s.slot_cur; s.sp = 0;
-    const T lq = b.get_lq(s.slot_cur);
+    const double lq = b.get_lq(s.slot_cur);
     if (!isfinite_(lq)) { opt_restart(); return; }
     T dd, qq;
     b.opt_norms(s.slot_cur, T(s.opt_lambda), &dd, &qq);
-    s.opt_f = (double)lq - 0.5 * s.opt_lambda * (double)qq;
+    s.opt_f = lq - 0.5 * s.opt_lambda * (double)qq;
     s.opt_dd = (double)dd;
     s.opt_alpha = 1.0 / (1.0 + sqrt_(s.opt_dd));       // first step no longer than 1
     s.opt_bt = 0;
@@ -458,8 +460,8 @@ template <class T, class B> struct Machine {
     s.phase = PH_OPT_REEVAL;
   }
   BN_HD void opt_reeval_post() {
-    T lq = b.model_grad(s.slot_cur);
-    if (!isfinite_(lq)) lq = -lim<T>::inf();
+    double lq = b.model_grad(s.slot_cur);
+    if (!isfinite_(lq)) lq = -lim<double>::inf();
     b.set_lq(s.slot_cur, lq);
     s.opt_iter = 0;
     opt_begin();
@@ -474,12 +476,12 @@ template <class T, class B> struct Machine {
     s.phase = PH_IDLE;
   }
   BN_HD void opt_post() {
-    T lq = b.model_grad(s.slot_new);
-    if (!isfinite_(lq)) lq = -lim<T>::inf();
+    double lq = b.model_grad(s.slot_new);
+    if (!isfinite_(lq)) lq = -lim<double>::inf();
     b.set_lq(s.slot_new, lq);
     T ddn, qqn, dod;
     b.opt_dots(s.slot_cur, s.slot_new, T(s.opt_lambda), &ddn, &qqn, &dod);
-    const double fn = isfinite_(lq) ? (double)lq - 0.5 * s.opt_lambda * (double)qqn : -lim<double>::inf();
+    const double fn = isfinite_(lq) ? lq - 0.5 * s.opt_lambda * (double)qqn : -lim<double>::inf();
     const bool accept = fn >= s.opt_f + 1e-4 * s.opt_alpha * s.opt_dd;   // Armijo; false for -Inf / NaN
     if (accept) {
       const double curv = s.opt_dd - (double)dod;      // -(s·y)/alpha with s = alpha d, y = d' - d
@@ -511,8 +513,8 @@ template <class T, class B> struct Machine {
     s.phase = PH_BARE_LEAF;
   }
   BN_HD void bare_post() {
-    T lq = b.model_grad(s.slot_new);
-    if (!isfinite_(lq)) lq = -lim<T>::inf();
+    double lq = b.model_grad(s.slot_new);
+    if (!isfinite_(lq)) lq = -lim<double>::inf();
     b.set_lq(s.slot_new, lq);
     (void)b.post_kick(s.slot_new, T(0.5) * s.teps, -1);
     s.slot_cur = s.slot_new;
@@ -530,8 +532,8 @@ template <class T, class B> struct Machine {
   // ---------------------------------------------------------------- set_positions
   // ≙ initialize_warmup_state, src/warmup.jl:119-124 (q already written to slot_cur)
   BN_HD void eval_post() {
-    T lq = b.model_grad(s.slot_cur);
-    if (!isfinite_(lq)) lq = -lim<T>::inf();
+    double lq = b.model_grad(s.slot_cur);
+    if (!isfinite_(lq)) lq = -lim<double>::inf();
     b.set_lq(s.slot_cur, lq);
     s.status = isfinite_(lq) ? 0 : ST_NONFINITE_START;
     s.phase = PH_IDLE;

@@ -143,14 +143,17 @@ template <class T> struct Model {
 
 // ------------------------------------------------------------------ types
 // ≙ EvaluatedLogDensity + PhasePoint, src/hamiltonian.jl:237-276
-template <class T> struct PhasePoint { T* q; T* p; T* g; T lq; };
+// Energy scalars (ℓ, H, Δ, log-weights) are Float64 for BOTH engine types: the reference is Float64-only, and an fp32 ℓ of
+// magnitude N·log 2 has an ulp of 0.03 at N = 1e6 and of 8 at N = 1e8 — no acceptance test survives that.  The fp32 variant
+// is fp32 STATE VECTORS (q, p, ∇ℓ, metric) and vector arithmetic; what a target's evaluation returns in T is widened once.
+template <class T> struct PhasePoint { T* q; T* p; T* g; double lq; };
 // ≙ GeneralizedTurnStatistic, src/NUTS.jl:93-97
 template <class T> struct TurnStat { const T* psm; const T* psp; const T* rho; };
 // ≙ AcceptanceStatistic, src/NUTS.jl:58-66
-template <class T> struct Visited { T lsa; int32_t steps; };
+template <class T> struct Visited { double lsa; int32_t steps; };
 // proposal ζ plus what TreeStatisticsNUTS needs from it (π = logdensity(H, ζ), src/NUTS.jl:262)
-template <class T> struct Proposal { PhasePoint<T> z; T pi; int32_t idx; };
-template <class T> struct SubTree { Proposal<T> zeta; T omega; TurnStat<T> tau; PhasePoint<T> zlast; int32_t ilast; };
+template <class T> struct Proposal { PhasePoint<T> z; double pi; int32_t idx; };
+template <class T> struct SubTree { Proposal<T> zeta; double omega; TurnStat<T> tau; PhasePoint<T> zlast; int32_t ilast; };
 // ≙ InvalidTree, src/tree.jl:278-300
 struct Invalid { bool flag; int32_t left, right; };
 
@@ -175,7 +178,8 @@ template <class T> struct Engine {
   bnuts_config cfg{};
   int C = 0, D = 0;
   Model<T> model;
-  std::vector<T> q, g, lq;       // [C][D], [C][D], [C]
+  std::vector<T> q, g;           // [C][D], [C][D]
+  std::vector<double> lq;        // [C]
   std::vector<T> Minv, W;        // [C][D]   (GaussianKineticEnergy, src/hamiltonian.jl:33-38)
   // shared dense metric (≙ the dense GaussianKineticEnergy constructor kept as a comment at
   // src/hamiltonian.jl:44): M⁻¹ [D][D] and the momentum factor W = L⁻ᵀ with M⁻¹ = L Lᵀ, so W Wᵀ = M.
@@ -258,10 +262,10 @@ template <class T> T kinetic_energy(const Ham<T>& H, const T* p) {
   return T(0.5) * butterfly(part);
 }
 // ≙ logdensity(H, z), src/kinetic_energy.jl:107-112
-template <class T> T logdensity(const Ham<T>& H, const PhasePoint<T>& z) {
-  if (!isfinite_(z.lq)) return -bn::lim<T>::inf();
+template <class T> double logdensity(const Ham<T>& H, const PhasePoint<T>& z) {
+  if (!isfinite_(z.lq)) return -bn::lim<double>::inf();
   const T K = kinetic_energy(H, z.p);
-  return z.lq - (isfinite_(K) ? K : bn::lim<T>::inf());
+  return z.lq - (isfinite_(K) ? double(K) : bn::lim<double>::inf());
 }
 // ≙ calculate_p♯, src/kinetic_energy.jl:39-46
 template <class T> T* calculate_psharp(Arena<T>& A, const Ham<T>& H, const T* p) {
@@ -273,11 +277,11 @@ template <class T> T* calculate_psharp(Arena<T>& A, const Ham<T>& H, const T* p)
   return ps;
 }
 // ≙ evaluate_ℓ!, src/kinetic_energy.jl:72-85 (non-finite ℓ -> -Inf, ∇ aliased to q)
-template <class T> T evaluate_l(ChainCtx<T>& X, const Ham<T>& H, const T* q, T* g) {
+template <class T> double evaluate_l(ChainCtx<T>& X, const Ham<T>& H, const T* q, T* g) {
   const T lq = H.E->model.eval(q, g, X.scratch);
-  if (isfinite_(lq)) return lq;
+  if (isfinite_(lq)) return double(lq);
   for (int d = 0; d < H.E->D; ++d) g[d] = q[d];
-  return -bn::lim<T>::inf();
+  return -bn::lim<double>::inf();
 }
 // ≙ leapfrog, src/kinetic_energy.jl:126-163 (and the stack twin :164-195)
 template <class T> PhasePoint<T> leapfrog(ChainCtx<T>& X, const Ham<T>& H, const PhasePoint<T>& z, T eps) {
@@ -305,7 +309,7 @@ template <class T> PhasePoint<T> leapfrog(ChainCtx<T>& X, const Ham<T>& H, const
 
 // ------------------------------------------------------------------ NUTS (src/NUTS.jl, src/tree.jl)
 template <class T> struct Trajectory {  // ≙ TrajectoryNUTS, src/NUTS.jl:5-16
-  T pi0, eps, min_delta;
+  double pi0; T eps; double min_delta;
   uint64_t seed;
   uint32_t chain, t;  // RNG position
   const double* exps = nullptr;  // scripted exponentials of this transition (bnuts_inject), or null
@@ -316,9 +320,9 @@ template <class T> struct Trajectory {  // ≙ TrajectoryNUTS, src/NUTS.jl:5-16
 // ≙ leaf, src/NUTS.jl:176-191 (+ leaf_acceptance_statistic :76-78, leaf_turn_statistic :113-116)
 template <class T>
 void leaf(ChainCtx<T>& X, const Ham<T>& H, const Trajectory<T>& tr, const PhasePoint<T>& z, bool is_initial,
-          int32_t idx, Proposal<T>* zeta, T* omega, TurnStat<T>* tau, Visited<T>* v, bool* isdiv) {
-  const T Hz = is_initial ? tr.pi0 : logdensity(H, z);
-  const T delta = is_initial ? T(0) : Hz - tr.pi0;
+          int32_t idx, Proposal<T>* zeta, double* omega, TurnStat<T>* tau, Visited<T>* v, bool* isdiv) {
+  const double Hz = is_initial ? tr.pi0 : logdensity(H, z);
+  const double delta = is_initial ? 0.0 : Hz - tr.pi0;
   *isdiv = delta < tr.min_delta;
   if (g_trace) {
     if (!is_initial) trace_min(g_trace->min_div, std::fabs(double(delta) - double(tr.min_delta)));
@@ -328,8 +332,8 @@ void leaf(ChainCtx<T>& X, const Ham<T>& H, const Trajectory<T>& tr, const PhaseP
     for (int d = 0; d < H.E->D; ++d) g2 += double(z.g[d]) * double(z.g[d]);
     if (g2 > g_trace->grad_sq && std::isfinite(g2)) g_trace->grad_sq = g2;
   }
-  if (is_initial) { v->lsa = -bn::lim<T>::inf(); v->steps = 0; }
-  else { v->lsa = (delta < T(0)) ? delta : T(0); v->steps = 1; }
+  if (is_initial) { v->lsa = -bn::lim<double>::inf(); v->steps = 0; }
+  else { v->lsa = (delta < 0.0) ? delta : 0.0; v->steps = 1; }
   zeta->z = z; zeta->pi = Hz; zeta->idx = idx;
   *omega = delta;
   if (*isdiv) { tau->psm = tau->psp = tau->rho = nullptr; return; }
@@ -370,25 +374,25 @@ template <class T> bool is_turning(int D, const TurnStat<T>& tau) {
   return (dm < T(0)) | (dp < T(0));
 }
 // ≙ rand_bool_logprob, src/NUTS.jl:32-34 — the draw is consumed only if logprob < 0
-template <class T> bool rand_bool_logprob(const Trajectory<T>& tr, T logprob, uint32_t j, uint32_t k, uint32_t n) {
+template <class T> bool rand_bool_logprob(const Trajectory<T>& tr, double logprob, uint32_t j, uint32_t k, uint32_t n) {
   // "logprob >= 0" is a decision too: it settles whether a draw is consumed, which shifts a scripted stream
   if (g_trace && std::isfinite(double(logprob))) trace_min(g_trace->min_sel, std::fabs(double(logprob)));
-  if (logprob >= T(0)) return true;
-  T e;
+  if (logprob >= 0.0) return true;
+  T e;   // the variate itself is a T (the engine type's stream); the comparison is Float64
   if (tr.exps && tr.n_exp < tr.n_exps) e = T(tr.exps[tr.n_exp]);   // scripted stream: consumed in call order
   else e = bn::std_exponential(tr.seed, tr.chain, tr.t, j, k, n, T(0));
   tr.n_exp += 1;
   if (g_trace) trace_min(g_trace->min_sel, std::fabs(double(e) + double(logprob)));
-  return e > -logprob;
+  return double(e) > -logprob;
 }
 // ≙ combine_proposals_and_logweights, src/tree.jl:238-245 with
 //   biased_progressive_logprob2 (src/tree.jl:261-263) and combine_proposals (src/NUTS.jl:40-45)
 template <class T>
-void combine_proposals_and_logweights(const Trajectory<T>& tr, const Proposal<T>& z1, const Proposal<T>& z2, T w1,
-                                      T w2, bool is_doubling, uint32_t j, uint32_t k, uint32_t n,
-                                      Proposal<T>* z, T* w) {
+void combine_proposals_and_logweights(const Trajectory<T>& tr, const Proposal<T>& z1, const Proposal<T>& z2, double w1,
+                                      double w2, bool is_doubling, uint32_t j, uint32_t k, uint32_t n,
+                                      Proposal<T>* z, double* w) {
   *w = logaddexp_(w1, w2);
-  const T logprob2 = w2 - (is_doubling ? w1 : *w);
+  const double logprob2 = w2 - (is_doubling ? w1 : *w);
   *z = rand_bool_logprob(tr, logprob2, j, k, n) ? z2 : z1;
 }
 
@@ -430,7 +434,7 @@ void sample_trajectory(ChainCtx<T>& X, const Ham<T>& H, const Trajectory<T>& tr,
                        int max_depth, uint32_t directions, Proposal<T>* zeta_out, Visited<T>* v_out,
                        Invalid* term_out, int32_t* depth_out) {
   Proposal<T> zeta;
-  T omega;
+  double omega;
   TurnStat<T> tau;
   Visited<T> v;
   bool isdiv;
@@ -478,7 +482,7 @@ bnuts_tree_stats sample_tree(Engine<T>& E, ChainCtx<T>& X, int c, double eps, ui
   } else {  // ≙ rand_p!, src/kinetic_energy.jl:63: p = W .* randn
     H.draw_momentum(z.p, E.seed, gchain, t);
   }
-  Trajectory<T> tr{logdensity(H, z), T(eps), T(E.cfg.min_delta), E.seed, gchain, t};
+  Trajectory<T> tr{logdensity(H, z), T(eps), double(E.cfg.min_delta), E.seed, gchain, t};
   if (injected && E.inj_nexp > 0) { tr.exps = E.inj_exps.data() + (it * E.C + c) * size_t(E.inj_nexp); tr.n_exps = E.inj_nexp; }
   Proposal<T> zeta;
   Visited<T> v;
@@ -489,8 +493,8 @@ bnuts_tree_stats sample_tree(Engine<T>& E, ChainCtx<T>& X, int c, double eps, ui
   g_trace = nullptr;
   bnuts_tree_stats st;
   st.pi = double(zeta.pi);
-  const T a = exp_(v.lsa) / T(v.steps);  // ≙ acceptance_rate, src/NUTS.jl:84
-  st.acceptance_rate = double(a < T(1) ? a : T(1));
+  const double a = exp_(v.lsa) / double(v.steps);  // ≙ acceptance_rate, src/NUTS.jl:84
+  st.acceptance_rate = a < 1.0 ? a : 1.0;
   st.term_left = term.left; st.term_right = term.right;
   st.depth = depth; st.steps = v.steps;
   for (int d = 0; d < D; ++d) { E.q[size_t(c) * D + d] = zeta.z.q[d]; E.g[size_t(c) * D + d] = zeta.z.g[d]; }
@@ -517,11 +521,11 @@ DAState da_adapt(const bnuts_dual_averaging& P, DAState A, double a) {
 
 // ≙ local_acceptance_ratio :150-160 — A(eps) = exp(H(leapfrog(z, eps)) - H(z))
 template <class T> struct LocalAcceptance {
-  ChainCtx<T>* X; Ham<T> H; PhasePoint<T> z; T target;
+  ChainCtx<T>* X; Ham<T> H; PhasePoint<T> z; double target;
   double operator()(double eps) const {
     X->arena.reset();
     const PhasePoint<T> zn = leapfrog(*X, H, z, T(eps));
-    return double(exp_(logdensity(H, zn) - target));
+    return exp_(logdensity(H, zn) - target);
   }
 };
 // ≙ find_crossing_stepsize :51-72, bisect_stepsize :83-102, find_initial_stepsize :111-126
@@ -677,7 +681,7 @@ template <class T> int32_t initial_stepsize(Engine<T>& E, const bnuts_stepsize_s
     const uint32_t gchain = uint32_t(E.cfg.chain_offset + c);
     H.draw_momentum(p.data(), E.seed, gchain, t);  // ≙ src/warmup.jl:195
     PhasePoint<T> z{&E.q[size_t(c) * D], p.data(), &E.g[size_t(c) * D], E.lq[c]};
-    const T target = logdensity(H, z);
+    const double target = logdensity(H, z);
     if (!isfinite_(target)) { E.status[c] = BNUTS_ERR_NONFINITE_START; bad += 1; continue; }
     LocalAcceptance<T> A{&X, H, z, target};
     double eps = 0;
@@ -707,7 +711,7 @@ template <class T> int32_t find_local_optimum(Engine<T>& E, double penalty, int3
     const uint32_t gchain = uint32_t(E.cfg.chain_offset + c);
     std::vector<T> q(&E.q[size_t(c) * D], &E.q[size_t(c) * D] + D), g(&E.g[size_t(c) * D], &E.g[size_t(c) * D] + D);
     std::vector<T> qn(D), gn(D), dv(D), dn(D);
-    T lq = E.lq[c];
+    double lq = E.lq[c];
     double lambda = penalty;
     int tries = 0, iter = 0;
     bool failed = false;
@@ -725,18 +729,18 @@ template <class T> int32_t find_local_optimum(Engine<T>& E, double penalty, int3
       const T lam = T(lambda);
       for (int d = 0; d < D; ++d) dv[d] = fma_(-lam, q[d], g[d]);
       double dd = double(dot_warp(dv.data(), dv.data(), D));
-      double f = double(lq) - 0.5 * lambda * double(dot_warp(q.data(), q.data(), D));
+      double f = lq - 0.5 * lambda * double(dot_warp(q.data(), q.data(), D));
       double alpha = 1.0 / (1.0 + bn::sqrt_(dd));
       int bt = 0;
       while (iter < iterations && dd > 0.0) {
         const T al = T(alpha);
         for (int d = 0; d < D; ++d) qn[d] = fma_(al, dv[d], q[d]);
-        T lqn = evaluate_l(X, H, qn.data(), gn.data());
+        const double lqn = evaluate_l(X, H, qn.data(), gn.data());
         for (int d = 0; d < D; ++d) dn[d] = fma_(-lam, qn[d], gn[d]);
         const T ddn = dot_warp(dn.data(), dn.data(), D);
         const T qqn = dot_warp(qn.data(), qn.data(), D);
         const T dod = dot_warp(dv.data(), dn.data(), D);
-        const double fn = isfinite_(lqn) ? double(lqn) - 0.5 * lambda * double(qqn) : -bn::lim<double>::inf();
+        const double fn = isfinite_(lqn) ? lqn - 0.5 * lambda * double(qqn) : -bn::lim<double>::inf();
         if (fn >= f + 1e-4 * alpha * dd) {
           const double curv = dd - double(dod);
           double an = curv > 0.0 ? alpha * dd / curv : 2.0 * alpha;
@@ -792,7 +796,7 @@ template <class T> Engine<T>* make_engine(const bnuts_config& cfg) {
   auto* E = new Engine<T>();
   E->cfg = cfg; E->C = cfg.n_chains; E->D = cfg.dim; E->seed = cfg.seed;
   const size_t n = size_t(E->C) * E->D;
-  E->q.assign(n, T(0)); E->g.assign(n, T(0)); E->lq.assign(E->C, T(0));
+  E->q.assign(n, T(0)); E->g.assign(n, T(0)); E->lq.assign(E->C, 0.0);
   E->Minv.assign(n, T(1)); E->W.assign(n, T(1));  // ≙ κ = I, src/warmup.jl:102
   E->eps.assign(E->C, 1.0); E->status.assign(E->C, 0);
   E->model.D = E->D;
