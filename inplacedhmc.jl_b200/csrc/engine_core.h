@@ -88,6 +88,7 @@ template <class T, class X> struct EngineCore {
   uint32_t* d_inj_dirs = nullptr; double* d_inj_p = nullptr; double* d_inj_exps = nullptr;
   double* d_tmp_cd = nullptr;   // [C][D] scratch (positions / momenta in)
   double* d_tmp_c = nullptr;    // [C]
+  double* d_bare_p = nullptr; double* d_bare_out = nullptr;   // bnuts_leapfrog: momenta in [C][D], (q, p, ∇ℓ, ℓ) out [3][C][D] + [C]
   std::vector<double> h_draws;  // staging when caller strides are not compact
   DenseMetric dm;
   std::vector<double> h_P;      // Gaussian target precision as given by the caller (user coordinates)
@@ -106,7 +107,7 @@ template <class T, class X> struct EngineCore {
 
   int32_t init(const bnuts_config& c) {
     cfg = c;
-    if (c.max_depth > MAX_LEVELS) return fail(BNUTS_ERR_UNSUPPORTED, "max_depth > 20 not supported by the device engine");
+    if (c.max_depth > MAX_LEVELS) return fail(BNUTS_ERR_UNSUPPORTED, "max_depth > 32 not supported (one UInt32 of directions, src/tree.jl:132)");
     int32_t rc = x.init(c.device, err);
     if (rc) return rc;
     M.C = c.n_chains; M.D = c.dim; M.Dp = (c.dim + 31) / 32 * 32;
@@ -145,7 +146,7 @@ template <class T, class X> struct EngineCore {
     if (d_xf_in) { x.free(d_xf_in); x.free(d_xf_out); d_xf_in = d_xf_out = nullptr; }
     void* ptrs[] = {M.zs, M.zlq, M.st_rho, M.st_psf, M.m_rho, M.m_psm, M.m_psp, M.ps_cur, M.Minv, M.W, M.cs,
                     M.stage_q, M.stage_g, M.stage_l, M.stage_ld, M.stage_bh, M.stage_bm, M.stage_bl, M.stage_row, M.draws, d_stats, d_sel, d_eps_hist,
-                    d_inj_dirs, d_inj_p, d_inj_exps, d_tmp_cd, d_tmp_c, model.P, model.X, model.y, model.Xb, model.yf};
+                    d_inj_dirs, d_inj_p, d_inj_exps, d_tmp_cd, d_tmp_c, d_bare_p, d_bare_out, model.P, model.X, model.y, model.Xb, model.yf};
     for (void* p : ptrs) if (p) x.free(p);
     x.shutdown();
   }
@@ -561,6 +562,7 @@ template <class T, class X> struct EngineCore {
   // gradient launch: the launch covers all real requests plus, at worst, a few stale rows nobody reads.  Counts
   // come back through a small ring of pinned slots (async copy + event); the host runs at most LAG steps ahead.
   int32_t run_pipelined(bool pending) {
+    typename X::Range nvtx_range("lockstep loop (pipelined): gradient kernel + k_advance per step");
     constexpr int LAG = 2;
     x.use();
     int64_t np_known = pending ? x.read_count() : -1;   // -1: nothing known yet (first step has no gradient)
@@ -597,6 +599,8 @@ template <class T, class X> struct EngineCore {
     const bool batched = model.batched();
     x.use();
     if (batched && !reduce_on && X::RING > 0) return run_pipelined(pending);
+    typename X::Range nvtx_range(reduce_on ? "lockstep loop (rows sharded): gradient kernel + exchange + k_advance per step"
+                                           : (batched ? "lockstep loop" : "k_advance: every chain to the end of the call"));
     const int iters = batched ? 1 : (1 << 30);
     int64_t np = 0;
     if (pending) np = reduce_on ? x.assign_rows(reduce_view(0), M) : x.read_count();
@@ -673,6 +677,8 @@ template <class T, class X> struct EngineCore {
 
   int32_t transitions(int N, const bnuts_dual_averaging* da, int metric_kind, double lambda, double* chain_out,
                       int64_t sd, int64_t sc, bnuts_tree_stats* stats_out, int64_t ssc, int32_t* sel, double* eps_out) {
+    typename X::Range nvtx_range(da ? (metric_kind == BNUTS_METRIC_DIAG ? "bnuts_warmup_stage (step size + metric)" : "bnuts_warmup_stage (step size)")
+                                    : (metric_kind == BNUTS_METRIC_DIAG ? "bnuts_warmup_stage (fixed step size, metric)" : "bnuts_sample"));
     if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
     if (N <= 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "N must be positive");
     if (metric_kind != BNUTS_METRIC_NONE && metric_kind != BNUTS_METRIC_DIAG)
@@ -714,6 +720,7 @@ template <class T, class X> struct EngineCore {
   }
 
   int32_t set_positions(const double* q) {
+    typename X::Range nvtx_range("bnuts_set_positions");
     if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
     if (q && dm.on) {                       // q̃ = L⁻¹ q
       double* qt = xf_host(q, M.C, dm.dLinvt);
@@ -764,9 +771,11 @@ template <class T, class X> struct EngineCore {
                    double* l_out) {
     if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
     if (!p_in || !eps || nsteps < 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "p_in, eps required");
+    typename X::Range nvtx_range("bnuts_leapfrog");
     const size_t n = size_t(M.C) * M.D;
-    double* d_p = x.template alloc<double>(n);
-    double* d_out = x.template alloc<double>(3 * n + M.C);
+    if (!d_bare_p) { d_bare_p = x.template alloc<double>(n); d_bare_out = x.template alloc<double>(3 * n + M.C); }   // once per engine
+    double* d_p = d_bare_p;
+    double* d_out = d_bare_out;
     if (dm.on) x.d2d(d_p, xf_host(p_in, M.C, dm.dL), n * sizeof(double));   // p̃ = Lᵀ p
     else x.h2d(d_p, p_in, n * sizeof(double));
     x.h2d(d_tmp_c, eps, size_t(M.C) * sizeof(double));
@@ -783,10 +792,10 @@ template <class T, class X> struct EngineCore {
       rc = x.check(err);
     }
     M.bare_p_in = nullptr; M.bare_out = nullptr;
-    x.free(d_p); x.free(d_out);
     return rc;
   }
   int32_t find_initial_stepsize(const bnuts_stepsize_search& P) {
+    typename X::Range nvtx_range("bnuts_find_initial_stepsize");
     if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
     // ≙ the (commented-out) @argcheck's of InitialStepsizeSearch, src/stepsize.jl:31-35
     if (!(P.a_min > 0.0 && P.a_min < P.a_max && P.a_max < 1.0 && P.C > 1.0 && P.eps0 > 0.0 && P.maxiter_crossing > 0 && P.maxiter_bisect > 0))
@@ -805,6 +814,7 @@ template <class T, class X> struct EngineCore {
   }
   // ≙ warmup!(FindLocalOptimum), src/warmup.jl:152-186
   int32_t find_local_optimum(double magnitude_penalty, int32_t iterations) {
+    typename X::Range nvtx_range("bnuts_find_local_optimum");
     if (model.kind == MODEL_NONE) return fail(BNUTS_ERR_NO_MODEL, "no model set");
     if (!(magnitude_penalty >= 0.0) || iterations < 0) return fail(BNUTS_ERR_INVALID_ARGUMENT, "bad FindLocalOptimum parameters");
     rp.opt.penalty = magnitude_penalty; rp.opt.iterations = iterations;

@@ -10,6 +10,7 @@
 //   logistic_tc.cu   tcgen05/TMA fused two-GEMM logistic gradient (fp32 variant)
 //   k_metric, k_finish_da, small gathers
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a tool is attached
 #include <dlfcn.h>
 #include <cstdio>
 #include <cstring>
@@ -506,6 +507,12 @@ int synth_fill_xb(cudaStream_t s, uint64_t seed, int64_t row0, int64_t N, int32_
 // ------------------------------------------------------------------ execution policy
 struct CudaExec {
   static constexpr bool has_tensor_path = true;
+  // NVTX range per phase of the C ABI (tracing); shows up in Nsight Systems / ncu --nvtx
+  struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range&) = delete; Range& operator=(const Range&) = delete;
+  };
   cudaStream_t stream = nullptr;
   cudaError_t first_err = cudaSuccess;
   const char* first_where = "";

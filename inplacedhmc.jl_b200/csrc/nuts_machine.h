@@ -28,7 +28,7 @@
 
 namespace bn {
 
-constexpr int MAX_LEVELS = 20;  // max_depth supported by the device engine
+constexpr int MAX_LEVELS = 32;  // max_depth supported by the engine ≙ MAX_DIRECTIONS_DEPTH, src/tree.jl:132 (one UInt32 of directions)
 
 enum Phase : int32_t {
   PH_IDLE = 0,
@@ -70,7 +70,7 @@ template <class T> struct ChainState {
   // magnitude N·log 2 has an ulp of 0.03 at N = 1e6, 8 at N = 1e8.  The fp32 variant is fp32 state VECTORS and vector arithmetic.
   double pi0; T teps;
   uint32_t dirs;
-  int32_t depth, fwd, n, sp;
+  int32_t depth, fwd; uint32_t n; int32_t sp;   // n: leaves of the current doubling built so far (up to 2^31)
   int32_t i_cur, i_minus, i_plus;
   int32_t slot_minus, slot_plus, slot_zeta, i_zeta;
   double omega, pi_zeta, v_lsa;
@@ -174,11 +174,11 @@ template <class T, class B> struct Machine {
   }
 
   BN_HD int32_t alloc_slot() const {
-    uint32_t used = (1u << s.slot_cur) | (1u << s.slot_minus) | (1u << s.slot_plus) | (1u << s.slot_zeta);
-    for (int k = 0; k < s.sp; ++k) used |= 1u << g->st_slot[k];
+    uint64_t used = (1ull << s.slot_cur) | (1ull << s.slot_minus) | (1ull << s.slot_plus) | (1ull << s.slot_zeta);
+    for (int k = 0; k < s.sp; ++k) used |= 1ull << g->st_slot[k];
     int32_t f = 0;
-    while (used & (1u << f)) ++f;
-    return f;  // n_slots = max_depth + 4 guarantees f < n_slots
+    while (used & (1ull << f)) ++f;
+    return f;  // n_slots = max_depth + 4 <= 36 guarantees f < n_slots
   }
 
   // ≙ rand_bool_logprob, src/NUTS.jl:32-34
@@ -258,8 +258,8 @@ template <class T, class B> struct Machine {
     if (!isfinite_(lq)) lq = -lim<double>::inf();  // ≙ evaluate_ℓ!, src/kinetic_energy.jl:80-84
     b.set_lq(s.slot_new, lq);
     const T e = s.fwd ? s.teps : -s.teps;
-    const int32_t n1 = s.n + 1;
-    const bool push_leaf = (n1 & 1) && s.depth > 0;
+    const uint32_t n1 = s.n + 1u;
+    const bool push_leaf = (n1 & 1u) && s.depth > 0;
     const T Ksum = b.post_kick(s.slot_new, T(0.5) * e, push_leaf ? s.sp : -1);
     s.slot_cur = s.slot_new;
     s.i_cur += s.fwd ? 1 : -1;
@@ -279,7 +279,7 @@ template <class T, class B> struct Machine {
     int32_t acc_slot = s.slot_cur, acc_iz = s.i_cur, acc_first = s.i_cur;
     int rhoR_is_leaf = 1;
     int m = 0;
-    while (!((n1 >> m) & 1)) ++m;  // trailing zeros; n1 <= 2^depth so m <= depth
+    while (!((n1 >> m) & 1u)) ++m;  // trailing zeros; n1 <= 2^depth so m <= depth
     for (int k = 1; k <= m; ++k) {  // ≙ adjacent_tree depth-k body, src/tree.jl:347-364
       const int L = s.sp - 1;
       acc_v = logaddexp_(g->st_vlsa[L], acc_v);
@@ -296,14 +296,14 @@ template <class T, class B> struct Machine {
       const double wl = g->st_omega[L];
       const double w = logaddexp_(wl, acc_omega);
       const double logprob2 = acc_omega - w;  // unbiased, src/tree.jl:261-263 with bias = false
-      if (!select_second(logprob2, (uint32_t)s.depth, (uint32_t)k, (uint32_t)n1)) {
+      if (!select_second(logprob2, (uint32_t)s.depth, (uint32_t)k, n1)) {
         acc_slot = g->st_slot[L]; acc_pi = g->st_pi[L]; acc_iz = g->st_izeta[L];
       }
       acc_omega = w;
       acc_first = g->st_first_i[L];
       s.sp = L;
     }
-    if (n1 == (1 << s.depth)) {
+    if (n1 == (1u << s.depth)) {
       top_merge(acc_v, acc_omega, acc_pi, acc_slot, acc_iz, rhoR_is_leaf);
       return;
     }

@@ -17,6 +17,7 @@ namespace bn {
 
 struct HostExec {
   static constexpr bool has_tensor_path = false;
+  struct Range { explicit Range(const char*) {} };   // tracing ranges exist on the device engine only
   int32_t init(int, std::string&) { return 0; }
   void shutdown() {}
   template <class U> U* alloc(size_t n) { return static_cast<U*>(std::calloc(n ? n : 1, sizeof(U))); }

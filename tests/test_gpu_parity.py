@@ -514,10 +514,10 @@ def test_synthetic_rows_on_device(bn, oracle_lib, cuda_lib):
 
 @pytest.mark.parametrize("C,D,max_depth,eps,kind", [
     (1, 1, 3, 0.4, "iid"), (2, 1, 1, 0.9, "funnel"), (3, 32, 2, 0.2, "gauss"), (3, 33, 4, 0.2, "gauss"),
-    (2, 128, 3, 0.05, "logit"), (2, 129, 3, 0.05, "logit"), (4, 5, 20, 1e-3, "iid"), (4, 7, 6, 50.0, "funnel"),
+    (2, 128, 3, 0.05, "logit"), (2, 129, 3, 0.05, "logit"), (4, 5, 20, 1e-3, "iid"), (3, 4, 32, 0.02, "iid"), (4, 7, 6, 50.0, "funnel"),
     (5, 6, 5, 1e-7, "iid")])
 def test_cuda_edge_shapes_and_regimes_bitwise(bn, oracle_lib, cuda_lib, C, D, max_depth, eps, kind):
-    """The edge cases of tests/test_machine_vs_oracle.py (one chain / one coordinate, max_depth 1 and 20, lane-row
+    """The edge cases of tests/test_machine_vs_oracle.py (one chain / one coordinate, max_depth 1, 20 and 32, lane-row
     boundaries, every-leaf-diverges and never-turns regimes) on the CUDA engine, deterministic gradient path, fp64:
     draws, statistics, selected indices and final state bit for bit against the oracle."""
     outs = []

@@ -82,7 +82,8 @@ def test_chain_offset_makes_sharding_invisible(bn, hostemu_lib):
     (3, 33, 4, 0.2, "gauss"),       # one element into the next group of 32
     (2, 128, 3, 0.05, "logit"),     # D = 128: four full lane rows
     (2, 129, 3, 0.05, "logit"),
-    (4, 5, 20, 1e-3, "iid"),        # max_depth at the engine's limit, tiny step: deep trees (capped by the draw count)
+    (4, 5, 20, 1e-3, "iid"),        # large max_depth, tiny step: deep trees (capped by the draw count)
+    (3, 4, 32, 0.02, "iid"),        # max_depth at the limit (≙ MAX_DIRECTIONS_DEPTH = 32, src/tree.jl:132): 36 phase-point slots
     (4, 7, 6, 50.0, "funnel"),      # absurd step: every first leaf diverges
     (5, 6, 5, 1e-7, "iid"),         # near-zero step: every tree hits max depth without turning
 ])
