@@ -50,7 +50,10 @@ template <class T> struct EngineMem {
   int32_t Dt;            // padded K of the tensor path
   const T* beta_ref;     // [Dp] reference point of the tensor path (staged operand is q − beta_ref), or null
   const double* lin_w;   // [Dp] tensor path: the kernel's log-density partials omit ½ Σ_d lin_w[d] q[d]
-  const double* grad0;   // [Dp] tensor path, single-term residual mode: the kernel's gradient partials omit X̃ᵀ·r0, or null
+  const double* grad0;   // [Dp] tensor path, single-term residual / remainder modes: the kernel's gradient partials omit X̃ᵀ·r0, or null
+  const float* lin_H;    // [D][Dp] tensor path, remainder mode (logistic_rm.cu): H0 = X̃ᵀ diag(σ'(η̃0)) X̃; the kernel's partials also omit
+                         // −H0 (q − beta_ref) and its log density is the remainder beyond ell0 + g0·δ − ½ δᵀH0 δ; or null
+  double ell0;           // Σ_i log σ(η̃0_i) (remainder mode)
   T tau;                 // logistic prior precision
   // per-call outputs
   double* draws;         // [C][N][D]
@@ -430,8 +433,10 @@ template <class T, class LP> struct Backend {
           for (int e = 0; e < 4; ++e) gv[e] = fma_(-M.tau, qv[e], acc[e]);
           st4(g + d0, gv, nv);
         }
+        double lin_l = 0.0;
+        if (M.lin_H) lin_l = linear_part(q, g, sg, bs);   // remainder mode: g −= H0 δ, ℓ += ell0 + δ·(g0 − ½ H0 δ + ⅓ X̃ᵀρ)
         if (M.stage_ld) {  // tensor path: partials are ~1e5..1e7 in magnitude, summed and kept in Float64
-          double lsd = 0.0;
+          double lsd = lin_l;
           for (int b = 0; b < M.stage_nb; ++b) lsd = lsd + M.stage_ld[b * rows + row];
           if (M.lin_w) {  // linear part of Σ log σ(η̃): ½ Σ_i η̃_i = ½ colsum(X̃)·q
             double part[LP::NACC];
@@ -455,6 +460,66 @@ template <class T, class LP> struct Backend {
     }
     lp.sync();
     return l;
+  }
+
+  // Remainder mode of the tensor path (logistic_rm.cu): the part of the model that is linear / quadratic in
+  // δ = q − beta_ref is exact arithmetic here, one D x D mat-vec per chain: y = H0 δ (fp32 FMAs, k sequential), then
+  // g −= y in place and the return value is ell0 + Σ_d δ_d (g0_d − ½ y_d + ⅓ (X̃ᵀρ)_d) in Float64; the last term is the part
+  // Σ_i δ_i ρ_i / 3 of the log density's remainder, which the kernel therefore does not sum.  Lane l owns the coordinates
+  // 4l..4l+3 (D <= 128, the domain of that kernel); δ_k is broadcast from its owner by a warp shuffle, row k of the
+  // symmetric H0 is one coalesced 16-byte load per lane.
+  BN_HD double linear_part(const T* q, T* g, const T* sg, int64_t bs) const {
+    double part[LP::NACC];
+    for (int i = 0; i < LP::NACC; ++i) part[i] = 0.0;
+#if defined(__CUDA_ARCH__)
+    const int d0 = lp.first4();
+    float dv[4] = {0.f, 0.f, 0.f, 0.f}, y[4] = {0.f, 0.f, 0.f, 0.f};
+    if (d0 < M.D) {
+      T qv[4], br[4];
+      ld4(q + d0, qv); ld4(M.beta_ref + d0, br);
+      for (int e = 0; e < 4; ++e) dv[e] = (d0 + e < M.D) ? (float)qv[e] - (float)br[e] : 0.f;
+    }
+    const int dl = d0 < M.Dp ? d0 : 0;   // lanes beyond the row read a valid (unused) address
+    for (int kk = 0; 4 * kk < M.D; ++kk) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float b = __shfl_sync(0xffffffffu, dv[e], kk);
+        if (4 * kk + e < M.D) {
+          const float4 hr = *reinterpret_cast<const float4*>(M.lin_H + (int64_t)(4 * kk + e) * M.Dp + dl);
+          y[0] = fmaf(hr.x, b, y[0]); y[1] = fmaf(hr.y, b, y[1]); y[2] = fmaf(hr.z, b, y[2]); y[3] = fmaf(hr.w, b, y[3]);
+        }
+      }
+    }
+    if (d0 < M.D) {
+      T gv[4]; double g0[4];
+      ld4(g + d0, gv); ld4(M.grad0 + d0, g0);
+      const int nv = M.D - d0 < 4 ? M.D - d0 : 4;
+      T rem[4] = {T(0), T(0), T(0), T(0)};   // X̃ᵀρ: the kernel's partials, folded in the order model_grad folds them
+      for (int b = 0; b < M.stage_nb; ++b) {
+        T pv[4];
+        ld4(sg + b * bs + d0, pv);
+        for (int e = 0; e < 4; ++e) rem[e] = rem[e] + pv[e];
+      }
+      for (int e = 0; e < 4; ++e) {
+        gv[e] = gv[e] - T(y[e]);
+        if (e < nv) part[0] = fma_((double)dv[e], g0[e] - 0.5 * (double)y[e] + (1.0 / 3.0) * (double)rem[e], part[0]);
+      }
+      st4(g + d0, gv, nv);
+    }
+#else
+    for (int d = 0; d < M.D; ++d) {   // host build: same definition, plain loops (the tensor path itself is CUDA-only)
+      float yd = 0.f;
+      for (int k = 0; k < M.D; ++k) yd = fmaf(M.lin_H[(int64_t)k * M.Dp + d], (float)q[k] - (float)M.beta_ref[k], yd);
+      g[d] = g[d] - T(yd);
+      T rem = T(0);
+      for (int b = 0; b < M.stage_nb; ++b) rem = rem + sg[b * bs + d];
+      double& a = part[lp.acc(d)];
+      a = fma_((double)((float)q[d] - (float)M.beta_ref[d]), M.grad0[d] - 0.5 * (double)yd + (1.0 / 3.0) * (double)rem, a);
+    }
+#endif
+    const double r = lp.reduce(part);
+    lp.sync();
+    return M.ell0 + r;
   }
 
   // ---- local optimum search (≙ warmup!(FindLocalOptimum), src/warmup.jl:152-186; see nuts_machine.h)

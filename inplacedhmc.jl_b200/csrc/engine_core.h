@@ -196,7 +196,7 @@ template <class T, class X> struct EngineCore {
     EngineMem<T> V = M;
     V.stage_q = wide_q; V.stage_bh = wide_bh; V.stage_bm = wide_bm; V.stage_bl = wide_bl;
     V.stage_active = d_active;
-    V.stage_g = red_g; V.stage_ld = red_l; V.stage_nb = 1; V.stage_rows = (int32_t)rows; V.lin_w = nullptr; V.grad0 = nullptr;
+    V.stage_g = red_g; V.stage_ld = red_l; V.stage_nb = 1; V.stage_rows = (int32_t)rows; V.lin_w = nullptr; V.grad0 = nullptr; V.lin_H = nullptr;
     return V;
   }
 
@@ -209,7 +209,7 @@ template <class T, class X> struct EngineCore {
     model = ModelCtx<T>();
     user_model_kind = MODEL_NONE; h_P.clear();
     M.stage_nb = 0;
-    M.beta_ref = nullptr; M.lin_w = nullptr; M.grad0 = nullptr;
+    M.beta_ref = nullptr; M.lin_w = nullptr; M.grad0 = nullptr; M.lin_H = nullptr; M.ell0 = 0.0;
   }
   int32_t model_simple(int kind) {
     free_model();

@@ -835,8 +835,8 @@ template <int NK> void launch256(LogisticTC& tc, cudaStream_t s, int nrows, int 
 }  // namespace
 
 // number of row splits for `nrows` active rows: fill the SMs in as few full waves as possible
-int LogisticTC::plan_splits(int nrows) const {
-  const int tiles = (nrows + CHAINS - 1) / CHAINS;
+int LogisticTC::plan_splits(int nrows, int tile_rows) const {
+  const int tiles = (nrows + tile_rows - 1) / tile_rows;
   const int64_t nblk = Npad / ROWS;
   if (force_nsplit > 0) return (int)std::min<int64_t>(force_nsplit, nblk);
   int best = 1;
@@ -853,6 +853,12 @@ int LogisticTC::plan_splits(int nrows) const {
 }
 void LogisticTC::run(cudaStream_t s, int nrows) {
   if (!ready || nrows <= 0) return;
+  if (rmode == 2) {   // remainder mode: chains are the MMA N dimension, 64-chain tiles for small launches
+    const int nc = nrows <= 64 ? 64 : 128;
+    last_nsplit = plan_splits(nrows, nc);
+    logistic_rm_launch(*this, s, nrows, last_nsplit, nc);
+    return;
+  }
   last_nsplit = plan_splits(nrows);
   if (variant == 256) {
     switch (dk / 16) {
@@ -891,6 +897,8 @@ void LogisticTC::destroy() {
   if (c0) cudaFree(c0);
   if (grad0) cudaFree(grad0);
   if (grad0_part) cudaFree(grad0_part);
+  void** rmp[] = {(void**)&rec, (void**)&rm_r0, (void**)&rm_w, (void**)&rm_f0, (void**)&H0, (void**)&H0_part, (void**)&rm_part, (void**)&ell0};
+  for (void** p : rmp) if (*p) { cudaFree(*p); *p = nullptr; }
   Xb = nullptr; colsum = nullptr; beta_ref = nullptr; eta0 = nullptr; c0 = nullptr; grad0 = nullptr; grad0_part = nullptr;
   ready = false; nterms = 3; rmode = 0; variant = 128;
 }
@@ -1045,6 +1053,7 @@ int32_t tc_alloc(LogisticTC& tc, std::string& err) {
     const int nr = std::min<int>(tc.C, tiles * CHAINS);
     worst = std::max<int64_t>(worst, (int64_t)tc.plan_splits(nr) * nr);
   }
+  worst = std::max<int64_t>(worst, (int64_t)tc.plan_splits(64, 64) * std::min<int>(tc.C, 64));   // remainder mode: 64-chain tiles
   tc.partial_rows = worst;
   return 0;
 }

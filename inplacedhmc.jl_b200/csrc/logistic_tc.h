@@ -32,7 +32,13 @@ struct LogisticTC {
   float* c0 = nullptr;       // [Npad] ½ − r0_i, r0_i = σ(−η̃0_i) (zero in the padding rows)
   double* grad0 = nullptr;   // [Dp] X̃ᵀ·r0 in Float64 from the stored fp32 values: added by the consumer (EngineMem::grad0)
   double* grad0_part = nullptr;  // [G0_BLOCKS][Dp] scratch of its two-pass (deterministic) reduction
-  int32_t rmode = 0;         // residual operand: 0 two bf16 terms of r; 1 one term of δ = r − r0
+  int32_t rmode = 0;         // residual operand: 0 two bf16 terms of r; 1 one term of δ = r − r0; 2 remainder mode (logistic_rm.cu)
+  // remainder mode (logistic_rm.cu): per-row records (A2, A3, A4, η̃0), H0 = X̃ᵀ diag(w) X̃ (fp32 [D][Dp]), ℓ0, radius² of the Taylor path
+  float* rec = nullptr; float* rm_r0 = nullptr; float* rm_w = nullptr; double* rm_f0 = nullptr;
+  float* H0 = nullptr; double* H0_part = nullptr; double* rm_part = nullptr; double* ell0 = nullptr;
+  double ell0_host = 0.0;
+  float kappa2 = 0.f;
+  int32_t rm_terms = 2;
   // borrowed from the engine
   const uint16_t* bh = nullptr; const uint16_t* bm = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
   float* G = nullptr;        // [nsplit][rows][Dp]
@@ -43,7 +49,7 @@ struct LogisticTC {
   bool ready = false;
   cudaError_t last = cudaSuccess;
 
-  int plan_splits(int nrows) const;
+  int plan_splits(int nrows, int tile_rows = 128) const;
   void run(cudaStream_t s, int nrows);
   void destroy();
 };
@@ -66,6 +72,9 @@ void logistic_tc_write_reference(LogisticTC& tc, cudaStream_t s, const float* be
 void logistic_tc_write_residual_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev);
 // staging rows: 1.0 in the reserved columns of the high term
 void logistic_tc_init_stage(LogisticTC& tc, cudaStream_t s, uint16_t* bh);
+// remainder mode (logistic_rm.cu): reference constants (records, g0 into tc.grad0, ℓ0, H0, κ²) and the launch
+int32_t logistic_rm_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev, std::string& err);
+void logistic_rm_launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit, int nc);
 
 template <class E> int32_t logistic_tc_attach(LogisticTC& tc, E& eng, std::string& err);
 
@@ -153,7 +162,7 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
     // back to the exact path (D <= 128) / to the zero reference (D > 128: always two terms, see k_logistic_tc256)
     tc.nterms = tc.variant == 256 ? 2 : 3;
     tc.rmode = 0;
-    M.grad0 = nullptr;
+    M.grad0 = nullptr; M.lin_H = nullptr; M.ell0 = 0.0; M.lin_w = tc.colsum;
     x.zero(tc.beta_ref, size_t(M.Dp) * sizeof(float));
     logistic_tc_write_reference(tc, x.stream, nullptr);
     if (!beta_ref) return x.check(err);
@@ -198,7 +207,23 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
     // when N >= 3.3e5·D over the whole row group (config 5); BNUTS_TC_RREF=0/1 overrides.
     const char* rr = std::getenv("BNUTS_TC_RREF");
     const bool rr_auto = double(tc.N) * double(eng.reduce_world()) >= 3.3e5 * double(M.D);
-    if (rr ? std::atoi(rr) != 0 : rr_auto) {
+    // Remainder mode (logistic_rm.cu; D <= 125, rows not sharded): the model is expanded about the reference row by row, the
+    // linear / quadratic part is exact D x D arithmetic in the consumer and only the small remainder goes through the tensor
+    // cores, as ONE bf16 term.  Default where it applies; BNUTS_TC_RMODE=0/1/2 overrides (0 / 1: the residual operands above).
+    const char* rme = std::getenv("BNUTS_TC_RMODE");
+    const bool rm_ok = tc.variant == 128 && tc.aug && !eng.reduce_on;
+    // ... by itself only for tall problems: the posterior's row-wise rms of δ is about sqrt(D / (N/5)); beyond ~0.04 most chains
+    // would sit outside the Taylor radius and take the closed forms (correct, but no faster than the modes above)
+    const bool rm_auto = rm_ok && double(tc.N) >= 3000.0 * double(M.D);
+    int want = rme ? std::atoi(rme) : (rr ? (std::atoi(rr) != 0 ? 1 : 0) : (rm_auto ? 2 : (rr_auto ? 1 : 0)));
+    if (want == 2 && !rm_ok) want = rr_auto ? 1 : 0;
+    if (want == 2) {
+      logistic_tc_write_reference(tc, x.stream, nullptr);   // S = X̃·(β − β₀) only: the reference columns of X̃ stay clear
+      int32_t rc2 = logistic_rm_write_reference(tc, x.stream, tc.beta_ref, err);
+      if (rc2) return rc2;
+      tc.rmode = 2;
+      M.grad0 = tc.grad0; M.lin_H = tc.H0; M.ell0 = tc.ell0_host; M.lin_w = nullptr;
+    } else if (want == 1) {
       logistic_tc_write_residual_reference(tc, x.stream, tc.beta_ref);
       tc.rmode = 1;
       M.grad0 = tc.grad0;
