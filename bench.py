@@ -317,6 +317,8 @@ def setup_engine(a, bn, rank, world, local):
         # doubling windows, then step size only
         stages = ((a.adapt, bn.METRIC_NONE), (25, bn.METRIC_DIAG), (50, bn.METRIC_DIAG), (100, bn.METRIC_DIAG), (a.adapt, bn.METRIC_NONE)) \
             if cfg == "c3" else ((a.adapt, bn.METRIC_NONE),)
+        if cfg == "c3" and a.full_warmup:   # the windows of default_warmup_stages itself (src/warmup.jl:361-372): 75 | 25 50 100 200 400 | 50
+            stages = ((75, bn.METRIC_NONE),) + tuple((n, bn.METRIC_DIAG) for n in (25, 50, 100, 200, 400)) + ((50, bn.METRIC_NONE),)
         info["init"] = "q0 ~ U[-2,2]^D; untimed warmup: FindLocalOptimum(1e-4, %d), step size search, stages %s" % (
             a.opt_iters, "|".join("%d%s" % (n, "m" if mk else "") for n, mk in stages))
     elif cfg == "c2":
@@ -368,6 +370,7 @@ def main():
     ap.add_argument("--no-vectorised", action="store_true", help="skip the non-parity vectorised CPU leg")
     ap.add_argument("--no-fp64", action="store_true", help="c3: skip the Float64-engine leg (reference precision)")
     ap.add_argument("--no-reference", action="store_true", help="keep the exact three-term position operand")
+    ap.add_argument("--full-warmup", action="store_true", help="c3: the windows of default_warmup_stages (75|25,50,100,200,400|50) instead of the shortened 40|25,50,100|40")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong (BASELINE config 3: --chains in total, sharded over the GPUs) or weak (--chains per GPU)")
     a = ap.parse_args()
@@ -526,6 +529,14 @@ def main():
         ach = 4.0 * N_gpu * D * rows / (grad_ms * 1e-3) / 1e12 if grad_n else None
         dk = (-(-(D + 3) // 16) * 16) if D <= 125 else (-(-D // 16) * 16)
         rterms = 2 if (a.config == "c3") else 1
+        # remainder mode (csrc/logistic_rm.cu): what logistic_tc_set_reference takes by itself for D <= 125, N >= 3000 D, rows not sharded
+        rmode_env = os.environ.get("BNUTS_TC_RMODE")
+        remainder = (terms == 2 and D <= 125 and a.config == "c3" and (int(rmode_env) == 2 if rmode_env else (N >= 3000 * D and "BNUTS_TC_RREF" not in os.environ)))
+        if remainder:
+            kern = "k_logistic_rm"
+        # executed on the tensor pipe per algorithmic flop: K padded to 16 and the position operand in `terms` bf16 terms in GEMM1;
+        # the residual in `rterms` terms with N = dk (k_logistic_tc) or the remainder in one term with M = 128 features (k_logistic_rm) in GEMM2
+        exe = ((terms * dk + 128) / (2.0 * D)) if remainder else ((terms + rterms) * dk / (2.0 * D))
         out["dtype"] = "f32 (exact bf16 operand splits on tcgen05, fp32 accumulate)"
         config["l2"] = "inputs larger than L2 (X is %d MB bf16 per GPU)" % (N_gpu * (128 if D <= 128 else 256) * 2 // 2**20)
         config["position_operand_terms"] = terms
@@ -534,15 +545,15 @@ def main():
                            # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
                            # (profiles/r1_ncu_full_details_k_logistic_tc_4096rows.csv: 292.4 MB + 14.5 MB; X is read once per
                            # launch whatever the number of active rows: 256 MB algorithmic)
-                           "traffic": 306.9e6 if (a.config == "c3" and N == 1_000_000 and D == 100) else None,
+                           "traffic": (None if remainder else 306.9e6) if (a.config == "c3" and N == 1_000_000 and D == 100) else None,
                            "traffic_unit": "bytes per launch (ncu, full 4096-row launch)",
                            "kernel": kern, "launches": int(grad_n), "avg_launch_ms": grad_ms / max(grad_n, 1),
                            "avg_rows_per_launch": rows / max(grad_n, 1), "peak_source": peak_src,
                            "kernel_share_of_step": grad_ms / ms,
                            # what the tensor pipe executes for those algorithmic flops: K and N padded to 16, the position
                            # operand in `terms` bf16 terms and the residual in `rterms`
-                           "executed_over_algorithmic": (terms + rterms) * dk / (2.0 * D),
-                           "executed": (ach * (terms + rterms) * dk / (2.0 * D)) if ach else None}
+                           "executed_over_algorithmic": exe,
+                           "executed": (ach * exe) if ach else None}
     else:
         sz = 8 if (a.config == "c4" and a.dtype == "f64") else 4
         peak_bw = peaks.get("hbm_gbs")

@@ -417,13 +417,24 @@ template <class T, class LP> struct Backend {
         const int64_t row = M.stage_row[c], rows = M.stage_rows;
         const int64_t bs = rows * M.Dp;
         const T* sg = M.stage_g + row * M.Dp;
+        T rem4[4] = {T(0), T(0), T(0), T(0)};   // remainder mode (D <= 128: one group per lane): the folded X̃ᵀρ of this lane's coordinates
         BN_FOR4(d0, nv) {
           T acc[4] = {T(0), T(0), T(0), T(0)}, qv[4], gv[4];
-          for (int b = 0; b < M.stage_nb; ++b) {
+          // the partial blocks are added in the order b = 0, 1, ... (fixed: the deterministic path is bit-identical to the
+          // oracle), but loaded four at a time: a small launch of the tensor path has up to 148 of them (one per SM) and one
+          // L2 round trip per partial made this fold the longest part of a lockstep step with few active chains
+          int b = 0;
+          for (; b + 4 <= M.stage_nb; b += 4) {
+            T p0[4], p1[4], p2[4], p3[4];
+            ld4(sg + (b + 0) * bs + d0, p0); ld4(sg + (b + 1) * bs + d0, p1); ld4(sg + (b + 2) * bs + d0, p2); ld4(sg + (b + 3) * bs + d0, p3);
+            for (int e = 0; e < 4; ++e) acc[e] = (((acc[e] + p0[e]) + p1[e]) + p2[e]) + p3[e];
+          }
+          for (; b < M.stage_nb; ++b) {
             T pv[4];
             ld4(sg + b * bs + d0, pv);
             for (int e = 0; e < 4; ++e) acc[e] = acc[e] + pv[e];
           }
+          for (int e = 0; e < 4; ++e) rem4[e] = acc[e];
           if (M.grad0) {  // constant part of the gradient about the reference point (see k_logistic_tc)
             double g0[4];
             ld4(M.grad0 + d0, g0);
@@ -434,10 +445,14 @@ template <class T, class LP> struct Backend {
           st4(g + d0, gv, nv);
         }
         double lin_l = 0.0;
-        if (M.lin_H) lin_l = linear_part(q, g, sg, bs);   // remainder mode: g −= H0 δ, ℓ += ell0 + δ·(g0 − ½ H0 δ + ⅓ X̃ᵀρ)
+        if (M.lin_H) lin_l = linear_part(q, g, rem4, sg, bs);   // remainder mode: g −= H0 δ, ℓ += ell0 + δ·(g0 − ½ H0 δ + ⅓ X̃ᵀρ)
         if (M.stage_ld) {  // tensor path: partials are ~1e5..1e7 in magnitude, summed and kept in Float64
-          double lsd = lin_l;
-          for (int b = 0; b < M.stage_nb; ++b) lsd = lsd + M.stage_ld[b * rows + row];
+          // Float64 partials of the splits: lane l adds the splits l, l + 32, ..., then the butterfly (a fixed order; one round
+          // trip to L2 instead of one per split)
+          double pl[LP::NACC];
+          for (int i = 0; i < LP::NACC; ++i) pl[i] = 0.0;
+          for (int b = lp.first(); b < M.stage_nb; b += lp.stride()) pl[LP::NACC == 1 ? 0 : (b & 31)] += M.stage_ld[b * rows + row];
+          double lsd = lin_l + lp.reduce(pl);
           if (M.lin_w) {  // linear part of Σ log σ(η̃): ½ Σ_i η̃_i = ½ colsum(X̃)·q
             double part[LP::NACC];
             for (int i = 0; i < LP::NACC; ++i) part[i] = 0.0;
@@ -468,7 +483,7 @@ template <class T, class LP> struct Backend {
   // Σ_i δ_i ρ_i / 3 of the log density's remainder, which the kernel therefore does not sum.  Lane l owns the coordinates
   // 4l..4l+3 (D <= 128, the domain of that kernel); δ_k is broadcast from its owner by a warp shuffle, row k of the
   // symmetric H0 is one coalesced 16-byte load per lane.
-  BN_HD double linear_part(const T* q, T* g, const T* sg, int64_t bs) const {
+  BN_HD double linear_part(const T* q, T* g, const T (&rem)[4], const T* sg, int64_t bs) const {
     double part[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) part[i] = 0.0;
 #if defined(__CUDA_ARCH__)
@@ -480,26 +495,24 @@ template <class T, class LP> struct Backend {
       for (int e = 0; e < 4; ++e) dv[e] = (d0 + e < M.D) ? (float)qv[e] - (float)br[e] : 0.f;
     }
     const int dl = d0 < M.Dp ? d0 : 0;   // lanes beyond the row read a valid (unused) address
-    for (int kk = 0; 4 * kk < M.D; ++kk) {
+    // rows k >= D of H0 are zero padding up to Dp (a multiple of 32) and δ_k = 0 there: no guards, so the eight row loads
+    // of two steps are in flight together (guarded, the compiler serialised them: one L2 round trip per row, 35 us per chain)
+    const float* Hl = M.lin_H + dl;
+    for (int kk = 0; 4 * kk < M.D; kk += 2) {
+      float4 hr[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float b = __shfl_sync(0xffffffffu, dv[e], kk);
-        if (4 * kk + e < M.D) {
-          const float4 hr = *reinterpret_cast<const float4*>(M.lin_H + (int64_t)(4 * kk + e) * M.Dp + dl);
-          y[0] = fmaf(hr.x, b, y[0]); y[1] = fmaf(hr.y, b, y[1]); y[2] = fmaf(hr.z, b, y[2]); y[3] = fmaf(hr.w, b, y[3]);
-        }
+      for (int u = 0; u < 8; ++u) hr[u] = *reinterpret_cast<const float4*>(Hl + (int64_t)(4 * kk + u) * M.Dp);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float b = __shfl_sync(0xffffffffu, dv[u & 3], kk + (u >> 2));
+        y[0] = fmaf(hr[u].x, b, y[0]); y[1] = fmaf(hr[u].y, b, y[1]); y[2] = fmaf(hr[u].z, b, y[2]); y[3] = fmaf(hr[u].w, b, y[3]);
       }
     }
     if (d0 < M.D) {
       T gv[4]; double g0[4];
       ld4(g + d0, gv); ld4(M.grad0 + d0, g0);
       const int nv = M.D - d0 < 4 ? M.D - d0 : 4;
-      T rem[4] = {T(0), T(0), T(0), T(0)};   // X̃ᵀρ: the kernel's partials, folded in the order model_grad folds them
-      for (int b = 0; b < M.stage_nb; ++b) {
-        T pv[4];
-        ld4(sg + b * bs + d0, pv);
-        for (int e = 0; e < 4; ++e) rem[e] = rem[e] + pv[e];
-      }
+      (void)sg; (void)bs;
       for (int e = 0; e < 4; ++e) {
         gv[e] = gv[e] - T(y[e]);
         if (e < nv) part[0] = fma_((double)dv[e], g0[e] - 0.5 * (double)y[e] + (1.0 / 3.0) * (double)rem[e], part[0]);
@@ -511,10 +524,10 @@ template <class T, class LP> struct Backend {
       float yd = 0.f;
       for (int k = 0; k < M.D; ++k) yd = fmaf(M.lin_H[(int64_t)k * M.Dp + d], (float)q[k] - (float)M.beta_ref[k], yd);
       g[d] = g[d] - T(yd);
-      T rem = T(0);
-      for (int b = 0; b < M.stage_nb; ++b) rem = rem + sg[b * bs + d];
+      T remd = T(0);
+      for (int b = 0; b < M.stage_nb; ++b) remd = remd + sg[b * bs + d];
       double& a = part[lp.acc(d)];
-      a = fma_((double)((float)q[d] - (float)M.beta_ref[d]), M.grad0[d] - 0.5 * (double)yd + (1.0 / 3.0) * (double)rem, a);
+      a = fma_((double)((float)q[d] - (float)M.beta_ref[d]), M.grad0[d] - 0.5 * (double)yd + (1.0 / 3.0) * (double)remd, a);
     }
 #endif
     const double r = lp.reduce(part);

@@ -12,6 +12,7 @@ sys.path.insert(0, ROOT)
 from bench import synth  # noqa: E402
 import inplacedhmc_jl_b200 as bn  # noqa: E402
 
+os.environ.setdefault("BNUTS_TC_RMODE", "2")   # the engine takes the mode by itself only for N >= 3000 D
 N, D = int(os.environ.get("NROWS", 200_000)), int(os.environ.get("DIM", 100))
 bits, y, beta = synth(N, D)
 X = (bits.astype(np.uint32) << 16).view(np.float32).astype(np.float64)

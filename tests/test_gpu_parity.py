@@ -434,14 +434,16 @@ def test_tensor_single_term_residual_forced(bn, oracle_lib, cuda_lib, monkeypatc
 
 def test_tensor_reference_modes_full_size(bn, cuda_lib, monkeypatch):
     """BASELINE config 3 shape (N = 1e6, D = 100) around the optimum found on the device: gradients in the posterior bulk
-    and its tails against numpy Float64 for the two residual modes of the reference-point path.  Two bf16 terms of r
-    (what the engine takes here): north-star fp32 tolerance, or the fp32 conditioning floor N * eps32 where
-    |grad| -> 0; slot / tile invariance bit for bit.  One term of delta forced on: within three times its error model
-    (1.7e-5 |grad| at this N / D, which is why it is not taken by itself here)."""
+    and its tails against numpy Float64 for the three modes of the reference-point path.  Remainder mode (what the engine
+    takes here, csrc/logistic_rm.cu): a fifth of the north-star fp32 tolerance in the bulk (the linear part is exact).
+    Two bf16 terms of r (BNUTS_TC_RMODE=0): the fp32 tolerance, or the fp32 conditioning floor N * eps32 where |grad| -> 0.
+    One term of delta (BNUTS_TC_RMODE=1): within three times its error model (1.7e-5 |grad| at this N / D).  Slot / tile
+    invariance bit for bit in every mode; the log density of the two residual modes is the same bits."""
     N, D, C = 1_000_000, 100, 256
     X, y, beta = make_logistic(N, D)
     rng = np.random.default_rng(4)
     monkeypatch.delenv("BNUTS_TC_RREF", raising=False)
+    monkeypatch.delenv("BNUTS_TC_RMODE", raising=False)
     tc = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR); tc.model_logistic(X, y, 1.0)
     tc.set_positions(np.repeat(_f32(beta)[None, :], C, axis=0))
     tc.find_local_optimum(1e-4, 50)
@@ -454,22 +456,26 @@ def test_tensor_reference_modes_full_size(bn, cuda_lib, monkeypatch):
     q[1 + nw:] = q[1 + (np.arange(C - 1 - nw) % nw)]
     eta = X @ q[1:1 + nw].T
     gref = ((y[:, None] - 1 / (1 + np.exp(-eta))).T @ X) - q[1:1 + nw]
+    lref = (y[:, None] * eta - np.logaddexp(0.0, eta)).sum(axis=0) - 0.5 * (q[1:1 + nw] ** 2).sum(axis=1)
     nrm = np.linalg.norm(gref, axis=1)
     out = {}
-    for mode, env in (("two", {}), ("delta", {"BNUTS_TC_RREF": "1"})):
-        monkeypatch.delenv("BNUTS_TC_RREF", raising=False)
+    for mode, env in (("remainder", {}), ("two", {"BNUTS_TC_RMODE": "0"}), ("delta", {"BNUTS_TC_RMODE": "1"})):
+        monkeypatch.delenv("BNUTS_TC_RMODE", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         tc.logistic_set_reference(b); tc.set_positions(q); _, g, l = tc.get_state()
         err = np.linalg.norm(g[1:1 + nw] - gref, axis=1)
-        tol = 3 * RR_MODEL * np.sqrt(D / N) if mode == "delta" else TOL32
+        # remainder mode: widths up to 0.006 (3 posterior sd) lie inside the Taylor radius, 0.02 and 0.06 take the closed forms
+        tol = {"remainder": np.where(np.array(widths) <= 0.006, TOL32 / 5, TOL32), "two": TOL32, "delta": 3 * RR_MODEL * np.sqrt(D / N)}[mode]
         assert np.all(err < np.maximum(tol * nrm, 3 * N * 6e-8)), (mode, err, nrm)
+        if mode == "remainder":   # the log density as well: exact quadratic form + a small remainder (the other modes: ~3e-2)
+            assert np.all(np.abs(l[1:1 + nw] - lref) < np.where(np.array(widths) <= 0.006, 2e-3, 5e-2)), np.abs(l[1:1 + nw] - lref)
         for k in range(1 + nw, C):
             assert g[k].tobytes() == g[1 + (k - 1 - nw) % nw].tobytes() and l[k] == l[1 + (k - 1 - nw) % nw]
         out[mode] = (g, l, err)
         print("N=1e6 D=100 mode", mode, "|grad|", nrm, "err", err, "rel", err / nrm)
-    assert out["two"][0].tobytes() != out["delta"][0].tobytes()
-    assert out["two"][1].tobytes() == out["delta"][1].tobytes()      # the log density is untouched
+    assert out["two"][0].tobytes() != out["delta"][0].tobytes() and out["two"][0].tobytes() != out["remainder"][0].tobytes()
+    assert out["two"][1].tobytes() == out["delta"][1].tobytes()      # the residual operand does not touch the log density
 
 
 def test_synthetic_rows_on_device(bn, oracle_lib, cuda_lib):
