@@ -739,8 +739,8 @@ k_logistic_tc256(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
           }
         }
-        bsum = lg2_approx(prod.x * prod.y);
-        asum = as2.x + as2.y;
+        bsum += lg2_approx(prod.x * prod.y);
+        asum += as2.x + as2.y;
         have_next = false;
         if (i + 2 < nb) have_next = load_item(i + 2, false);
         tmem_st16(tS, hi);

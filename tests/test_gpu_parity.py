@@ -580,3 +580,28 @@ def test_tensor_path_posterior_moments_within_mcse(bn, cuda_lib):
     assert np.max(np.abs(mB - b) / sd) < 0.25
     Hinv = np.linalg.inv((X * ((lambda s_: s_ * (1 - s_))(1 / (1 + np.exp(-(X @ b)))))[:, None]).T @ X + np.eye(D))
     assert np.max(np.abs(vB / np.diag(Hinv) - 1)) < 0.15
+
+
+def test_tensor_d256_log_density_many_blocks(bn, cuda_lib):
+    """k_logistic_tc256 with many row blocks per CTA (the Float64 folding of the log-density partials every eight blocks is
+    only reached then): gradient and log density against numpy Float64 from |eta| ~ 0.5 to |eta| ~ 200 (config 5's optimiser
+    starts at U[-2,2]^256).  Regression: the per-block partial sums were assigned instead of accumulated, so seven of every
+    eight blocks were missing from the log density while the gradient was right."""
+    N, D, C = 60_000, 256, 8
+    Xb, y, beta = bn.synth_logistic_rows(5, 0, N, D, lib=cuda_lib)
+    X = (Xb.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    Xs = X * (2 * y - 1)[:, None]
+    rng = np.random.default_rng(2)
+    e = bn.Engine(C, D, dtype=F32, lib=cuda_lib, gradient_path=TENSOR)
+    e.model_logistic_synthetic(5, 0, N, 1.0)
+    for k in (0.05, 1.0, 5.0):
+        q = _f32(rng.uniform(-1, 1, size=(C, D)) * k)
+        eta = Xs @ q.T
+        l0 = (np.minimum(eta, 0) - np.log1p(np.exp(-np.abs(eta)))).sum(0) - 0.5 * (q * q).sum(1)
+        with np.errstate(over="ignore"):
+            g0 = (Xs.T @ (1 / (1 + np.exp(eta)))).T - q
+        e.set_positions(q)
+        _, g, l = e.get_state()
+        assert np.max(np.linalg.norm(g - g0, axis=1) / np.linalg.norm(g0, axis=1)) < TOL32
+        assert np.max(np.abs(l - l0) / np.abs(l0)) < 5e-6, (k, l[0], l0[0])
+    e.close()
