@@ -417,7 +417,7 @@ template <class T, class LP> struct Backend {
         const int64_t row = M.stage_row[c], rows = M.stage_rows;
         const int64_t bs = rows * M.Dp;
         const T* sg = M.stage_g + row * M.Dp;
-        T rem4[4] = {T(0), T(0), T(0), T(0)};   // remainder mode (D <= 128: one group per lane): the folded X̃ᵀρ of this lane's coordinates
+        T rem4[2][4] = {{T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0)}};   // remainder mode (D <= 256: at most two groups per lane): the folded X̃ᵀρ of this lane's coordinates
         BN_FOR4(d0, nv) {
           T acc[4] = {T(0), T(0), T(0), T(0)}, qv[4], gv[4];
           // the partial blocks are added in the order b = 0, 1, ... (fixed: the deterministic path is bit-identical to the
@@ -434,7 +434,7 @@ template <class T, class LP> struct Backend {
             ld4(sg + b * bs + d0, pv);
             for (int e = 0; e < 4; ++e) acc[e] = acc[e] + pv[e];
           }
-          for (int e = 0; e < 4; ++e) rem4[e] = acc[e];
+          for (int e = 0; e < 4; ++e) rem4[(d0 >> 7) & 1][e] = acc[e];
           if (M.grad0) {  // constant part of the gradient about the reference point (see k_logistic_tc)
             double g0[4];
             ld4(M.grad0 + d0, g0);
@@ -483,41 +483,70 @@ template <class T, class LP> struct Backend {
   // Σ_i δ_i ρ_i / 3 of the log density's remainder, which the kernel therefore does not sum.  Lane l owns the coordinates
   // 4l..4l+3 (D <= 128, the domain of that kernel); δ_k is broadcast from its owner by a warp shuffle, row k of the
   // symmetric H0 is one coalesced 16-byte load per lane.
-  BN_HD double linear_part(const T* q, T* g, const T (&rem)[4], const T* sg, int64_t bs) const {
+  BN_HDN double linear_part(const T* q, T* g, const T (&rem)[2][4], const T* sg, int64_t bs) const {
     double part[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) part[i] = 0.0;
 #if defined(__CUDA_ARCH__)
-    const int d0 = lp.first4();
-    float dv[4] = {0.f, 0.f, 0.f, 0.f}, y[4] = {0.f, 0.f, 0.f, 0.f};
-    if (d0 < M.D) {
-      T qv[4], br[4];
-      ld4(q + d0, qv); ld4(M.beta_ref + d0, br);
-      for (int e = 0; e < 4; ++e) dv[e] = (d0 + e < M.D) ? (float)qv[e] - (float)br[e] : 0.f;
-    }
-    const int dl = d0 < M.Dp ? d0 : 0;   // lanes beyond the row read a valid (unused) address
-    // rows k >= D of H0 are zero padding up to Dp (a multiple of 32) and δ_k = 0 there: no guards, so the eight row loads
-    // of two steps are in flight together (guarded, the compiler serialised them: one L2 round trip per row, 35 us per chain)
-    const float* Hl = M.lin_H + dl;
-    for (int kk = 0; 4 * kk < M.D; kk += 2) {
-      float4 hr[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) hr[u] = *reinterpret_cast<const float4*>(Hl + (int64_t)(4 * kk + u) * M.Dp);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float b = __shfl_sync(0xffffffffu, dv[u & 3], kk + (u >> 2));
-        y[0] = fmaf(hr[u].x, b, y[0]); y[1] = fmaf(hr[u].y, b, y[1]); y[2] = fmaf(hr[u].z, b, y[2]); y[3] = fmaf(hr[u].w, b, y[3]);
+    // lane l owns the groups d = 4l .. 4l+3 and (D > 128) 128 + 4l .. 128 + 4l+3
+    const int l4 = lp.first4();
+    const int ng = M.D > 128 ? 2 : 1;
+    float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, y[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int gI = 0; gI < ng; ++gI) {
+      const int d0 = 128 * gI + l4;
+      if (d0 < M.D) {
+        T qv[4], br[4];
+        ld4(q + d0, qv); ld4(M.beta_ref + d0, br);
+        for (int e = 0; e < 4; ++e) dv[gI][e] = (d0 + e < M.D) ? (float)qv[e] - (float)br[e] : 0.f;
       }
     }
-    if (d0 < M.D) {
-      T gv[4]; double g0[4];
-      ld4(g + d0, gv); ld4(M.grad0 + d0, g0);
-      const int nv = M.D - d0 < 4 ? M.D - d0 : 4;
-      (void)sg; (void)bs;
-      for (int e = 0; e < 4; ++e) {
-        gv[e] = gv[e] - T(y[e]);
-        if (e < nv) part[0] = fma_((double)dv[e], g0[e] - 0.5 * (double)y[e] + (1.0 / 3.0) * (double)rem[e], part[0]);
+    // rows k >= D of H0 are zero padding up to Dp (a multiple of 32) and δ_k = 0 there: no guards, so the row loads of two
+    // steps are in flight together (guarded, the compiler serialised them: one L2 round trip per row, 35 us per chain)
+    const float* Hl = M.lin_H + (l4 < M.Dp ? l4 : 0);   // lanes beyond the row read a valid (unused) address
+    if (ng == 1) {
+      for (int kk = 0; 4 * kk < M.D; kk += 2) {
+        float4 hr[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) hr[u] = *reinterpret_cast<const float4*>(Hl + (int64_t)(4 * kk + u) * M.Dp);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float b = __shfl_sync(0xffffffffu, dv[0][u & 3], kk + (u >> 2));
+          y[0][0] = fmaf(hr[u].x, b, y[0][0]); y[0][1] = fmaf(hr[u].y, b, y[0][1]); y[0][2] = fmaf(hr[u].z, b, y[0][2]); y[0][3] = fmaf(hr[u].w, b, y[0][3]);
+        }
       }
-      st4(g + d0, gv, nv);
+    } else {
+      const bool two = 128 + l4 < M.Dp;
+      for (int gk = 0; gk < 2; ++gk) {                     // δ_k is broadcast from lane (k % 128) / 4, group k / 128
+        const int kend = (M.D - 128 * gk + 3) / 4 < 32 ? (M.D - 128 * gk + 3) / 4 : 32;
+        for (int kk = 0; kk < kend; ++kk) {
+          float4 hr[4], hs[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float* rowp = Hl + (int64_t)(128 * gk + 4 * kk + u) * M.Dp;
+            hr[u] = *reinterpret_cast<const float4*>(rowp);
+            hs[u] = two ? *reinterpret_cast<const float4*>(rowp + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float b = __shfl_sync(0xffffffffu, gk ? dv[1][u] : dv[0][u], kk);
+            y[0][0] = fmaf(hr[u].x, b, y[0][0]); y[0][1] = fmaf(hr[u].y, b, y[0][1]); y[0][2] = fmaf(hr[u].z, b, y[0][2]); y[0][3] = fmaf(hr[u].w, b, y[0][3]);
+            y[1][0] = fmaf(hs[u].x, b, y[1][0]); y[1][1] = fmaf(hs[u].y, b, y[1][1]); y[1][2] = fmaf(hs[u].z, b, y[1][2]); y[1][3] = fmaf(hs[u].w, b, y[1][3]);
+          }
+        }
+      }
+    }
+    (void)sg; (void)bs;
+    for (int gI = 0; gI < ng; ++gI) {
+      const int d0 = 128 * gI + l4;
+      if (d0 < M.D) {
+        T gv[4]; double g0[4];
+        ld4(g + d0, gv); ld4(M.grad0 + d0, g0);
+        const int nv = M.D - d0 < 4 ? M.D - d0 : 4;
+        for (int e = 0; e < 4; ++e) {
+          gv[e] = gv[e] - T(y[gI][e]);
+          if (e < nv) part[0] = fma_((double)dv[gI][e], g0[e] - 0.5 * (double)y[gI][e] + (1.0 / 3.0) * (double)rem[gI][e], part[0]);
+        }
+        st4(g + d0, gv, nv);
+      }
     }
 #else
     for (int d = 0; d < M.D; ++d) {   // host build: same definition, plain loops (the tensor path itself is CUDA-only)

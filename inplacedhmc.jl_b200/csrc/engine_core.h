@@ -196,7 +196,8 @@ template <class T, class X> struct EngineCore {
     EngineMem<T> V = M;
     V.stage_q = wide_q; V.stage_bh = wide_bh; V.stage_bm = wide_bm; V.stage_bl = wide_bl;
     V.stage_active = d_active;
-    V.stage_g = red_g; V.stage_ld = red_l; V.stage_nb = 1; V.stage_rows = (int32_t)rows; V.lin_w = nullptr; V.grad0 = nullptr; V.lin_H = nullptr;
+    V.stage_g = red_g; V.stage_ld = red_l; V.stage_nb = 1; V.stage_rows = (int32_t)rows; V.lin_w = nullptr;
+    if (!M.lin_H) V.grad0 = nullptr;   // remainder mode: the consumer adds g0 - H0 (q - beta_ref) (constants summed over the group at set-up)
     return V;
   }
 

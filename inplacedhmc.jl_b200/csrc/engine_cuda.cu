@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_fold_partials(EngineMem<T> M, i
     T acc = T(0);
     if (d < M.D) {
       for (int b = 0; b < M.stage_nb; ++b) acc = acc + sg[b * bs + d];
-      if (M.grad0) acc = T((double)acc + M.grad0[d]);
+      if (M.grad0 && !M.lin_H) acc = T((double)acc + M.grad0[d]);   // remainder mode: the consumer adds g0 (summed over the group) with the linear part
       if (M.lin_w) lin = fma(M.lin_w[d], (double)M.stage_q[(int64_t)row * M.Dp + d], lin);
     }
     red_g[(int64_t)row * M.Dp + d] = acc;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_fold_push(EngineMem<T> M, int r
       T acc = T(0);
       if (d < M.D) {
         for (int b = 0; b < M.stage_nb; ++b) acc = acc + sg[b * bs + d];
-        if (M.grad0) acc = T((double)acc + M.grad0[d]);
+        if (M.grad0 && !M.lin_H) acc = T((double)acc + M.grad0[d]);
         if (M.lin_w) lin = fma(M.lin_w[d], (double)M.stage_q[(int64_t)row * M.Dp + d], lin);
       }
       for (int r = 0; r < V.world; ++r)

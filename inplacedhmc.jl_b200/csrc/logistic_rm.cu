@@ -107,11 +107,15 @@ __device__ __forceinline__ void mma_ss_mn_run(uint32_t d_tmem, uint32_t a_lo, ui
 
 template <int DT, int NC, int NT> struct RmPlan {
   static constexpr int KC = DT / 64;
-  static constexpr int B_BYTES = KC * CHUNK_BYTES;          // one ΔB term: 128 staged rows x DT columns
-  static constexpr int X_BYTES = KC * CHUNK_BYTES;          // one X stage
+  static constexpr int BR = NC > 64 ? 128 : 64;              // staged rows per ΔB tile (TMA box height)
+  static constexpr int B_CHUNK = BR * 128;                   // one 64-column chunk of a ΔB tile
+  static constexpr int B_BYTES = KC * B_CHUNK;               // one ΔB term
+  static constexpr int X_BYTES = KC * CHUNK_BYTES;           // one X stage: 128 rows x DT columns
   static constexpr int R_BYTES = (NC > 64 ? 2 : 1) * CHUNK_BYTES;   // one R buffer: 128 rows x NC chains (64-chain chunks)
   static constexpr int NSB = 3;                              // S buffers in TMEM
   static constexpr int NRB = 2;                              // R buffers in shared memory
+  static constexpr int NGH = DT > 128 ? 2 : 1;               // 128-feature halves of the GEMM2 accumulator
+  static_assert(NSB * 128 + NGH * NC <= 512, "TMEM columns");
   static constexpr int FIXED = NT * B_BYTES + NRB * R_BYTES + 512;
   static constexpr int NS0 = (232448 - FIXED) / X_BYTES;     // X stages: as many as fit (the stage of block i is held from its TMA
   static constexpr int NS = NS0 > 8 ? 8 : NS0;               // load until GEMM2(i) has read it, so depth hides the HBM latency)
@@ -183,8 +187,8 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (lane == 0 && nb > 0) {
       mbar_expect_tx(bar_b, NT * P::B_BYTES);
       for (int kc = 0; kc < KC; ++kc) {
-        tma_load_2d(&tmBh, sB + 0 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * NC);
-        if (NT > 1) tma_load_2d(&tmBm, sB + 1 * P::B_BYTES + kc * CHUNK_BYTES, bar_b, kc * 64, tile * NC);
+        tma_load_2d(&tmBh, sB + 0 * P::B_BYTES + kc * P::B_CHUNK, bar_b, kc * 64, tile * NC);
+        if (NT > 1) tma_load_2d(&tmBm, sB + 1 * P::B_BYTES + kc * P::B_CHUNK, bar_b, kc * 64, tile * NC);
       }
       // L2 prefetch PF blocks ahead of the loads: a stage is refilled only after GEMM2 of its previous block, so the refill
       // itself must not wait on HBM
@@ -225,11 +229,11 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
           for (int c = 0; c < (NK + 3) / 4; ++c) {
             constexpr int LAST = NK - ((NK + 3) / 4 - 1) * 4;   // K steps in the last chunk
-            const uint32_t off = (uint32_t)(c * (CHUNK_BYTES >> 4));
+            const uint32_t off = (uint32_t)(c * (CHUNK_BYTES >> 4)), offb = (uint32_t)(c * (P::B_CHUNK >> 4));
             const uint32_t acc = (term | c) ? 1u : 0u;
             if (RMDBG & 2) continue;
-            if (c + 1 < (NK + 3) / 4) mma_ss_run<4>(d, xlo + off, km_hi, bB[term] + off, km_hi, IDESC1, acc);
-            else mma_ss_run<LAST>(d, xlo + off, km_hi, bB[term] + off, km_hi, IDESC1, acc);
+            if (c + 1 < (NK + 3) / 4) mma_ss_run<4>(d, xlo + off, km_hi, bB[term] + offb, km_hi, IDESC1, acc);
+            else mma_ss_run<LAST>(d, xlo + off, km_hi, bB[term] + offb, km_hi, IDESC1, acc);
           }
         }
         if (elect_one()) tc_commit(&s_full[buf]);
@@ -258,8 +262,12 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const uint32_t rm = mn_lo0 + ((aR + (uint32_t)rb * P::R_BYTES) >> 4);
           const uint32_t acc0 = (in_period > 0 || ph > 0) ? 1u : 0u;
           if (!(RMDBG & 4)) {
-            mma_ss_mn_run<4>(tmem_G, xm, mn_hi, rm, mn_hi, IDESC2, acc0);
-            mma_ss_mn_run<4>(tmem_G, xm + 4u * 128u, mn_hi, rm + 4u * 128u, mn_hi, IDESC2, 1u);
+#pragma unroll
+            for (int gh = 0; gh < P::NGH; ++gh) {   // features 128 gh .. 128 gh + 127: the 64-column chunks 2 gh, 2 gh + 1 of the X tile
+              const uint32_t xa = xm + (uint32_t)gh * (2u * CHUNK_BYTES >> 4), dg = tmem_G + (uint32_t)(gh * NC);
+              mma_ss_mn_run<4>(dg, xa, mn_hi, rm, mn_hi, IDESC2, acc0);
+              mma_ss_mn_run<4>(dg, xa + 4u * 128u, mn_hi, rm + 4u * 128u, mn_hi, IDESC2, 1u);
+            }
           }
           if (elect_one()) { if (ph + 1 == nph) tc_commit(&x_empty[st]); tc_commit(&r_empty[rb]); }
           __syncwarp();
@@ -292,7 +300,7 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         for (int u = 0; u < 8; ++u) {
           uint32_t w0, w1, w2, w3;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                       : "r"(base + (uint32_t)kc * CHUNK_BYTES + (uint32_t)((u ^ (c & 7)) << 4)));
+                       : "r"(base + (uint32_t)kc * P::B_CHUNK + (uint32_t)((u ^ (c & 7)) << 4)));
           const uint32_t ws[4] = {w0, w1, w2, w3};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -441,18 +449,19 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           tc_fence_after();
           if (live) {
 #pragma unroll 1
-            for (int qt = 0; qt < 4; ++qt) {
+            for (int gq = 0; gq < 4 * P::NGH; ++gq) {
+              const int gh = gq >> 2, qt = gq & 3, feat = gh * 128 + r;
               uint32_t w[8];
-              tmem_ld8(tmem_G + lane_sel + (uint32_t)h * 32u + (uint32_t)qt * 8u, w);
+              tmem_ld8(tmem_G + lane_sel + (uint32_t)(gh * NC) + (uint32_t)h * 32u + (uint32_t)qt * 8u, w);
               tmem_ld_wait();
-              if (r < Dp) {
+              if (feat < Dp) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const int row = tile * NC + h * 32 + qt * 8 + j;
                   if (row < nrows) {
-                    float* gp = G + ((size_t)split * nrows + (size_t)row) * Dp + r;   // lanes = consecutive features: one 128-byte line per warp
+                    float* gp = G + ((size_t)split * nrows + (size_t)row) * Dp + feat;   // lanes = consecutive features: one 128-byte line per warp
                     if (RMDBG) { *gp = 0.f; continue; }
-                    if (period > 0) atomicAdd(gp, __uint_as_float(w[j]));              // only this thread ever touches the address: same bits as load + add
+                    if (period > 0) atomicAdd(gp, __uint_as_float(w[j]));                 // only this thread ever touches the address: same bits as load + add
                     else *gp = __uint_as_float(w[j]);
                   }
                 }
@@ -499,15 +508,14 @@ template <int DT, int NK, int NC, int NT> void launch_rm_nc(LogisticTC& tc, cuda
   dim3 grid(tiles, nsplit);
   CUtensorMap m[3];
   std::memcpy(&m[0], tc.tmaps[0], sizeof(CUtensorMap));
-  std::memcpy(&m[1], tc.tmaps[1], sizeof(CUtensorMap));
-  std::memcpy(&m[2], tc.tmaps[2], sizeof(CUtensorMap));
+  std::memcpy(&m[1], tc.tmaps[NC > 64 ? 1 : 5], sizeof(CUtensorMap));   // ΔB high / middle terms: 128- or 64-row boxes
+  std::memcpy(&m[2], tc.tmaps[NC > 64 ? 2 : 6], sizeof(CUtensorMap));
   k_logistic_rm<DT, NK, NC, NT><<<grid, RM_THREADS, P::TOTAL, s>>>(m[0], m[1], m[2], reinterpret_cast<const float4*>(tc.rec), tc.G, tc.Ld, nrows,
                                                                tc.D, tc.Dp, (int)(tc.Npad / ROWS), nsplit, tc.flush_every, tc.kappa2);
 }
 template <int DT, int NK> void launch_rm_nk(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit, int nc) {
-  if (tc.rm_terms == 1) {
-    if (nc == 64) launch_rm_nc<DT, NK, 64, 1>(tc, s, nrows, nsplit);
-    else launch_rm_nc<DT, NK, 128, 1>(tc, s, nrows, nsplit);
+  if constexpr (DT > 128) {
+    launch_rm_nc<DT, NK, 64, 2>(tc, s, nrows, nsplit);   // two ΔB terms of 256 columns leave room for 64-chain tiles only
   } else {
     if (nc == 64) launch_rm_nc<DT, NK, 64, 2>(tc, s, nrows, nsplit);
     else launch_rm_nc<DT, NK, 128, 2>(tc, s, nrows, nsplit);
@@ -558,12 +566,14 @@ __global__ void k_rm_g0_sum(const double* __restrict__ part, double* grad0, doub
     if (d < Dp) grad0[d] = acc; else *ell0 = acc;
   }
 }
-constexpr int H0_BLOCKS = 148, H0_THREADS = 512, H0_ACC = 32;   // D x D <= 128 x 128 = 512 x 32 accumulators per block
-// H = X̃ᵀ diag(w) X̃ (w == nullptr: X̃ᵀX̃) in Float64 from the stored fp32 w: each block sums a contiguous range of rows
-// into D x D register accumulators (pair p = a D + b -> thread p % 512, slot p / 512), then one pass adds the blocks in order
+constexpr int H0_BLOCKS = 148, H0_THREADS = 512, H0_ACC = 32;   // a 128 x 128 block of the matrix = 512 x 32 accumulators per thread block
+// H = X̃ᵀ diag(w) X̃ (w == nullptr: X̃ᵀX̃) in Float64 from the stored fp32 w, one 128 x 128 block (a0, b0) of it per launch:
+// each thread block sums a contiguous range of rows into register accumulators (pair p = a 128 + b -> thread p % 512, slot
+// p / 512), then one pass adds the blocks in order
 __global__ void __launch_bounds__(H0_THREADS) k_rm_hess_partial(const uint16_t* __restrict__ Xb, const float* __restrict__ w, double* part,
-                                                                long long N, int D, int Dt) {
-  __shared__ float xs[8][128];
+                                                                long long N, int D, int Dt, int a0, int b0) {
+  __shared__ float xa[8][128];
+  __shared__ float xb[8][128];
   __shared__ float ws[8];
   const long long r0 = N * blockIdx.x / gridDim.x, r1 = N * (blockIdx.x + 1) / gridDim.x;
   double acc[H0_ACC];
@@ -572,30 +582,27 @@ __global__ void __launch_bounds__(H0_THREADS) k_rm_hess_partial(const uint16_t* 
   for (int m = 0; m < H0_ACC; ++m) {
     acc[m] = 0.0;
     const int p = threadIdx.x + m * H0_THREADS;
-    pa[m] = p < D * D ? p / D : -1;
-    pb[m] = p < D * D ? p % D : 0;
+    pa[m] = p >> 7; pb[m] = p & 127;
   }
   for (long long it = r0; it < r1; it += 8) {
     const int nr = (int)((r1 - it < 8) ? (r1 - it) : 8);
     __syncthreads();
     for (int idx = threadIdx.x; idx < nr * 128; idx += H0_THREADS) {
       const int rr = idx >> 7, d = idx & 127;
-      xs[rr][d] = d < D ? bf16_val(Xb[(it + rr) * Dt + d]) : 0.f;
+      xa[rr][d] = a0 + d < D ? bf16_val(Xb[(it + rr) * Dt + a0 + d]) : 0.f;
+      xb[rr][d] = b0 + d < D ? bf16_val(Xb[(it + rr) * Dt + b0 + d]) : 0.f;
     }
     if (threadIdx.x < nr) ws[threadIdx.x] = w ? w[it + threadIdx.x] : 1.f;
     __syncthreads();
     for (int rr = 0; rr < nr; ++rr) {
       const double wv = (double)ws[rr];
 #pragma unroll
-      for (int m = 0; m < H0_ACC; ++m)
-        if (pa[m] >= 0) acc[m] = fma((double)(xs[rr][pa[m]] * xs[rr][pb[m]]), wv, acc[m]);   // bf16 x bf16 is exact in fp32
+      for (int m = 0; m < H0_ACC; ++m) acc[m] = fma((double)(xa[rr][pa[m]] * xb[rr][pb[m]]), wv, acc[m]);   // bf16 x bf16 is exact in fp32
     }
   }
 #pragma unroll
-  for (int m = 0; m < H0_ACC; ++m) {
-    const int p = threadIdx.x + m * H0_THREADS;
-    if (p < D * D) part[(size_t)blockIdx.x * D * D + p] = acc[m];
-  }
+  for (int m = 0; m < H0_ACC; ++m)
+    if (a0 + pa[m] < D && b0 + pb[m] < D) part[((size_t)blockIdx.x * D + (a0 + pa[m])) * D + (b0 + pb[m])] = acc[m];
 }
 __global__ void k_rm_hess_sum(const double* __restrict__ part, float* H, int nb, int D, int Dp) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -616,14 +623,23 @@ void logistic_rm_launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit, i
     case 5: launch_rm_nk<128, 5>(tc, s, nrows, nsplit, nc); break;
     case 6: launch_rm_nk<128, 6>(tc, s, nrows, nsplit, nc); break;
     case 7: launch_rm_nk<128, 7>(tc, s, nrows, nsplit, nc); break;
-    default: launch_rm_nk<128, 8>(tc, s, nrows, nsplit, nc); break;
+    case 8: launch_rm_nk<128, 8>(tc, s, nrows, nsplit, nc); break;
+    case 9: launch_rm_nk<192, 9>(tc, s, nrows, nsplit, nc); break;
+    case 10: launch_rm_nk<192, 10>(tc, s, nrows, nsplit, nc); break;
+    case 11: launch_rm_nk<192, 11>(tc, s, nrows, nsplit, nc); break;
+    case 12: launch_rm_nk<192, 12>(tc, s, nrows, nsplit, nc); break;
+    case 13: launch_rm_nk<256, 13>(tc, s, nrows, nsplit, nc); break;
+    case 14: launch_rm_nk<256, 14>(tc, s, nrows, nsplit, nc); break;
+    case 15: launch_rm_nk<256, 15>(tc, s, nrows, nsplit, nc); break;
+    default: launch_rm_nk<256, 16>(tc, s, nrows, nsplit, nc); break;
   }
 }
 
 // per-row records, g0 = X̃ᵀ r0, ℓ0 = Σ log σ(η̃0), H0 = X̃ᵀ diag(w) X̃ and the radius κ of the Taylor path.
 // κ: the row-wise rms of δ = x̃·(β − β₀) is at most sqrt(λ_max(X̃ᵀX̃ / N))·‖β − β₀‖; the degree-4 remainder is good to ~1e-2·15·s⁴
 // of the gradient at rms s, so chains with a bound above 0.08 take the closed forms instead.
-int32_t logistic_rm_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev, std::string& err) {
+int32_t logistic_rm_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev, RmGroupSum group_sum, void* group_ctx,
+                                    int world, std::string& err) {
   const size_t np = size_t(tc.Npad);
   auto need = [&](void** p, size_t bytes) { return *p || cudaMalloc(p, bytes) == cudaSuccess; };
   if (!need((void**)&tc.rec, np * 16) || !need((void**)&tc.rm_r0, np * 4) || !need((void**)&tc.rm_w, np * 4) || !need((void**)&tc.rm_f0, np * 8) ||
@@ -638,8 +654,16 @@ int32_t logistic_rm_write_reference(LogisticTC& tc, cudaStream_t s, const float*
   k_rm_g0_sum<<<1, 160, 0, s>>>(tc.rm_part, tc.grad0, tc.ell0, RMG_BLOCKS, tc.Dp);
   // λ_max(X̃ᵀX̃ / N) by power iteration on the host (D x D), then H0 into the same buffer
   cudaMemsetAsync(tc.H0, 0, size_t(tc.Dp) * tc.Dp * 4, s);
-  k_rm_hess_partial<<<H0_BLOCKS, H0_THREADS, 0, s>>>(tc.Xb, nullptr, tc.H0_part, (long long)tc.N, tc.D, tc.Dt);
+  for (int a0 = 0; a0 < tc.D; a0 += 128)
+    for (int b0 = 0; b0 < tc.D; b0 += 128)
+      k_rm_hess_partial<<<H0_BLOCKS, H0_THREADS, 0, s>>>(tc.Xb, nullptr, tc.H0_part, (long long)tc.N, tc.D, tc.Dt, a0, b0);
   k_rm_hess_sum<<<(tc.D * tc.D + 255) / 256, 256, 0, s>>>(tc.H0_part, tc.H0, H0_BLOCKS, tc.D, tc.Dp);
+  // rows sharded over a group of engines: every constant is a sum over ALL rows (g0 and X̃ᵀX̃ here, ℓ0 and H0 below)
+  if (group_sum) {
+    int32_t rc = group_sum(group_ctx, tc.H0, (int64_t)tc.Dp * tc.Dp, tc.grad0, tc.Dp);
+    if (!rc) rc = group_sum(group_ctx, nullptr, 0, tc.ell0, 1);
+    if (rc) { err = "remainder-mode reference: the sum over the row group failed"; return rc; }
+  }
   std::vector<float> g2(size_t(tc.Dp) * tc.Dp);
   if (cudaMemcpyAsync(g2.data(), tc.H0, g2.size() * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
     err = "remainder-mode reference: device failure";
@@ -660,16 +684,20 @@ int32_t logistic_rm_write_reference(LogisticTC& tc, cudaStream_t s, const float*
       if (!(lam > 0.0)) break;
       for (int a = 0; a < D; ++a) v[size_t(a)] = y[size_t(a)] / lam;
     }
-    lam = 1.1 * lam / double(tc.N);                      // power iteration converges from below
+    lam = 1.1 * lam / (double(tc.N) * double(world));     // power iteration converges from below; equal shards
     const char* ke = std::getenv("BNUTS_TC_RM_RADIUS");   // rms of δ beyond which a chain takes the closed forms (default 0.08)
     const double s_max = ke ? std::atof(ke) : 0.08;
     tc.kappa2 = lam > 0.0 ? float(s_max * s_max / lam) : 0.f;
-    const char* te = std::getenv("BNUTS_TC_RM_TERMS");   // bf16 terms of β − β₀ in GEMM1 (the remainder needs three digits of δ)
-    tc.rm_terms = te && std::atoi(te) == 1 ? 1 : 2;
   }
   cudaMemsetAsync(tc.H0, 0, size_t(tc.Dp) * tc.Dp * 4, s);
-  k_rm_hess_partial<<<H0_BLOCKS, H0_THREADS, 0, s>>>(tc.Xb, tc.rm_w, tc.H0_part, (long long)tc.N, tc.D, tc.Dt);
+  for (int a0 = 0; a0 < tc.D; a0 += 128)
+    for (int b0 = 0; b0 < tc.D; b0 += 128)
+      k_rm_hess_partial<<<H0_BLOCKS, H0_THREADS, 0, s>>>(tc.Xb, tc.rm_w, tc.H0_part, (long long)tc.N, tc.D, tc.Dt, a0, b0);
   k_rm_hess_sum<<<(tc.D * tc.D + 255) / 256, 256, 0, s>>>(tc.H0_part, tc.H0, H0_BLOCKS, tc.D, tc.Dp);
+  if (group_sum) {
+    const int32_t rc = group_sum(group_ctx, tc.H0, (int64_t)tc.Dp * tc.Dp, nullptr, 0);
+    if (rc) { err = "remainder-mode reference: the sum over the row group failed"; return rc; }
+  }
   if (cudaMemcpyAsync(&tc.ell0_host, tc.ell0, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
     err = "remainder-mode reference: device failure";
     return BNUTS_ERR_CUDA;

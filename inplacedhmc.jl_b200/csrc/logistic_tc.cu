@@ -854,7 +854,7 @@ int LogisticTC::plan_splits(int nrows, int tile_rows) const {
 void LogisticTC::run(cudaStream_t s, int nrows) {
   if (!ready || nrows <= 0) return;
   if (rmode == 2) {   // remainder mode: chains are the MMA N dimension, 64-chain tiles for small launches
-    const int nc = nrows <= 64 ? 64 : 128;
+    const int nc = (nrows <= 64 || variant == 256) ? 64 : 128;
     last_nsplit = plan_splits(nrows, nc);
     logistic_rm_launch(*this, s, nrows, last_nsplit, nc);
     return;
@@ -1053,7 +1053,10 @@ int32_t tc_alloc(LogisticTC& tc, std::string& err) {
     const int nr = std::min<int>(tc.C, tiles * CHAINS);
     worst = std::max<int64_t>(worst, (int64_t)tc.plan_splits(nr) * nr);
   }
-  worst = std::max<int64_t>(worst, (int64_t)tc.plan_splits(64, 64) * std::min<int>(tc.C, 64));   // remainder mode: 64-chain tiles
+  for (int tiles = 1; tiles <= (tc.C + 63) / 64; ++tiles) {   // remainder mode: 64-chain tiles (small launches; every launch for D > 128)
+    const int nr = std::min<int>(tc.C, tiles * 64);
+    worst = std::max<int64_t>(worst, (int64_t)tc.plan_splits(nr, 64) * nr);
+  }
   tc.partial_rows = worst;
   return 0;
 }
@@ -1110,7 +1113,11 @@ int32_t logistic_tc_maps(LogisticTC& tc, std::string& err) {
     err = "cuTensorMapEncodeTiled failed";
     return BNUTS_ERR_CUDA;
   }
-  if (!encode_map(tc.tmaps[4], tc.Xb, (uint64_t)tc.Npad, (uint64_t)tc.Dt, 64)) { err = "cuTensorMapEncodeTiled failed"; return BNUTS_ERR_CUDA; }
+  if (!encode_map(tc.tmaps[4], tc.Xb, (uint64_t)tc.Npad, (uint64_t)tc.Dt, 64) || !encode_map(tc.tmaps[5], tc.bh, crow, (uint64_t)tc.Dt, 64) ||
+      !encode_map(tc.tmaps[6], tc.bm, crow, (uint64_t)tc.Dt, 64)) {
+    err = "cuTensorMapEncodeTiled failed";
+    return BNUTS_ERR_CUDA;
+  }
   tc.ready = true;
   return 0;
 }

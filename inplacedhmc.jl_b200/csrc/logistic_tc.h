@@ -44,7 +44,7 @@ struct LogisticTC {
   float* G = nullptr;        // [nsplit][rows][Dp]
   double* Ld = nullptr;      // [nsplit][C] log-density partials (Float64: ~1e5..1e6 in magnitude)
   // opaque tensor maps (4 x CUtensorMap, 128 B each, 64 B aligned): X, βh, βm, βl
-  alignas(64) unsigned char tmaps[5][128];   // X (128-row box), βh, βm, βl, X (64-row box)
+  alignas(64) unsigned char tmaps[7][128];   // X (128-row box), βh, βm, βl, X (64-row box), βh and βm with 64-row boxes
   int32_t variant = 128;     // 128: k_logistic_tc (D <= 128, 128-row blocks); 256: k_logistic_tc256 (128 < D <= 256, 64-row blocks)
   bool ready = false;
   cudaError_t last = cudaSuccess;
@@ -73,7 +73,10 @@ void logistic_tc_write_residual_reference(LogisticTC& tc, cudaStream_t s, const 
 // staging rows: 1.0 in the reserved columns of the high term
 void logistic_tc_init_stage(LogisticTC& tc, cudaStream_t s, uint16_t* bh);
 // remainder mode (logistic_rm.cu): reference constants (records, g0 into tc.grad0, ℓ0, H0, κ²) and the launch
-int32_t logistic_rm_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev, std::string& err);
+// group_sum (or null): adds an fp32 and a Float64 device buffer in place over the engines that share the rows (either may be empty)
+typedef int32_t (*RmGroupSum)(void* ctx, float* f32, int64_t nf, double* f64, int64_t nd);
+int32_t logistic_rm_write_reference(LogisticTC& tc, cudaStream_t s, const float* beta_ref_dev, RmGroupSum group_sum, void* group_ctx,
+                                    int world, std::string& err);
 void logistic_rm_launch(LogisticTC& tc, cudaStream_t s, int nrows, int nsplit, int nc);
 
 template <class E> int32_t logistic_tc_attach(LogisticTC& tc, E& eng, std::string& err);
@@ -211,15 +214,28 @@ int32_t logistic_tc_set_reference(LogisticTC& tc, E& eng, const double* beta_ref
     // linear / quadratic part is exact D x D arithmetic in the consumer and only the small remainder goes through the tensor
     // cores, as ONE bf16 term.  Default where it applies; BNUTS_TC_RMODE=0/1/2 overrides (0 / 1: the residual operands above).
     const char* rme = std::getenv("BNUTS_TC_RMODE");
-    const bool rm_ok = tc.variant == 128 && tc.aug && !eng.reduce_on;
+    // (D <= 125: the spare K columns are not needed, but the exact path the check above ran on has them; 128 < D <= 256: 64-chain
+    // tiles; rows sharded: the set-up sums go over the row group, which needs a collective — NCCL or the host callback, not the
+    // peer-memory exchange)
+    const bool rm_ok = ((tc.variant == 128 && tc.aug) || tc.variant == 256) && (!eng.reduce_on || !eng.p2p_on);
     // ... by itself only for tall problems: the posterior's row-wise rms of δ is about sqrt(D / (N/5)); beyond ~0.04 most chains
     // would sit outside the Taylor radius and take the closed forms (correct, but no faster than the modes above)
-    const bool rm_auto = rm_ok && double(tc.N) >= 3000.0 * double(M.D);
+    const bool rm_auto = rm_ok && double(tc.N) * double(eng.reduce_world()) >= 3000.0 * double(M.D);
     int want = rme ? std::atoi(rme) : (rr ? (std::atoi(rr) != 0 ? 1 : 0) : (rm_auto ? 2 : (rr_auto ? 1 : 0)));
     if (want == 2 && !rm_ok) want = rr_auto ? 1 : 0;
     if (want == 2) {
       logistic_tc_write_reference(tc, x.stream, nullptr);   // S = X̃·(β − β₀) only: the reference columns of X̃ stay clear
-      int32_t rc2 = logistic_rm_write_reference(tc, x.stream, tc.beta_ref, err);
+      struct Ctx { E* eng; } ctx{&eng};
+      RmGroupSum gs = nullptr;
+      if (eng.reduce_on)
+        gs = [](void* c, float* f32, int64_t nf, double* f64, int64_t nd) -> int32_t {
+          E& en = *static_cast<Ctx*>(c)->eng;
+          // x.allreduce sums one fp32 and one Float64 buffer; an empty one is replaced by a one-element scratch
+          float* fb = nf ? f32 : reinterpret_cast<float*>(en.red_g);
+          double* db = nd ? f64 : en.red_l;
+          return en.x.allreduce(fb, nf ? nf : 1, true, db, nd ? nd : 1, en.red_fn, en.red_ctx, en.err);
+        };
+      int32_t rc2 = logistic_rm_write_reference(tc, x.stream, tc.beta_ref, gs, &ctx, eng.reduce_world(), err);
       if (rc2) return rc2;
       tc.rmode = 2;
       M.grad0 = tc.grad0; M.lin_H = tc.H0; M.ell0 = tc.ell0_host; M.lin_w = nullptr;
