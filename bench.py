@@ -531,12 +531,13 @@ def main():
         rterms = 2 if (a.config == "c3") else 1
         # remainder mode (csrc/logistic_rm.cu): what logistic_tc_set_reference takes by itself for D <= 125, N >= 3000 D, rows not sharded
         rmode_env = os.environ.get("BNUTS_TC_RMODE")
-        remainder = (terms == 2 and D <= 125 and a.config == "c3" and (int(rmode_env) == 2 if rmode_env else (N >= 3000 * D and "BNUTS_TC_RREF" not in os.environ)))
+        remainder = (terms == 2 and (D <= 125 or D > 128) and (a.config == "c3" or a.exchange == "nccl" or world == 1)
+                     and (int(rmode_env) == 2 if rmode_env else (N >= 3000 * D and "BNUTS_TC_RREF" not in os.environ)))
         if remainder:
             kern = "k_logistic_rm"
         # executed on the tensor pipe per algorithmic flop: K padded to 16 and the position operand in `terms` bf16 terms in GEMM1;
         # the residual in `rterms` terms with N = dk (k_logistic_tc) or the remainder in one term with M = 128 features (k_logistic_rm) in GEMM2
-        exe = ((terms * dk + 128) / (2.0 * D)) if remainder else ((terms + rterms) * dk / (2.0 * D))
+        exe = ((terms * dk + (128 if D <= 128 else 256)) / (2.0 * D)) if remainder else ((terms + rterms) * dk / (2.0 * D))
         out["dtype"] = "f32 (exact bf16 operand splits on tcgen05, fp32 accumulate)"
         config["l2"] = "inputs larger than L2 (X is %d MB bf16 per GPU)" % (N_gpu * (128 if D <= 128 else 256) * 2 // 2**20)
         config["position_operand_terms"] = terms

@@ -399,7 +399,18 @@ template <class T, class X> struct EngineCore {
   int32_t logistic_set_reference(const double* beta_ref) {
     if (model.kind != MODEL_LOGISTIC || !model.tensor)
       return fail(BNUTS_ERR_UNSUPPORTED, "reference point applies to the tensor-core logistic path only");
-    return x.logistic_reference(*this, beta_ref, err);
+    const int32_t rc = x.logistic_reference(*this, beta_ref, err);
+    if (rc) return rc;
+    // The reference changes the arithmetic of the model (operand split, residual mode, remainder mode): the (ℓ, ∇ℓ) the
+    // chains hold were computed by the previous arithmetic.  At N = 1e6 the two differ by ~3e-2 in ℓ; at N = 1e7 by several
+    // units, which no step-size search or Armijo test that starts from the stored ℓ survives.  Re-evaluate where the chains are.
+    x.gather_state(M, d_tmp_cd);
+    M.pos_in = d_tmp_cd;
+    PrepareArgs a{}; a.mode = MODE_EVAL;
+    if (reduce_on) x.prepare(reduce_view(0), rp, a); else x.prepare(M, rp, a);
+    const int32_t rc2 = run(true);
+    M.pos_in = nullptr;
+    return rc2;
   }
 
   // ---------------------------------------------------------------- state setters

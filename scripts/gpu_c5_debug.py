@@ -39,6 +39,17 @@ except bn.BnutsError as ex:
     print("search:", ex)
 show("after search")
 eps = e.get_stepsize()
+if os.environ.get("CHECK") == "1":   # the reference values of a single engine with all rows (rank 0 only builds it)
+    q = e.get_state()[0]
+    qs = q[:64] + np.random.default_rng(3).normal(size=(64, D)) * 1e-3
+    qq = np.tile(qs, (C // 64, 1))
+    e.set_positions(qq); _, g, l = e.get_state()
+    if rank == 0:
+        f = bn.Engine(C, D, dtype=bn.F32, seed=20261018, device=local, gradient_path=bn.GRAD_TENSOR)
+        f.model_logistic_synthetic(5, 0, N, 1.0); f.logistic_set_reference(q.mean(axis=0)); f.set_positions(qq)
+        _, gf, lf = f.get_state()
+        print("rows sharded vs one engine: grad rel diff max %.3g, log density abs diff max %.3g (l = %.8g)" % (
+            np.max(np.linalg.norm(g - gf, axis=1) / np.linalg.norm(gf, axis=1)), np.max(np.abs(l - lf)), lf[0]), flush=True)
 if rank == 0:
     print("eps", np.percentile(eps, [0, 50, 100]))
 if world > 1:
