@@ -162,7 +162,10 @@ template <class T> BN_HD void st4(T* p, const T (&v)[4], int nv) {
 #define BN_FOR4(d0, nv) \
   for (int d0 = lp.first4(), nv = (M.D - d0 < 4 ? M.D - d0 : 4); d0 < M.D; d0 += lp.stride4(), nv = (M.D - d0 < 4 ? M.D - d0 : 4))
 
-template <class T, class LP> struct Backend {
+// RM = 1: the kernel instance that serves the remainder mode of the tensor-core logistic path (logistic_rm.cu): only it carries
+// the D x D linear part (its registers and code would otherwise be charged to every target's state machine: measured −20 % on
+// the Gaussian and funnel configurations when it was compiled into the one kernel)
+template <class T, class LP, int RM = 0> struct Backend {
   const EngineMem<T>& M;
   int32_t c;
   LP lp;
@@ -363,6 +366,71 @@ template <class T, class LP> struct Backend {
     return lp.reduce(part);
   }
 
+  // ≙ logdensity_and_gradient! of the logistic target, second half: the batched kernel has written partial gradients / log
+  // densities for this chain's staging row; fold them, add the prior (and, in the remainder mode of the tensor path, the
+  // exact linear / quadratic part).  A real function: its registers must not be charged to the state machine of the other targets.
+  template <bool WITH_LIN> BN_HD double logistic_finalize_t(const T* q, T* g) const {
+    double l;
+    const int64_t row = M.stage_row[c], rows = M.stage_rows;
+    const int64_t bs = rows * M.Dp;
+    const T* sg = M.stage_g + row * M.Dp;
+    T rem4[2][4] = {{T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0)}};   // remainder mode (D <= 256: at most two groups per lane): the folded X̃ᵀρ of this lane's coordinates
+    BN_FOR4(d0, nv) {
+      T acc[4] = {T(0), T(0), T(0), T(0)}, qv[4], gv[4];
+      // the partial blocks are added in the order b = 0, 1, ... (fixed: the deterministic path is bit-identical to the
+      // oracle), but loaded four at a time: a small launch of the tensor path has up to 148 of them (one per SM) and one
+      // L2 round trip per partial made this fold the longest part of a lockstep step with few active chains
+      int b = 0;
+      for (; b + 4 <= M.stage_nb; b += 4) {
+        T p0[4], p1[4], p2[4], p3[4];
+        ld4(sg + (b + 0) * bs + d0, p0); ld4(sg + (b + 1) * bs + d0, p1); ld4(sg + (b + 2) * bs + d0, p2); ld4(sg + (b + 3) * bs + d0, p3);
+        for (int e = 0; e < 4; ++e) acc[e] = (((acc[e] + p0[e]) + p1[e]) + p2[e]) + p3[e];
+      }
+      for (; b < M.stage_nb; ++b) {
+        T pv[4];
+        ld4(sg + b * bs + d0, pv);
+        for (int e = 0; e < 4; ++e) acc[e] = acc[e] + pv[e];
+      }
+      if constexpr (WITH_LIN) { for (int e = 0; e < 4; ++e) rem4[(d0 >> 7) & 1][e] = acc[e]; }
+      if (M.grad0) {  // constant part of the gradient about the reference point (see k_logistic_tc)
+        double g0[4];
+        ld4(M.grad0 + d0, g0);
+        for (int e = 0; e < 4; ++e) acc[e] = T((double)acc[e] + g0[e]);
+      }
+      ld4(q + d0, qv);
+      for (int e = 0; e < 4; ++e) gv[e] = fma_(-M.tau, qv[e], acc[e]);
+      st4(g + d0, gv, nv);
+    }
+    double lin_l = 0.0;
+    if constexpr (WITH_LIN) { if (M.lin_H) lin_l = linear_part(q, g, rem4, sg, bs); }   // remainder mode: g −= H0 δ, ℓ += ell0 + δ·(g0 − ½ H0 δ + ⅓ X̃ᵀρ)
+    if (M.stage_ld) {  // tensor path: partials are ~1e5..1e7 in magnitude, summed and kept in Float64
+      // Float64 partials of the splits: lane l adds the splits l, l + 32, ..., then the butterfly (a fixed order; one round
+      // trip to L2 instead of one per split)
+      double pl[LP::NACC];
+      for (int i = 0; i < LP::NACC; ++i) pl[i] = 0.0;
+      for (int b = lp.first(); b < M.stage_nb; b += lp.stride()) pl[LP::NACC == 1 ? 0 : (b & 31)] += M.stage_ld[b * rows + row];
+      double lsd = lin_l + lp.reduce(pl);
+      if (M.lin_w) {  // linear part of Σ log σ(η̃): ½ Σ_i η̃_i = ½ colsum(X̃)·q
+        double part[LP::NACC];
+        for (int i = 0; i < LP::NACC; ++i) part[i] = 0.0;
+        BN_FOR4(d0, nv) {
+          T qv[4]; double wv[4];
+          ld4(q + d0, qv); ld4(M.lin_w + d0, wv);
+          for (int e = 0; e < nv; ++e) { double& a = part[lp.acc(d0 + e)]; a = fma_(wv[e], (double)qv[e], a); }
+        }
+        lsd = fma_(0.5, lp.reduce(part), lsd);
+      }
+      l = fma_(-0.5 * (double)M.tau, (double)dot(q, q), lsd);
+    } else {
+      T ls = T(0);
+      for (int b = 0; b < M.stage_nb; ++b) ls = ls + M.stage_l[b * rows + row];
+      l = (double)fma_(T(-0.5) * M.tau, dot(q, q), ls);
+    }
+
+    return l;
+  }
+  BN_HDN double logistic_finalize_rm(const T* q, T* g) const { return logistic_finalize_t<true>(q, g); }
+
   // ≙ logdensity_and_gradient! (call site src/kinetic_energy.jl:73); SURVEY.md §A.4 targets.
   // Elementwise targets are evaluated here; batched targets were evaluated by a
   // separate kernel into the staging buffers and are finalised here.
@@ -413,64 +481,9 @@ template <class T, class LP> struct Backend {
         l = (double)(T(0.5) * dot(q, g));
         break;
       }
-      case MODEL_LOGISTIC: {
-        const int64_t row = M.stage_row[c], rows = M.stage_rows;
-        const int64_t bs = rows * M.Dp;
-        const T* sg = M.stage_g + row * M.Dp;
-        T rem4[2][4] = {{T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0)}};   // remainder mode (D <= 256: at most two groups per lane): the folded X̃ᵀρ of this lane's coordinates
-        BN_FOR4(d0, nv) {
-          T acc[4] = {T(0), T(0), T(0), T(0)}, qv[4], gv[4];
-          // the partial blocks are added in the order b = 0, 1, ... (fixed: the deterministic path is bit-identical to the
-          // oracle), but loaded four at a time: a small launch of the tensor path has up to 148 of them (one per SM) and one
-          // L2 round trip per partial made this fold the longest part of a lockstep step with few active chains
-          int b = 0;
-          for (; b + 4 <= M.stage_nb; b += 4) {
-            T p0[4], p1[4], p2[4], p3[4];
-            ld4(sg + (b + 0) * bs + d0, p0); ld4(sg + (b + 1) * bs + d0, p1); ld4(sg + (b + 2) * bs + d0, p2); ld4(sg + (b + 3) * bs + d0, p3);
-            for (int e = 0; e < 4; ++e) acc[e] = (((acc[e] + p0[e]) + p1[e]) + p2[e]) + p3[e];
-          }
-          for (; b < M.stage_nb; ++b) {
-            T pv[4];
-            ld4(sg + b * bs + d0, pv);
-            for (int e = 0; e < 4; ++e) acc[e] = acc[e] + pv[e];
-          }
-          for (int e = 0; e < 4; ++e) rem4[(d0 >> 7) & 1][e] = acc[e];
-          if (M.grad0) {  // constant part of the gradient about the reference point (see k_logistic_tc)
-            double g0[4];
-            ld4(M.grad0 + d0, g0);
-            for (int e = 0; e < 4; ++e) acc[e] = T((double)acc[e] + g0[e]);
-          }
-          ld4(q + d0, qv);
-          for (int e = 0; e < 4; ++e) gv[e] = fma_(-M.tau, qv[e], acc[e]);
-          st4(g + d0, gv, nv);
-        }
-        double lin_l = 0.0;
-        if (M.lin_H) lin_l = linear_part(q, g, rem4, sg, bs);   // remainder mode: g −= H0 δ, ℓ += ell0 + δ·(g0 − ½ H0 δ + ⅓ X̃ᵀρ)
-        if (M.stage_ld) {  // tensor path: partials are ~1e5..1e7 in magnitude, summed and kept in Float64
-          // Float64 partials of the splits: lane l adds the splits l, l + 32, ..., then the butterfly (a fixed order; one round
-          // trip to L2 instead of one per split)
-          double pl[LP::NACC];
-          for (int i = 0; i < LP::NACC; ++i) pl[i] = 0.0;
-          for (int b = lp.first(); b < M.stage_nb; b += lp.stride()) pl[LP::NACC == 1 ? 0 : (b & 31)] += M.stage_ld[b * rows + row];
-          double lsd = lin_l + lp.reduce(pl);
-          if (M.lin_w) {  // linear part of Σ log σ(η̃): ½ Σ_i η̃_i = ½ colsum(X̃)·q
-            double part[LP::NACC];
-            for (int i = 0; i < LP::NACC; ++i) part[i] = 0.0;
-            BN_FOR4(d0, nv) {
-              T qv[4]; double wv[4];
-              ld4(q + d0, qv); ld4(M.lin_w + d0, wv);
-              for (int e = 0; e < nv; ++e) { double& a = part[lp.acc(d0 + e)]; a = fma_(wv[e], (double)qv[e], a); }
-            }
-            lsd = fma_(0.5, lp.reduce(part), lsd);
-          }
-          l = fma_(-0.5 * (double)M.tau, (double)dot(q, q), lsd);
-        } else {
-          T ls = T(0);
-          for (int b = 0; b < M.stage_nb; ++b) ls = ls + M.stage_l[b * rows + row];
-          l = (double)fma_(T(-0.5) * M.tau, dot(q, q), ls);
-        }
+      case MODEL_LOGISTIC:
+        if constexpr (RM != 0) l = logistic_finalize_rm(q, g); else l = logistic_finalize_t<false>(q, g);
         break;
-      }
       default: l = lim<double>::nan();
     }
     lp.sync();
@@ -483,7 +496,7 @@ template <class T, class LP> struct Backend {
   // Σ_i δ_i ρ_i / 3 of the log density's remainder, which the kernel therefore does not sum.  Lane l owns the coordinates
   // 4l..4l+3 (D <= 128, the domain of that kernel); δ_k is broadcast from its owner by a warp shuffle, row k of the
   // symmetric H0 is one coalesced 16-byte load per lane.
-  BN_HDN double linear_part(const T* q, T* g, const T (&rem)[2][4], const T* sg, int64_t bs) const {
+  BN_HD double linear_part(const T* q, T* g, const T (&rem)[2][4], const T* sg, int64_t bs) const {
     double part[LP::NACC];
     for (int i = 0; i < LP::NACC; ++i) part[i] = 0.0;
 #if defined(__CUDA_ARCH__)
@@ -709,7 +722,7 @@ BN_HD void prepare_chain(const EngineMem<T>& M, const RunParams<T>& rp, const Pr
 // advance one chain: consume a pending gradient, run to the next gradient request.
 // `max_iters` > 1 lets elementwise targets run many leapfrogs inside one launch.
 // Returns true if a gradient is pending for this chain on exit.
-template <class T, class LP>
+template <class T, class LP, int RM = 0>
 BN_HD bool advance_chain(const EngineMem<T>& M, const RunParams<T>& rp, int32_t c, LP lp, int max_iters) {
   ChainState<T>* g = &M.cs[c];
   if (g->phase == PH_IDLE) return false;
@@ -721,8 +734,8 @@ BN_HD bool advance_chain(const EngineMem<T>& M, const RunParams<T>& rp, int32_t 
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s);
     for (int i = 0; i < nwords; ++i) dst[i] = src[i];
   }
-  Backend<T, LP> b(M, c, lp, rp);
-  Machine<T, Backend<T, LP>> m(b, s, g, rp, c);
+  Backend<T, LP, RM> b(M, c, lp, rp);
+  Machine<T, Backend<T, LP, RM>> m(b, s, g, rp, c);
   bool pending = false;
   for (int it = 0; it < max_iters; ++it) {
     pending = m.step();

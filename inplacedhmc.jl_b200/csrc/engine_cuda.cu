@@ -35,26 +35,26 @@ template <class T> __global__ void __launch_bounds__(ADV_THREADS) k_prepare(Engi
   prepare_chain(M, rp, a, c, WarpLanes{(int)(threadIdx.x & 31)});
 }
 
-template <class T>
+template <class T, int RM>
 __global__ void __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS) k_advance(EngineMem<T> M, RunParams<T> rp, int iters, unsigned long long* pending) {
   const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (c >= M.C) return;
   const int lane = (int)(threadIdx.x & 31);
-  const bool p = advance_chain(M, rp, c, WarpLanes{lane}, iters);
+  const bool p = advance_chain<T, WarpLanes, RM>(M, rp, c, WarpLanes{lane}, iters);
   if (p && lane == 0 && !M.stage_q) atomicAdd(pending, 1ull);  // batched targets count through take_row()
 }
 
 // Same, for the pipelined run loop: no memset / copy / event around it.  The request counter alternates between
 // two device words (this launch counts into `cnt` and clears `cnt_next` for the following one); the last CTA to
 // finish publishes {sequence number, count} into a pinned, device-mapped host word the host polls.
-template <class T>
+template <class T, int RM>
 __global__ void __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS) k_advance_ring(EngineMem<T> M, RunParams<T> rp, int iters, unsigned long long* cnt,
                                                               unsigned long long* cnt_next, unsigned int* done,
                                                               volatile unsigned long long* host_slot, unsigned int seq) {
   const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (c < M.C) {
     const int lane = (int)(threadIdx.x & 31);
-    const bool p = advance_chain(M, rp, c, WarpLanes{lane}, iters);
+    const bool p = advance_chain<T, WarpLanes, RM>(M, rp, c, WarpLanes{lane}, iters);
     if (p && lane == 0 && !M.stage_q) atomicAdd(cnt, 1ull);
   }
   __syncthreads();
@@ -649,8 +649,15 @@ struct CudaExec {
     ring_expect[slot] = ring_seq;
     EngineMem<T> Ml = M;
     Ml.stage_count = d_scal + parity;
-    k_advance_ring<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(Ml, rp, iters, d_scal + parity, d_scal + (parity ^ 1), d_done,
-                                                                  d_ring + slot, ring_seq);
+    // the remainder mode of the tensor-core logistic path has its own instance (fp32 engines only): see Backend
+    bool rm = false;
+    if constexpr (std::is_same<T, float>::value) rm = M.lin_H != nullptr;
+    if (rm) {
+      if constexpr (std::is_same<T, float>::value)
+        k_advance_ring<T, 1><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(Ml, rp, iters, d_scal + parity, d_scal + (parity ^ 1), d_done, d_ring + slot, ring_seq);
+    } else {
+      k_advance_ring<T, 0><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(Ml, rp, iters, d_scal + parity, d_scal + (parity ^ 1), d_done, d_ring + slot, ring_seq);
+    }
     note(cudaGetLastError(), "k_advance");
   }
   bool count_ready(int slot) { return (unsigned int)(h_ring[slot] >> 32) == ring_expect[slot]; }
@@ -669,7 +676,13 @@ struct CudaExec {
   bool failed() const { return first_err != cudaSuccess; }
   template <class T> int64_t advance(const EngineMem<T>& M, const RunParams<T>& rp, int iters) {
     note(cudaMemsetAsync(d_scal, 0, sizeof(unsigned long long), stream), "memset");
-    k_advance<T><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, iters, d_scal);
+    bool rm = false;
+    if constexpr (std::is_same<T, float>::value) rm = M.lin_H != nullptr;
+    if (rm) {
+      if constexpr (std::is_same<T, float>::value) k_advance<T, 1><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, iters, d_scal);
+    } else {
+      k_advance<T, 0><<<warp_grid(M.C), ADV_THREADS, 0, stream>>>(M, rp, iters, d_scal);
+    }
     note(cudaGetLastError(), "k_advance");
     note(cudaMemcpyAsync(h_scal, d_scal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "pending d2h");
     note(cudaStreamSynchronize(stream), "k_advance sync");

@@ -321,7 +321,10 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
     for (int j = 0; j < 16; ++j) lacc[j] = make_float2(0.f, 0.f);
     const float4* recp = rec + (size_t)b0 * ROWS + r;
+    // the records are read from global memory two blocks ahead (one block ahead, the first use of a record was the largest
+    // single stall of the kernel: 14 % of the warp samples, ncu source page)
     float4 rc_next = nb > 0 ? __ldg(recp) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 rc_next2 = nb > 1 ? __ldg(recp + ROWS) : make_float4(0.f, 0.f, 0.f, 0.f);
     // this thread's 64 bytes of a row of R: chunk h / 2, 16-byte units 4 (h % 2) + qt (8 chains each), swizzled with the row
     const uint32_t r_row = smem_u32(sRb) + (uint32_t)(h >> 1) * CHUNK_BYTES + (uint32_t)r * 128u;
     const uint32_t r_sw = (uint32_t)(r & 7), u0 = (uint32_t)(h & 1) * 4u;
@@ -336,7 +339,8 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         const int j0 = FARP ? 2 * i : i;                               // hand-off of R: one per block, two (hi, lo) in far tiles
         const int rb = j0 % NRB;
         const float4 rc = rc_next;                                   // (A2, A3, A4, eta0) of this thread's row
-        if (i + 1 < nb) rc_next = __ldg(recp + (size_t)(i + 1) * ROWS);
+        rc_next = rc_next2;
+        if (i + 2 < nb) rc_next2 = __ldg(recp + (size_t)(i + 2) * ROWS);
         mbar_wait(&s_full[buf], (uint32_t)(i / NSB) & 1u);
         tc_fence_after();
         if (j0 >= NRB) mbar_wait(&r_empty[rb], (uint32_t)(j0 / NRB - 1) & 1u);
