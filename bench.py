@@ -543,10 +543,11 @@ def main():
         config["position_operand_terms"] = terms
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                            "frac": (ach / peak_tf) if ach else None,
-                           # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
-                           # (profiles/r1_ncu_full_details_k_logistic_tc_4096rows.csv: 292.4 MB + 14.5 MB; X is read once per
-                           # launch whatever the number of active rows: 256 MB algorithmic)
-                           "traffic": (None if remainder else 306.9e6) if (a.config == "c3" and N == 1_000_000 and D == 100) else None,
+                           # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full captures
+                           # (k_logistic_rm: profiles/r2_ncu_full_details_k_logistic_rm_4096rows.csv, 306.2 MB + 14.7 MB against 256 MB of
+                           # X + 16 MB of per-row records algorithmic; k_logistic_tc: profiles/r1_..._k_logistic_tc_4096rows.csv,
+                           # 292.4 MB + 14.5 MB); X is read once per launch whatever the number of active rows
+                           "traffic": (320.8e6 if remainder else 306.9e6) if (a.config == "c3" and N == 1_000_000 and D == 100) else None,
                            "traffic_unit": "bytes per launch (ncu, full 4096-row launch)",
                            "kernel": kern, "launches": int(grad_n), "avg_launch_ms": grad_ms / max(grad_n, 1),
                            "avg_rows_per_launch": rows / max(grad_n, 1), "peak_source": peak_src,
