@@ -126,8 +126,13 @@ int32_t bnuts_synth_logistic_rows(uint64_t data_seed, int64_t row_offset, int64_
  * three-term path stays in force.  beta_ref == NULL returns to the three-term path.  For 128 < D <= 256 the kernel always
  * works about a reference point (zero until one is set; there is no three-term form to fall back to), so any finite
  * point is accepted there: optimise, set the reference, optimise again from the more accurate operand, set it again.
- * For tall problems (N >= 3.3e5 D over the whole row group) the residual is carried about the reference as well
- * (one bf16 term of sigma(−eta) − sigma(−eta_ref) instead of two of sigma(−eta); BNUTS_TC_RREF=0/1 overrides). */
+ * For tall problems (N >= 3000 D over the whole row group) the engine switches to the REMAINDER MODE (csrc/logistic_rm.cu): the
+ * model is expanded about beta_ref row by row, the part that is linear / quadratic in beta − beta_ref (g0 − H0 (beta − beta_ref), D x D
+ * constants formed in Float64 at this call) is exact arithmetic per chain, and only the small Taylor remainder goes through the tensor
+ * cores; chains far from the reference fall back to closed forms inside the same kernel.  Gradient within 1e-6, log density within
+ * 1e-4 of Float64 near the reference.  BNUTS_TC_RMODE=0/1/2 overrides (0: two bf16 terms of sigma(−eta); 1: one term of
+ * sigma(−eta) − sigma(−eta_ref), the default for N >= 3.3e5 D where the remainder mode does not apply).
+ * The call re-evaluates (log density, gradient) of every chain at its current position: the stored values came from the previous arithmetic. */
 int32_t bnuts_logistic_set_reference(bnuts_engine* e, const double* beta_ref);
 
 /* ≙ initialize_warmup_state(q = …), src/warmup.jl:100-129: sets q and evaluates
