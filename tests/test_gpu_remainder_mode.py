@@ -117,3 +117,38 @@ def test_remainder_mode_is_taken_for_tall_problems_only(bn, cuda_lib, monkeypatc
         tight = np.abs(l - l0).max() < 2e-4
         assert tight == expect or (not expect and tight), (N, np.abs(l - l0).max())   # a small N may be accurate either way; a tall one must be
         e.close()
+
+
+@pytest.mark.parametrize("D,N", [(100, 40_000), (256, 60_000)])
+def test_remainder_mode_with_sharded_rows_group_of_one(bn, cuda_lib, monkeypatch, D, N):
+    """Rows "sharded" over a group of one (NCCL, world 1): the set-up constants go through the group sum, the folded
+    remainder through the per-leapfrog exchange, and the consumer adds the linear part behind it — against the ordinary
+    engine in the same mode and against numpy Float64 (the 2- and 8-GPU runs are scripts/gpu_c5_debug.py and bench.py --config c5)."""
+    monkeypatch.setenv("BNUTS_TC_RMODE", "2")
+    X, y, Xs, b, sd = _setup(N, D)
+    C = 96
+    rng = np.random.default_rng(9)
+    q = (b[None, :] + rng.normal(size=(C, D)) * sd[None, :]).astype(np.float32).astype(np.float64)
+    g0, l0 = _ref(Xs, q)
+    outs = []
+    for sharded in (False, True):
+        e = bn.Engine(C, D, dtype=bn.F32, lib=cuda_lib, gradient_path=bn.GRAD_TENSOR, seed=4, max_depth=6)
+        e.model_logistic(X, y, 1.0)
+        if sharded:
+            try:
+                e.set_nccl(bn.nccl_unique_id(cuda_lib), 1, 0)
+            except bn.BnutsError as ex:
+                pytest.skip(f"NCCL not loadable here: {ex}")
+        e.logistic_set_reference(b)
+        e.set_positions(q)
+        _, g, l = e.get_state()
+        e.set_stepsize(1e-3)
+        ch, st = e.sample(3)
+        outs.append((g, l, ch, st))
+        e.close()
+    (ga, la, cha, sta), (gb, lb, chb, stb) = outs
+    for g, l in ((ga, la), (gb, lb)):
+        assert np.max(np.linalg.norm(g - g0, axis=1) / np.linalg.norm(g0, axis=1)) < 2e-6
+        assert np.abs(l - l0).max() < 2e-3
+    assert np.max(np.linalg.norm(gb - ga, axis=1) / np.linalg.norm(ga, axis=1)) < 3e-7 and np.abs(lb - la).max() < 1e-4
+    assert (sta["steps"] == stb["steps"]).mean() > 0.9
