@@ -67,14 +67,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "r"(taddr)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
 // v[j] = (chains 2j, 2j+1) of this lane's row slot: returns, in lane l, the sum over the warp's 32 lanes of chain l
 // (recursive halving: 31 shuffles instead of 32 x 5)
 __device__ __forceinline__ float lane_sums(const float2* v2, int lane) {
@@ -127,6 +119,8 @@ template <int DT, int NC, int NT> struct RmPlan {
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
 };
 
+// NT = bf16 terms of β − β₀ in GEMM1.  Two: with one, the truncation of the operand is a coherent perturbation of δ over the rows and
+// the gradient error measured 5e-6 (median) … 1.4e-5 of |∇ℓ| at one posterior sd, for 3 % of time: only NT = 2 is instantiated.
 template <int DT, int NK, int NC, int NT>
 __global__ void __launch_bounds__(RM_THREADS, 1)
 k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBm,

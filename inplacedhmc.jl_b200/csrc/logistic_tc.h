@@ -38,7 +38,6 @@ struct LogisticTC {
   float* H0 = nullptr; double* H0_part = nullptr; double* rm_part = nullptr; double* ell0 = nullptr;
   double ell0_host = 0.0;
   float kappa2 = 0.f;
-  int32_t rm_terms = 2;
   // borrowed from the engine
   const uint16_t* bh = nullptr; const uint16_t* bm = nullptr; const uint16_t* bl = nullptr;  // [C][Dt]
   float* G = nullptr;        // [nsplit][rows][Dp]
