@@ -539,15 +539,20 @@ def test_cuda_edge_shapes_and_regimes_bitwise(bn, oracle_lib, cuda_lib, C, D, ma
     assert_bitwise(outs[0], outs[1])
 
 
-def test_tensor_path_posterior_moments_within_mcse(bn, cuda_lib):
+@pytest.mark.parametrize("N,D", [(50_000, 100), (40_000, 10)])
+def test_tensor_path_posterior_moments_within_mcse(bn, cuda_lib, monkeypatch, N, D):
     """north_star: "posterior means and variances must agree within Monte-Carlo standard error" — for the PRODUCTION path.
     c3-shaped problem (logistic regression, D = 100, N/D = 500), the reference's default pipeline (FindLocalOptimum, step
     size search, windowed warmup with per-chain diagonal metric, then draws; src/warmup.jl:361-372), run twice on the
     device: (A) the Float64 engine with the deterministic gradient — bit-identical to the oracle by the protocol tests —
     and (B) the fp32 tensor-core engine with the reference point set, as bench.py runs it.  Chains are independent, so
     the standard error of a posterior mean / variance estimate is the across-chain spread of the per-chain estimates
-    divided by sqrt(C); A and B use different seeds.  Also checked loosely against the Laplace approximation."""
-    N, D, C, draws = 50_000, 100, 256, 150
+    divided by sqrt(C); A and B use different seeds.  Also checked loosely against the Laplace approximation.
+    Two shapes: N / D = 500 keeps the exact-split kernel with the two-term operand (k_logistic_tc); N / D = 4000 is tall
+    enough for the engine to take the REMAINDER MODE by itself (k_logistic_rm, what config 3 runs on), with the posterior
+    inside its Taylor radius."""
+    monkeypatch.delenv("BNUTS_TC_RMODE", raising=False); monkeypatch.delenv("BNUTS_TC_RREF", raising=False)
+    C, draws = 256, 150
     X, y, beta = make_logistic(N, D)
     b, sd = _newton_mode(X, y, beta)
     res = []
