@@ -55,6 +55,10 @@ constexpr int ROWS = 128;            // data rows per block (GEMM1 M, GEMM2 K)
 #define BNUTS_RM_DEBUG 0      // timing experiments only (results are wrong): 1 skip the elementwise arithmetic, 2 skip GEMM1, 4 skip GEMM2, 8 skip the stores of R
 #endif
 constexpr int RMDBG = BNUTS_RM_DEBUG;
+#ifndef BNUTS_RM_ARRIVE_ALL
+#define BNUTS_RM_ARRIVE_ALL 0   // 1: every elementwise thread arrives on the hand-off barriers; 0: one elected lane per warp after __syncwarp
+#endif
+constexpr int ARR_ALL = BNUTS_RM_ARRIVE_ALL;
 #include "tc_ptx.h"
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -66,6 +70,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
                : "memory");
+}
+__device__ __forceinline__ void ew_arrive(uint64_t* bar, int lane) {
+  if (ARR_ALL) { mbar_arrive(bar); return; }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
 }
 // v[j] = (chains 2j, 2j+1) of this lane's row slot: returns, in lane l, the sum over the warp's 32 lanes of chain l
 // (recursive halving: 31 shuffles instead of 32 x 5)
@@ -158,10 +167,10 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (smem_u32(smem) & 1023u) asm volatile("trap;");
     mbar_init(bar_b, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], NEW); }
-    for (int i = 0; i < NRB; ++i) { mbar_init(&r_full[i], NEW); mbar_init(&r_empty[i], 1); }
+    for (int i = 0; i < NSB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], ARR_ALL ? 32 * NEW : NEW); }
+    for (int i = 0; i < NRB; ++i) { mbar_init(&r_full[i], ARR_ALL ? 32 * NEW : NEW); mbar_init(&r_empty[i], 1); }
     mbar_init(g_full, 1);
-    mbar_init(g_empty, NEW);
+    mbar_init(g_empty, ARR_ALL ? 32 * NEW : NEW);
     *far_flag = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -358,7 +367,7 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           for (int qt = 0; qt < 4; ++qt) {
             tmem_ld_wait();
             if (qt + 1 < 4) tmem_ld8(ts + (uint32_t)(qt + 1) * 8u, v[(qt + 1) & 1]);
-            else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&s_empty[buf]); }   // S is in registers: GEMM1 may overwrite the buffer
+            else { tc_fence_before(); ew_arrive(&s_empty[buf], lane); }   // S is in registers: GEMM1 may overwrite the buffer
                                                                                                    // (one arrival per warp: 512 per-thread arrivals on one word serialise)
             const uint32_t* vv = v[qt & 1];
             uint32_t pk[4];
@@ -413,14 +422,12 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           }
         } else {
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[buf]);
+          ew_arrive(&s_empty[buf], lane);
 #pragma unroll
           for (int u = 0; u < 4; ++u) sts128(rbase + (((u0 + (uint32_t)u) ^ r_sw) << 4), 0u, 0u, 0u, 0u);
         }
         fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&r_full[rb]);
+        ew_arrive(&r_full[rb], lane);
         if constexpr (FARP) {
           // second hand-off of the block: the low halves; then this block's μ folded into Float64 per chain
           const int j1 = j0 + 1, rb1 = j1 % NRB;
@@ -432,8 +439,7 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             else sts128(rbase1 + (((u0 + (uint32_t)u) ^ r_sw) << 4), 0u, 0u, 0u, 0u);
           }
           fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&r_full[rb1]);
+          ew_arrive(&r_full[rb1], lane);
           dacc += (double)lane_sums(lacc, lane);
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) lacc[jj] = make_float2(0.f, 0.f);
@@ -467,8 +473,7 @@ k_logistic_rm(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             }
           }
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(g_empty);
+          ew_arrive(g_empty, lane);
         }
       }
       if constexpr (FARP) lsum_out = dacc; else lsum_out = (double)lane_sums(lacc, lane);
