@@ -152,3 +152,20 @@ def test_remainder_mode_with_sharded_rows_group_of_one(bn, cuda_lib, monkeypatch
         assert np.abs(l - l0).max() < 2e-3
     assert np.max(np.linalg.norm(gb - ga, axis=1) / np.linalg.norm(ga, axis=1)) < 3e-7 and np.abs(lb - la).max() < 1e-4
     assert (sta["steps"] == stb["steps"]).mean() > 0.9
+
+
+@pytest.mark.parametrize("D", [61, 129, 200])
+def test_remainder_mode_other_widths(bn, cuda_lib, monkeypatch, D):
+    """Tile widths the headline shapes do not reach: D = 61 (one 64-column chunk), D = 129 and 200 (three chunks: the second
+    128-feature half of the GEMM2 accumulator is only partly backed by data)."""
+    monkeypatch.setenv("BNUTS_TC_RMODE", "2")
+    X, y, Xs, b, sd = _setup(30_000, D)
+    C = 70
+    q = (b[None, :] + np.random.default_rng(11).normal(size=(C, D)) * sd[None, :] * 0.3).astype(np.float32).astype(np.float64)
+    g0, l0 = _ref(Xs, q)
+    e = bn.Engine(C, D, dtype=bn.F32, lib=cuda_lib, gradient_path=bn.GRAD_TENSOR)
+    e.model_logistic(X, y, 1.0); e.logistic_set_reference(b); e.set_positions(q)
+    _, g, l = e.get_state()
+    err = np.linalg.norm(g - g0, axis=1) / np.linalg.norm(g0, axis=1)
+    assert err.max() < 3e-6 and np.abs(l - l0).max() < 2e-3, (D, err.max(), np.abs(l - l0).max())
+    e.close()
