@@ -13,9 +13,9 @@
 // The D x D linear part is EXACT fp32/Float64 arithmetic done by the consumer (backend.h model_grad); only the remainder
 // goes through the tensor cores.  In the posterior bulk |δ| ≈ 0.02 and |X̃ᵀρ| is < 1 % of the gradient, so ρ needs three
 // digits, not seven: ONE bf16 term carries it (2⁻⁹ relative, random over the rows: ~1e-7 of |∇ℓ| at N = 1e6), the
-// elementwise stage is a handful of packed FMAs per (row, chain) — no exp, no reciprocal, no hi/lo split, no log — and the
-// kernel is bound by its MMAs instead of by MUFU / issue slots (ablations of k_logistic_tc, profiles/r2_k_logistic_tc_ablation.txt:
-// 2.4 ms of its 2.8 ms remain with both GEMMs removed).
+// elementwise stage is six packed FMAs and one bf16 pack per pair of chains — no exp, no reciprocal, no hi/lo split, no log
+// (ablations of round 1's k_logistic_tc, profiles/r2_k_logistic_tc_ablation.txt: 2.4 ms of its 2.8 ms remain with both GEMMs
+// removed: the sigmoid, not the tensor pipe, set its pace).
 //
 // Layout: DATA ROWS are the MMA M dimension (TMEM lane = row), chains the N dimension:
 //     GEMM1  S[128 rows x NC chains]   = X̃blk[128 x K] · ΔBᵀ[K x NC]      (A, B from smem, K-major; ΔB = β − β₀ in two bf16 terms)
@@ -26,9 +26,11 @@
 // MMA cost follows the number of chains in the tile (NC = 64 for launches of <= 64 chains: HBM-bound, not tile-bound), and
 // the per-chain log-density sum is a per-thread register accumulation reduced once at the end.
 //
-// Chains far from the reference (‖β − β₀‖² > κ², measured by the kernel itself from the staged operand) take an exact
-// path per 32-chain group, warp-uniformly: ρ = σ(−η̃0 − δ) − r0 + wδ and λ from the closed forms, still one bf16 term
-// (its rounding is relative to ρ and averages over N rows: ≤ 1e-5 of the then large gradient).
+// Chains far from the reference (‖β − β₀‖² > κ², measured by the kernel itself from the staged operand tile): a tile that
+// holds one switches, for the whole launch, to a loop whose flagged chains take the closed forms ρ = σ(−η̃0 − δ) − r0 + wδ and
+// λ from log σ, and which hands R to GEMM2 in TWO bf16 halves per block (hi, lo: the remainder is no longer small there); the
+// log-density remainder is folded into Float64 per chain every block.  Correct everywhere (60 posterior sd: 7e-6 of |∇ℓ|),
+// fast near the reference.
 //
 // Warp roles (608 threads): warps 0-15 elementwise / epilogue: TMEM lane quarter q = warp % 4 (hardware rule), chain group
 // warp / 4 (32 chains each) — four warps per scheduler: packed f32x2 arithmetic issues every 2.0 clk with four warps per
