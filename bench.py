@@ -510,6 +510,13 @@ def main():
               "mean_tree_depth": float(stats["depth"].mean()), "mean_leapfrogs_per_transition": float(stats["steps"].mean()),
               "lockstep_steps_timed": lock,
               "active_row_fraction": float(leap_local / max(1, lock * C)) if a.config != "c4" else None}
+    if a.config == "c3":
+        # measured (profiles/r2_tail_probe_summary.json): a chain's mean tree length is persistent (NUTS resonance
+        # of a near-isotropic posterior), so the lockstep count of a call is the sequential depth of its slowest chain whatever the
+        # scheduling; one call over all transitions would give 0.225 (0.108 with the reference's own warmup windows, --full-warmup,
+        # which leave a MORE ragged workload: 1.10 M leapfrog steps/s in profiles/r2_bench_c3_1gpu_full_warmup.json)
+        config["active_row_fraction_bound"] = "persistent per-chain tree lengths: <= 0.23 for this workload under any scheduling (DESIGN.md section 5)"
+        config["warmup_windows"] = "reference default 75|25,50,100,200,400|50 (--full-warmup)" if a.full_warmup else "shortened 40|25,50,100|40 (the reference's default windows: --full-warmup)"
     out = {
         "metric": METRICS[a.config], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
