@@ -206,9 +206,10 @@ def _oracle_trace(lib, e, enable):
     return out
 
 
-@pytest.mark.parametrize("N,D,C,T,depth,eps,use_ref,min_clear", [(2000, 50, 128, 10, 6, 0.02, False, 0.6),
-                                                                 (100_000, 100, 64, 5, 5, 0.004, True, 0.3)])
-def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib, N, D, C, T, depth, eps, use_ref, min_clear):
+@pytest.mark.parametrize("N,D,C,T,depth,eps,use_ref,min_clear,rmode", [(2000, 50, 128, 10, 6, 0.02, False, 0.6, None),
+                                                                       (100_000, 100, 64, 5, 5, 0.004, True, 0.3, "0"),
+                                                                       (100_000, 100, 64, 5, 5, 0.004, True, 0.3, "2")])
+def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib, monkeypatch, N, D, C, T, depth, eps, use_ref, min_clear, rmode):
     """Both sides restart every transition from the same fp32-representable state with the same injected directions,
     momenta AND merge exponentials (all three random streams of src/NUTS.jl:251-258, :32-34).  Every chain-transition
     whose depth / termination / steps / selected index differ must contain a decision within the measured error of its
@@ -217,6 +218,13 @@ def test_tensor_tree_decisions_teacher_forced(bn, oracle_lib, cuda_lib, N, D, C,
     energies are ~6e4 with an ulp of 4e-3, so more selections sit within the measured error (1.5e-2) of their threshold
     and the provably-identical class is smaller (measured on B200: 140 of 320, against 1033 of 1280 in the first case;
     2 and 3 mismatches, each with a decision within 1 % / 7 % of its bound)."""
+    # rmode: the mode the reference point puts the tensor engine in ("0": two bf16 terms of the residual, k_logistic_tc; "2": the
+    # remainder mode, k_logistic_rm — what config 3 runs on; at this N / D it is forced, the engine takes it from N >= 3000 D)
+    monkeypatch.delenv("BNUTS_TC_RREF", raising=False)
+    if rmode is None:
+        monkeypatch.delenv("BNUTS_TC_RMODE", raising=False)
+    else:
+        monkeypatch.setenv("BNUTS_TC_RMODE", rmode)
     X, y, beta = make_logistic(N, D)
     b, sd = _newton_mode(X, y, beta)
     rng = np.random.default_rng(3)
