@@ -274,7 +274,21 @@ def setup_engine(a, bn, rank, world, local):
     t_w = time.perf_counter()
     if cfg in ("c3", "c5"):
         D = a.dim
-        if cfg == "c3":
+        if cfg == "c3" and a.sharding == "rows" and world > 1:
+            # OPTION (not BASELINE config 3's layout, which shards chains): config 5's layout on config 3's problem — every GPU holds
+            # all chains and 1/world of the rows (30 MB at 8 GPUs: L2-resident), one NCCL exchange per leapfrog
+            C = a.chains
+            bits, y, beta = synth(a.rows, D)
+            lo, hi = a.rows * rank // world, a.rows * (rank + 1) // world
+            e = bn.Engine(C, D, dtype=bn.F32, seed=20261018, device=local, gradient_path=bn.GRAD_TENSOR)
+            e.model_logistic(bits[lo:hi], y[lo:hi], 1.0)
+            info["cpu_inputs"] = (bits, y)
+            info["rows_this_rank"] = hi - lo
+            import torch.distributed as dist
+            ids = [bn.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            e.set_nccl(ids[0], world, rank)
+        elif cfg == "c3":
             C = a.chains // world if a.scaling == "strong" else a.chains   # chains shard across GPUs, no communication
             bits, y, beta = synth(a.rows, D)
             e = bn.Engine(C, D, dtype=bn.F32, seed=20261018, chain_offset=rank * C, device=local, gradient_path=bn.GRAD_TENSOR)
@@ -370,6 +384,8 @@ def main():
     ap.add_argument("--no-vectorised", action="store_true", help="skip the non-parity vectorised CPU leg")
     ap.add_argument("--no-fp64", action="store_true", help="c3: skip the Float64-engine leg (reference precision)")
     ap.add_argument("--no-reference", action="store_true", help="keep the exact three-term position operand")
+    ap.add_argument("--sharding", default="chains", choices=["chains", "rows"],
+                    help="c3 on several GPUs: chains (BASELINE config 3, default) or rows with a per-leapfrog NCCL exchange (an option: every GPU advances all chains)")
     ap.add_argument("--full-warmup", action="store_true", help="c3: the windows of default_warmup_stages (75|25,50,100,200,400|50) instead of the shortened 40|25,50,100|40")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong (BASELINE config 3: --chains in total, sharded over the GPUs) or weak (--chains per GPU)")
@@ -412,7 +428,7 @@ def main():
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t[0])
 
-    replicated = a.config == "c5"          # every rank runs the same chains: count them once
+    replicated = a.config == "c5" or (a.config == "c3" and a.sharding == "rows" and world > 1)   # every rank runs the same chains: count them once
     e, C, info = setup_engine(a, bn, rank, world, local)
     D, T = a.dim, a.transitions
     for _ in range(a.warmup):
@@ -468,7 +484,7 @@ def main():
         # (estimated on the first 512 chains of the rank and scaled to all of them: chains are i.i.d. replicas)
         nsub = min(C, 512)
         ess_d = (np.array([bn.diagnostics.ess(kept[:nsub, :, d]) for d in range(D)]) * (C / nsub)) if kept.shape[1] >= 4 else np.zeros(D)
-        if dist is not None:
+        if dist is not None and not replicated:
             tt = torch.tensor(ess_d, dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.SUM)
             ess_d = tt.cpu().numpy()
         min_ess = float(ess_d.min())
@@ -503,7 +519,7 @@ def main():
     rows = c1["gradient_rows"] - c0["gradient_rows"]   # active chains summed over the gradient launches
     chains_total = C if replicated else C * world
     config = {"workload": workload_name(a, chains_total), "chains_per_gpu": C,
-              "parallelism": ("rows sharded over %d GPUs, chains replicated, per-leapfrog exchange (%s)" % (world, a.exchange)) if replicated
+              "parallelism": ("rows sharded over %d GPUs, chains replicated, per-leapfrog exchange (%s)" % (world, a.exchange if a.config == "c5" else "nccl")) if replicated
               else "chains sharded, no collective",
               "init": info["init"] + ", %.1f s" % info["warmup_s"],
               "step": "%d NUTS transitions of every chain (async within the call)" % T,
@@ -526,7 +542,7 @@ def main():
     }
     if a.config in ("c3", "c5"):
         N = a.rows
-        N_gpu = a.rows if a.config == "c3" else info["rows_this_rank"]
+        N_gpu = info.get("rows_this_rank", a.rows)
         peak_tf = peaks.get("bf16_tflops_sustained")
         peak_src = "measured sustained (MEASURED_PEAKS.json)" if peak_tf else "fallback 1400 (B200_PROFILING.md)"
         peak_tf = peak_tf or 1400.0
