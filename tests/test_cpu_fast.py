@@ -58,3 +58,20 @@ def test_reference_arm_ignores_inherited_omp_num_threads():
             "print(lib.cpufast_max_threads(), bench.host_cores())" % ROOT)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split()
     assert out[0] == out[1]
+
+
+def test_bench_flags_named_in_the_docs_exist():
+    """DESIGN.md / profiles/README.md quote bench.py command lines: every flag they name is one the parser knows."""
+    import re
+    import subprocess
+    import sys
+    help_text = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, check=True).stdout
+    known = set(re.findall(r"--[a-z][a-z0-9-]+", help_text))
+    named = set()
+    for doc in ("DESIGN.md", "profiles/README.md", "README.md", "BASELINE.md"):
+        with open(os.path.join(ROOT, doc)) as f:
+            for line in f:
+                for cmd in re.findall(r"bench\.py((?: --?[A-Za-z0-9|\\=-]+(?: [A-Za-z0-9_.]+)?)+)", line):
+                    named |= set(re.findall(r"--[a-z][a-z0-9-]+", cmd))
+    assert named, "no bench.py command line found in the docs"
+    assert named <= known, sorted(named - known)
